@@ -1,0 +1,130 @@
+/*
+ * depthpro_b200.h — C-ABI of the B200-native Depth Pro inference engine.
+ *
+ * The reference (tdj28/ml-depth-pro-video) has no FFI layer: its hot path is reached only
+ * through Python (`depth_pro.create_model_and_transforms`, `DepthPro.infer`, `depth_to_3d`).
+ * This header is the boundary a binding for that path targets; the drop-in Python package
+ * `ml-depth-pro-video_b200/depth_pro` calls it through ctypes.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - plain C types only; pointers are device pointers unless the name says `host`;
+ *   - every function returns 0 on success, non-zero on error; `dp_last_error()` returns the
+ *     message of the calling thread's last failure (Python shim raises RuntimeError);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no hidden syncs
+ *     except in create / finalize / destroy and the `*_host` helpers;
+ *   - one engine per GPU; a handle is not thread-safe; the engine owns weights + workspace,
+ *     the caller owns inputs and outputs;
+ *   - there is no CPU fallback: on a machine without an sm_100 device `dp_engine_create`
+ *     fails.
+ */
+#ifndef DEPTHPRO_B200_H
+#define DEPTHPRO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dp_engine dp_engine;
+
+/* precision of the compute path */
+enum { DP_PREC_FP32 = 0, DP_PREC_BF16 = 1 };
+/* source image formats accepted by dp_preprocess / dp_infer */
+enum {
+  DP_SRC_F32_CHW = 0, /* float32 (B,3,H,W) already normalised to [-1,1]  (output of the
+                         reference `transform`, src/depth_pro/depth_pro.py:125-132) */
+  DP_SRC_U8_HWC = 1   /* uint8 (B,H,W,3) as returned by `load_rgb` (src/depth_pro/utils.py:47);
+                         ToTensor + Normalize(0.5,0.5) is fused into the resize kernel */
+};
+
+const char* dp_last_error(void);
+int dp_version(void);
+
+/* src/depth_pro/depth_pro.py:72-123  create_model_and_transforms (model construction). */
+int dp_engine_create(int device, int precision, int max_batch, dp_engine** out);
+int dp_engine_destroy(dp_engine* e);
+
+/* src/depth_pro/depth_pro.py:134-149  (load_state_dict): hand over ONE tensor of the
+ * reference-format state_dict (fp32, contiguous, reference key name and shape).  `on_device`
+ * != 0 means `data` is a device pointer on the engine's GPU, else host memory.  The engine
+ * repacks into its kernel-native layout (bf16 / fp32, K-major, conv taps outermost). */
+int dp_engine_set_weight(dp_engine* e, const char* name, const void* data,
+                         const int64_t* shape, int ndim, int on_device);
+/* Number of reference tensors still missing (0 = complete). */
+int dp_engine_missing_weights(dp_engine* e);
+/* Allocate workspace, build TMA descriptors.  Must follow the last set_weight. */
+int dp_engine_finalize(dp_engine* e);
+
+/* src/depth_pro/depth_pro.py:125-132 (transform) + :273-279 (F.interpolate to 1536^2,
+ * bilinear, align_corners=False).  img -> x_1536 float32 (B,3,1536,1536). */
+int dp_preprocess(dp_engine* e, const void* img, int B, int H, int W, int src_fmt,
+                  float* x_1536, void* stream);
+
+/* src/depth_pro/network/encoder.py:151-188, 253-263  (_create_pyramid + split + cat):
+ * x_1536 (B,3,1536,1536) -> patches float32 (35*B,3,384,384) in the REFERENCE order
+ * (25*B level-0 patches, then 9*B level-1, then B level-2; patch-major, batch-minor). */
+int dp_split(dp_engine* e, const float* x_1536, int B, float* patches, void* stream);
+
+/* src/depth_pro/network/encoder.py:190-231 (reshape_feature + merge): tokens float32
+ * (steps*steps*B, 577, C) in reference order -> merged float32 (B, C, S, S), S = 96 for
+ * steps 5 / padding 3, 48 for steps 3 / padding 6. */
+int dp_merge(dp_engine* e, const float* tokens, int B, int steps, int padding, int C,
+             float* merged, void* stream);
+
+/* src/depth_pro/depth_pro.py:218-241  DepthPro.forward: x (B,3,1536,1536) ->
+ * canonical inverse depth (B,1,1536,1536) and fov_deg (B). */
+int dp_forward(dp_engine* e, const float* x_1536, int B, float* canon_inv_depth,
+               float* fov_deg, void* stream);
+
+/* src/depth_pro/depth_pro.py:243-298  DepthPro.infer.  `f_px_host` (host, B floats) may be
+ * NULL -> focal length estimated from the FOV head.  depth_out float32 (B,H,W), f_px_out
+ * float32 (B) on device. */
+int dp_infer(dp_engine* e, const void* img, int B, int H, int W, int src_fmt,
+             const float* f_px_host, float* depth_out, float* f_px_out, void* stream);
+
+/* Same call with HOST buffers: H2D copy, dp_infer, D2H copy, stream sync.  This is the
+ * call generate_depth_maps.py:113-121 (transform -> infer -> .cpu().numpy()) amounts to. */
+int dp_infer_host(dp_engine* e, const void* img_host, int B, int H, int W, int src_fmt,
+                  const float* f_px_host, float* depth_out_host, float* f_px_out_host);
+
+/* img_to_normalized_pointcloud.py:819-856  depth_to_3d (+ colours, :1226).  Row-major stream
+ * compaction by valid = !isnan(d) && d > 0.  xyz float32 (N,3); rgb_out float32 (N,3) =
+ * rgb/255 if rgb != NULL; valid_mask uint8 (H,W) optional; n_valid int64 on device.
+ * `f_px_dev` is a device pointer to the focal length (so it chains after dp_infer). */
+int dp_unproject(dp_engine* e, const float* depth, const uint8_t* rgb, int H, int W,
+                 const float* f_px_dev, float* xyz, float* rgb_out, uint8_t* valid_mask,
+                 int64_t* n_valid, void* stream);
+
+/* generate_depth_maps.py:15-44, 128-143  colorize_depth / 16-bit export.  `lut` = 256x3 uint8
+ * colour table (device) -> rgb_out uint8 (H,W,3); if lut == NULL writes uint16 (H,W)
+ * normalised depth to `out` instead. */
+int dp_colorize(dp_engine* e, const float* depth, int H, int W, const uint8_t* lut,
+                void* out, void* stream);
+
+/* Parity taps: copy a named stage tensor of the LAST dp_forward as float32 in the
+ * reference's layout (NCHW / (n,577,C)).  Returns the element count in *numel. */
+int dp_tap(dp_engine* e, const char* stage, float* out, int64_t capacity, int64_t* numel,
+           void* stream);
+
+/* Unit-test / microbenchmark entry for the GEMM cores:  C[M,N] = A[M,K] * W[N,K]^T (+bias),
+ * fp32 row-major in and out; `backend` 0 = fp32 CUDA-core, 1 = bf16 tcgen05 (inputs are
+ * rounded to bf16 on the fly). */
+int dp_gemm_test(dp_engine* e, int backend, const float* A, const float* Wt, const float* bias,
+                 float* C, int M, int N, int K, int act, void* stream);
+/* Same for 3x3 / pad 1 / stride 1 convolution over NHWC fp32 (B,H,W,Cin) with OIHW weights. */
+int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float* w_oihw,
+                    const float* bias, float* y_nhwc, int B, int H, int W, int Cin, int Cout,
+                    void* stream);
+/* Attention core: qkv fp32 (n,577,3072) -> out fp32 (n,577,1024), 16 heads x 64. */
+int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, int n,
+                      void* stream);
+
+/* Kernel launches issued by this engine since creation (bench.py's `gpu_launches`). */
+int64_t dp_launch_count(dp_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEPTHPRO_B200_H */

@@ -1,0 +1,94 @@
+// Shared declarations of the Depth Pro B200 engine (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace dp {
+
+typedef __nv_bfloat16 bf16;
+
+struct Error : std::runtime_error {
+  explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define DP_CHECK(cond, msg)                                                        \
+  do {                                                                             \
+    if (!(cond)) throw ::dp::Error(std::string(msg) + " [" #cond "] at " __FILE__ ":" + \
+                                   std::to_string(__LINE__));                      \
+  } while (0)
+
+#define DP_CUDA(expr)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess)                                                         \
+      throw ::dp::Error(std::string("CUDA error: ") + cudaGetErrorString(_e) +     \
+                        " in " #expr " at " __FILE__ ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+// Launch counter (reported by dp_launch_count, used for bench.py's gpu_launches).
+extern int64_t g_launches;
+inline void count_launch(int n = 1) { g_launches += n; }
+
+#define DP_LAUNCH_CHECK()                \
+  do {                                   \
+    ::dp::count_launch();                \
+    DP_CUDA(cudaGetLastError());         \
+  } while (0)
+
+enum Prec { FP32 = 0, BF16 = 1 };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+// How the A operand rows of a GEMM are addressed.
+enum AMode {
+  A_ROWMAJOR = 0,  // A[m, k] at A + m*lda + k
+  A_CONV3X3 = 1,   // implicit 3x3 / pad 1 / stride 1 over NHWC (B,H,W,C); k = (ky*3+kx)*C + c
+};
+
+// Where a GEMM output element (m, n) goes.
+enum OutMode {
+  O_ROWMAJOR = 0,    // out[m*ldo + col_off + n]
+  O_CONVT2X2 = 1,    // ConvTranspose2d k2 s2: n = (dy*2+dx)*Cout + co, m = (b,y,x) on an HxW grid
+                     //   -> out[((b*2H + 2y+dy)*2W + 2x+dx)*ldo + col_off + co]
+  O_PATCH_EMBED = 2, // m = patch*576 + p -> row patch*577 + 1 + p, plus pos_embed[1+p][n]
+  O_DOT_RELU = 3,    // head.2 + ReLU + head.4 (1x1, 32->1) + ReLU: out[m] (fp32), N must be 32
+};
+
+// One GEMM / implicit-GEMM convolution launch, shared by the fp32 SIMT and bf16 tcgen05 cores.
+// Activations are `prec`-typed (float or bf16) unless stated; weights Wt are [N, K] K-major.
+struct GemmOp {
+  int M = 0, N = 0, K = 0;
+  // A
+  const void* A = nullptr;
+  int a_mode = A_ROWMAJOR;
+  int lda = 0;
+  int B = 1, H = 0, W = 0, C = 0;  // conv geometry (input grid); also the grid for O_CONVT2X2
+  // W
+  const void* Wt = nullptr;
+  // epilogue:  v = acc + bias[n]; v = act(v); v = v*gamma[n]; v += res; v += res2
+  const float* bias = nullptr;
+  int bias_mod = 0;             // if > 0, bias index is n % bias_mod (ConvT)
+  const float* gamma = nullptr;
+  int act = ACT_NONE;
+  const void* res = nullptr;    // residual, same (row, n) addressing as out in O_ROWMAJOR
+  int res_f32 = 0;              // residual dtype: 1 = float, 0 = activation dtype
+  const void* res2 = nullptr;   // second addend (activation dtype)
+  int ldres = 0;
+  // output
+  void* out = nullptr;
+  int out_f32 = 0;              // 1 = float output regardless of prec
+  void* out_relu = nullptr;     // optional second store of relu(v) (activation dtype)
+  int out_mode = O_ROWMAJOR;
+  int ldo = 0, col_off = 0;
+  int cout = 0;                 // O_CONVT2X2: Cout
+  const float* pos = nullptr;   // O_PATCH_EMBED: pos_embed (577, N) fp32
+  const float* dot_w = nullptr; // O_DOT_RELU: head.4 weight (32), dot_b: bias (1)
+  const float* dot_b = nullptr;
+};
+
+}  // namespace dp

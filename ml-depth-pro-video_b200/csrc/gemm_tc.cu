@@ -1,0 +1,459 @@
+// bf16 GEMM / implicit-GEMM 3x3 convolution on the 5th-generation tensor cores (sm_100a).
+//
+//   D[M,N] = A[M,K] * W[N,K]^T   (fp32 accumulate in TMEM), fused epilogue (common.cuh GemmOp).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer  : cp.async.bulk.tensor (128B swizzle) A and W k-blocks into a
+//                               4-stage shared-memory ring, completion on mbarriers.
+//                               A is either a 2D row-major matrix or — for 3x3 convolutions —
+//                               a 4D NHWC tensor map: the 128-row tile is an 8x16 pixel block
+//                               and every filter tap is one shifted box load whose
+//                               out-of-bounds pixels TMA zero-fills (= the padding).
+//   warp 1      MMA issuer    : one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block
+//                               into a double-buffered TMEM accumulator; tcgen05.commit releases
+//                               smem stages and publishes finished accumulators.
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue      : tcgen05.ld (thread = one output row, 32 columns per load),
+//                               bias / GELU / ReLU / LayerScale / residual / pixel-shuffle
+//                               scatter, vectorised global stores; overlaps the next tile's MMA.
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace dp {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 256;
+constexpr int TILE_W = 16, TILE_H = 8;  // conv: 128 rows = 8 x 16 output pixels
+
+struct TileGeom {
+  int m_tiles, n_tiles, k_blocks;
+  int tiles_x, tiles_y;  // conv only
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <typename T>
+__device__ __forceinline__ void load32(const T* p, float (&v)[32]);
+template <>
+__device__ __forceinline__ void load32<float>(const float* p, float (&v)[32]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = q[i];
+    v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+  }
+}
+template <>
+__device__ __forceinline__ void load32<bf16>(const bf16* p, float (&v)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t = q[i];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(h[j]);
+      v[8 * i + 2 * j] = f.x, v[8 * i + 2 * j + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void store32(float* p, const float (&v)[32]) {
+  float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void store32(bf16* p, const float (&v)[32], bool relu) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = v[8 * i + 2 * j], b = v[8 * i + 2 * j + 1];
+      if (relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
+      h[j] = __floats2bfloat162_rn(a, b);
+    }
+    q[i] = t;
+  }
+}
+
+// Epilogue for one output row `m` (linear row / NHWC pixel index) and 32 columns starting at n0.
+__device__ __forceinline__ void epilogue_chunk(const GemmOp& op, long long m, int n0, float (&v)[32]) {
+  float t[32];
+  if (op.bias) {
+    load32<float>(op.bias + (op.bias_mod ? n0 % op.bias_mod : n0), t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += t[j];
+  }
+  if (op.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (op.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (op.gamma) {
+    load32<float>(op.gamma + n0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= t[j];
+  }
+
+  long long off;  // element offset of (m, n0) in `out`
+  if (op.out_mode == O_ROWMAJOR) {
+    off = m * op.ldo + op.col_off + n0;
+  } else if (op.out_mode == O_CONVT2X2) {
+    const int q = n0 / op.cout, co = n0 - q * op.cout;
+    const int x = static_cast<int>(m % op.W);
+    const long long by = m / op.W;  // b*H + y
+    const int y = static_cast<int>(by % op.H);
+    const long long b = by / op.H;
+    const long long orow = (b * 2 * op.H + 2 * y + (q >> 1)) * (2LL * op.W) + 2 * x + (q & 1);
+    off = orow * op.ldo + op.col_off + co;
+  } else if (op.out_mode == O_PATCH_EMBED) {
+    const long long patch = m / 576;
+    const int p = static_cast<int>(m - patch * 576);
+    load32<float>(op.pos + (1 + p) * static_cast<long long>(op.N) + n0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += t[j];
+    off = (patch * 577 + 1 + p) * op.ldo + n0;
+  } else {  // O_DOT_RELU: (already bias + ReLU'd) 32-channel pixel -> 1 channel
+    load32<float>(op.dot_w, t);
+    float s = op.dot_b[0];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s = fmaf(v[j], t[j], s);
+    reinterpret_cast<float*>(op.out)[m] = fmaxf(s, 0.f);
+    return;
+  }
+
+  if (op.res) {
+    const long long roff = m * op.ldres + n0;
+    if (op.res_f32)
+      load32<float>(reinterpret_cast<const float*>(op.res) + roff, t);
+    else
+      load32<bf16>(reinterpret_cast<const bf16*>(op.res) + roff, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += t[j];
+  }
+  if (op.res2) {
+    load32<bf16>(reinterpret_cast<const bf16*>(op.res2) + m * op.ldres + n0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += t[j];
+  }
+  if (op.out) {
+    if (op.out_f32)
+      store32(reinterpret_cast<float*>(op.out) + off, v);
+    else
+      store32(reinterpret_cast<bf16*>(op.out) + off, v, false);
+  }
+  if (op.out_relu) store32(reinterpret_cast<bf16*>(op.out_relu) + off, v, true);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmOp op, const TileGeom g) {
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], EPI_THREADS);
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % g.n_tiles, mt = t / g.n_tiles;
+        int b = 0, y0 = 0, x0 = 0;
+        if (op.a_mode == A_CONV3X3) {
+          const int per_img = g.tiles_x * g.tiles_y;
+          b = mt / per_img;
+          const int r = mt - b * per_img;
+          y0 = (r / g.tiles_x) * TILE_H;
+          x0 = (r % g.tiles_x) * TILE_W;
+        }
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
+          if (op.a_mode == A_CONV3X3) {
+            const int k = kb * BK;
+            const int tap = k / op.C, c0 = k - tap * op.C;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            ptx::tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b);
+          } else {
+            ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, mt * BM);
+          }
+          ptx::tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, nt * BN);
+          if (++s == STAGES) s = 0, ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        ptx::mbar_wait(&tempty[acc], acc_ph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a0 = ptx::smem_u32(sA + s * A_BYTES);
+          const uint32_t b0 = ptx::smem_u32(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a0 + k * 32), ptx::umma_desc_sw128(b0 + k * 32),
+                           IDESC, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty[s]);
+          if (++s == STAGES) s = 0, ph ^= 1;
+        }
+        ptx::umma_commit(&tfull[acc]);
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int grp = (warp - EPI_WARP0) >> 2;  // column half
+    constexpr int COLS_PER_GRP = (BN >= 64) ? BN / 2 : BN;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const int nt = t % g.n_tiles, mt = t / g.n_tiles;
+      long long m;
+      bool valid;
+      if (op.a_mode == A_CONV3X3) {
+        const int per_img = g.tiles_x * g.tiles_y;
+        const int b = mt / per_img;
+        const int r = mt - b * per_img;
+        const int y = (r / g.tiles_x) * TILE_H + row / TILE_W;
+        const int x = (r % g.tiles_x) * TILE_W + row % TILE_W;
+        m = (static_cast<long long>(b) * op.H + y) * op.W + x;
+        valid = true;
+      } else {
+        m = static_cast<long long>(mt) * BM + row;
+        valid = m < op.M;
+      }
+      ptx::mbar_wait(&tfull[acc], acc_ph);
+      ptx::tc_fence_after();
+      if (BN >= 64 || grp == 0) {
+#pragma unroll 1
+        for (int c = 0; c < COLS_PER_GRP; c += 32) {
+          const int col = grp * COLS_PER_GRP + c;
+          uint32_t r[32];
+          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col, r);
+          ptx::tmem_ld_wait();
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            epilogue_chunk(op, m, nt * BN + col, v);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    DP_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t d0, d1, d2, d3, s1, s2, s3;
+  uint32_t b0, b1, b2, b3;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && s1 == o.s1 &&
+           s2 == o.s2 && s3 == o.s3 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && b3 == o.b3;
+  }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    for (uint64_t v : {k.d0, k.d1, k.d2, k.d3, k.s1, k.s2, k.s3, (uint64_t)k.b0, (uint64_t)k.b1, (uint64_t)k.b2})
+      h = h * 1000003u ^ v;
+    return h;
+  }
+};
+std::unordered_map<TmapKey, CUtensorMap, TmapHash>& tmap_cache() {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapHash> c;
+  return c;
+}
+
+const CUtensorMap& get_tmap(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box) {
+  TmapKey key{ptr, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, strides_bytes[0],
+              rank > 2 ? strides_bytes[1] : 0, rank > 3 ? strides_bytes[2] : 0, box[0], box[1],
+              rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0};
+  auto& cache = tmap_cache();
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap tm;
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) gd[i] = dims[i], bx[i] = box[i];
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  DP_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16-byte aligned");
+  CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return cache.emplace(key, tm).first->second;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev;
+    DP_CUDA(cudaGetDevice(&dev));
+    DP_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+template <int BN>
+void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB,
+            cudaStream_t stream) {
+  constexpr size_t SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
+  static bool configured = false;
+  if (!configured) {
+    DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    configured = true;
+  }
+  const int tiles = g.m_tiles * g.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, SMEM, stream>>>(tmA, tmB, op, g);
+  DP_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+void tmap_cache_clear() { tmap_cache().clear(); }
+
+void gemm_tc(const GemmOp& op, cudaStream_t stream) {
+  DP_CHECK(op.K % BK == 0, "gemm_tc: K must be a multiple of 64");
+  int bn = 0;
+  if (op.N % 256 == 0) bn = 256;
+  else if (op.N % 128 == 0) bn = 128;
+  else if (op.N == 32) bn = 32;
+  DP_CHECK(bn != 0, "gemm_tc: unsupported N");
+  if (op.out_mode == O_DOT_RELU) DP_CHECK(op.N == 32, "O_DOT_RELU needs N == 32");
+  if (op.out_mode == O_CONVT2X2) DP_CHECK(op.cout % 32 == 0 && op.N == 4 * op.cout, "bad ConvT shape");
+
+  TileGeom g{};
+  g.n_tiles = op.N / bn;
+  g.k_blocks = op.K / BK;
+  const CUtensorMap* tmA;
+  if (op.a_mode == A_CONV3X3) {
+    DP_CHECK(op.C % BK == 0 && op.K == 9 * op.C, "conv3x3: C must be a multiple of 64");
+    DP_CHECK(op.W % TILE_W == 0 && op.H % TILE_H == 0, "conv3x3: H, W must be multiples of 8, 16");
+    g.tiles_x = op.W / TILE_W;
+    g.tiles_y = op.H / TILE_H;
+    g.m_tiles = op.B * g.tiles_x * g.tiles_y;
+    const uint64_t dims[4] = {(uint64_t)op.C, (uint64_t)op.W, (uint64_t)op.H, (uint64_t)op.B};
+    const uint64_t str[3] = {(uint64_t)op.C * 2, (uint64_t)op.W * op.C * 2, (uint64_t)op.H * op.W * op.C * 2};
+    const uint32_t box[4] = {BK, TILE_W, TILE_H, 1};
+    tmA = &get_tmap(op.A, 4, dims, str, box);
+  } else {
+    g.m_tiles = (op.M + BM - 1) / BM;
+    const uint64_t dims[2] = {(uint64_t)op.K, (uint64_t)op.M};
+    const uint64_t str[1] = {(uint64_t)op.lda * 2};
+    const uint32_t box[2] = {BK, BM};
+    tmA = &get_tmap(op.A, 2, dims, str, box);
+  }
+  const uint64_t wd[2] = {(uint64_t)op.K, (uint64_t)op.N};
+  const uint64_t ws[1] = {(uint64_t)op.K * 2};
+  const uint32_t wb[2] = {BK, (uint32_t)bn};
+  const CUtensorMap& tmB = get_tmap(op.Wt, 2, wd, ws, wb);
+
+  if (bn == 256) launch<256>(op, g, *tmA, tmB, stream);
+  else if (bn == 128) launch<128>(op, g, *tmA, tmB, stream);
+  else launch<32>(op, g, *tmA, tmB, stream);
+}
+
+}  // namespace dp

@@ -1,0 +1,696 @@
+// HBM-bound kernels of the Depth Pro engine (see kernels.cuh).  Reference lines are cited per
+// kernel; paths are relative to the reference repo root.
+#include "kernels.cuh"
+
+namespace dp {
+
+namespace {
+
+constexpr int IMG = 1536;
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+inline int blocks_for(long long n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------
+// resize: src/depth_pro/depth_pro.py:125-132 (ToTensor, Normalize) + :273-279 (F.interpolate,
+// bilinear, align_corners=False, no antialias).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float src_px(const void* src, int fmt, int b, int c, int y, int x, int H, int W) {
+  if (fmt == 0) return reinterpret_cast<const float*>(src)[((static_cast<long long>(b) * 3 + c) * H + y) * W + x];
+  const uint8_t u = reinterpret_cast<const uint8_t*>(src)[((static_cast<long long>(b) * H + y) * W + x) * 3 + c];
+  const float t = __fdiv_rn(static_cast<float>(u), 255.f);  // ToTensor
+  return __fmul_rn(__fsub_rn(t, 0.5f), 2.f);                // Normalize(0.5, 0.5)
+}
+
+__global__ void resize_kernel(const void* __restrict__ src, int fmt, int B, int H, int W, float* __restrict__ x) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * 3 * IMG * IMG;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % IMG);
+  const int oy = static_cast<int>((idx / IMG) % IMG);
+  const int c = static_cast<int>((idx / (static_cast<long long>(IMG) * IMG)) % 3);
+  const int b = static_cast<int>(idx / (3LL * IMG * IMG));
+  if (H == IMG && W == IMG) {
+    x[idx] = src_px(src, fmt, b, c, oy, ox, H, W);
+    return;
+  }
+  const float sh = static_cast<float>(H) / IMG, sw = static_cast<float>(W) / IMG;
+  float fy = __fsub_rn(__fmul_rn(sh, oy + 0.5f), 0.5f);
+  float fx = __fsub_rn(__fmul_rn(sw, ox + 0.5f), 0.5f);
+  fy = fy < 0.f ? 0.f : fy;
+  fx = fx < 0.f ? 0.f : fx;
+  int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  y0 = y0 > H - 1 ? H - 1 : y0;
+  x0 = x0 > W - 1 ? W - 1 : x0;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+  const float ly1 = fminf(fmaxf(fy - y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - x0, 0.f), 1.f);
+  const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+  const float p00 = src_px(src, fmt, b, c, y0, x0, H, W), p01 = src_px(src, fmt, b, c, y0, x1, H, W);
+  const float p10 = src_px(src, fmt, b, c, y1, x0, H, W), p11 = src_px(src, fmt, b, c, y1, x1, H, W);
+  const float t0 = __fadd_rn(__fmul_rn(lx0, p00), __fmul_rn(lx1, p01));
+  const float t1 = __fadd_rn(__fmul_rn(lx0, p10), __fmul_rn(lx1, p11));
+  x[idx] = __fadd_rn(__fmul_rn(ly0, t0), __fmul_rn(ly1, t1));
+}
+
+// ------------------------------------------------------------------------------------------
+// pyramid + split + im2col: src/depth_pro/network/encoder.py:151-188, 253-263 and the timm
+// patch-embed conv (k16 s16) unrolled.  Level 1 / 2 are the closed forms of
+// F.interpolate(scale_factor=0.5 / 0.25, bilinear): source index 2d+0.5 / 4d+1.5, weights 0.5.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float box4(float a, float b, float c, float d) {
+  // 0.5*(0.5a + 0.5b) + 0.5*(0.5c + 0.5d): scalings by 0.5 are exact, two roundings as in ATen.
+  return __fadd_rn(__fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, a), __fmul_rn(0.5f, b))),
+                   __fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, c), __fmul_rn(0.5f, d))));
+}
+
+template <typename T>
+__global__ void split_im2col_kernel(const float* __restrict__ x, int B, T* __restrict__ A35, T* __restrict__ A1) {
+  // one thread = 8 consecutive kx of one (row, c, ky)
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * 35 * 576 * 96;
+  if (idx >= total) return;
+  const int col8 = static_cast<int>(idx % 96);
+  const long long row = idx / 96;
+  const int col = col8 * 8;
+  const int c = col >> 8, ky = (col >> 4) & 15, kx0 = col & 15;
+  const int tok = static_cast<int>(row % 576);
+  const int patch = static_cast<int>((row / 576) % 35);
+  const int b = static_cast<int>(row / (576 * 35));
+  const int py = (tok / 24) * 16 + ky, px = (tok % 24) * 16 + kx0;
+  const float* img = x + (static_cast<long long>(b) * 3 + c) * IMG * IMG;
+  float v[8];
+  if (patch < 25) {
+    const int Y = (patch / 5) * 288 + py, X = (patch % 5) * 288 + px;
+    const float* p = img + static_cast<long long>(Y) * IMG + X;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = p[i];
+  } else if (patch < 34) {
+    const int q = patch - 25;
+    const int Y = (q / 3) * 192 + py, X = (q % 3) * 192 + px;
+    const float* p0 = img + static_cast<long long>(2 * Y) * IMG + 2 * X;
+    const float* p1 = p0 + IMG;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = box4(p0[2 * i], p0[2 * i + 1], p1[2 * i], p1[2 * i + 1]);
+  } else {
+    const float* p0 = img + static_cast<long long>(4 * py + 1) * IMG + 4 * px + 1;
+    const float* p1 = p0 + IMG;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = box4(p0[4 * i], p0[4 * i + 1], p1[4 * i], p1[4 * i + 1]);
+  }
+  T* dst = A35 + row * 768 + col;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[i] = from_f<T>(v[i]);
+  if (A1 != nullptr && patch == 34) {
+    T* d1 = A1 + (static_cast<long long>(b) * 576 + tok) * 768 + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d1[i] = from_f<T>(v[i]);
+  }
+}
+
+__global__ void im2col_to_ref_kernel(const float* __restrict__ A35, int B, float* __restrict__ patches) {
+  // patches index: (n, c, py, px), n in the reference order (encoder.py:186-188, 260-263)
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * 35 * 3 * 384 * 384;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % 384), py = static_cast<int>((idx / 384) % 384);
+  const int c = static_cast<int>((idx / (384 * 384)) % 3);
+  const int n = static_cast<int>(idx / (3LL * 384 * 384));
+  int patch, b;
+  if (n < 25 * B) patch = n / B, b = n % B;
+  else if (n < 34 * B) patch = 25 + (n - 25 * B) / B, b = (n - 25 * B) % B;
+  else patch = 34, b = n - 34 * B;
+  const long long row = (static_cast<long long>(b) * 35 + patch) * 576 + (py / 16) * 24 + px / 16;
+  patches[idx] = A35[row * 768 + c * 256 + (py % 16) * 16 + (px % 16)];
+}
+
+// ------------------------------------------------------------------------------------------
+// tokens
+// ------------------------------------------------------------------------------------------
+__global__ void cls_rows_kernel(float* resid, const float* cls, const float* pos, int nseq) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nseq * 1024) return;
+  const int n = idx & 1023, r = idx >> 10;
+  resid[static_cast<long long>(r) * 577 * 1024 + n] = cls[n] + pos[n];
+}
+
+// dest row -> source row of the token matrix (encoder.py:190-231, merge + reshape_feature)
+__device__ __forceinline__ long long map_row(const RowMap& m, long long d) {
+  if (m.mode == 0) return d;
+  const int S = m.S;
+  const int x = static_cast<int>(d % S), y = static_cast<int>((d / S) % S);
+  const long long b = d / (static_cast<long long>(S) * S);
+  const int first = 24 - m.pad, stride = 24 - 2 * m.pad;
+  int j = 0, i = 0;
+  if (m.steps > 1) {
+    j = y < first ? 0 : min(m.steps - 1, 1 + (y - first) / stride);
+    i = x < first ? 0 : min(m.steps - 1, 1 + (x - first) / stride);
+  }
+  const int ty = y - j * stride, tx = x - i * stride;
+  const int patch = m.patch_base + j * m.steps + i;
+  return (b * m.sb + static_cast<long long>(patch) * m.sp) * 577 + 1 + ty * 24 + tx;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, T* __restrict__ out,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        long long n_out, RowMap map, int ln) {
+  const long long d = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (d >= n_out) return;
+  const int lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(in + map_row(map, d) * 1024);
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = src[lane + 32 * i];
+  if (ln) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / 1024.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i].x -= mean, v[i].y -= mean, v[i].z -= mean, v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.f / sqrtf(q * (1.f / 1024.f) + 1e-6f);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 ww = w4[lane + 32 * i], bb = b4[lane + 32 * i];
+      v[i].x = v[i].x * rstd * ww.x + bb.x;
+      v[i].y = v[i].y * rstd * ww.y + bb.y;
+      v[i].z = v[i].z * rstd * ww.z + bb.z;
+      v[i].w = v[i].w * rstd * ww.w + bb.w;
+    }
+  }
+  T* dst = out + d * 1024;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = (lane + 32 * i) * 4;
+    if (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + e) = v[i];
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x, v[i].y), hi = __floats2bfloat162_rn(v[i].z, v[i].w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(dst) + e) = pk;
+    }
+  }
+}
+
+__global__ void merge_f32_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int C,
+                                 RowMap map) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C);
+  const long long d = idx / C;
+  out[idx] = in[map_row(map, d) * C + c];
+}
+
+// ------------------------------------------------------------------------------------------
+// FOV head convolutions: src/depth_pro/network/fov.py:29-46, 78-82
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void conv_direct_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                   T* __restrict__ y, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                                   int Ho, int Wo, int relu, const T* __restrict__ add_tokens) {
+  extern __shared__ float patch[];  // k*k*Cin
+  const int o = blockIdx.x;         // output pixel (b, oy, ox)
+  const int ox = o % Wo, oy = (o / Wo) % Ho, b = o / (Wo * Ho);
+  const int nel = k * k * Cin;
+  for (int e = threadIdx.x; e < nel; e += blockDim.x) {
+    const int ci = e % Cin, t = e / Cin;
+    const int yy = oy * stride - pad + t / k, xx = ox * stride - pad + t % k;
+    patch[e] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                   ? to_f(x[((static_cast<long long>(b) * H + yy) * W + xx) * Cin + ci])
+                   : 0.f;
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float acc = 0.f;
+    for (int e = 0; e < nel; ++e) acc = fmaf(patch[e], w[static_cast<long long>(e) * Cout + co], acc);
+    acc += bias[co];
+    if (relu) acc = fmaxf(acc, 0.f);
+    if (add_tokens) acc += to_f(add_tokens[(static_cast<long long>(b) * 577 + 1 + oy * Wo + ox) * Cout + co]);
+    y[static_cast<long long>(o) * Cout + co] = from_f<T>(acc);
+  }
+}
+
+template <typename T>
+__global__ void fov_final_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                 float* __restrict__ fov) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < 1152; e += blockDim.x) acc = fmaf(to_f(x[b * 1152 + e]), w[e], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) s += red[i];
+    fov[b] = s + bias[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// metric depth epilogue: src/depth_pro/depth_pro.py:282-298
+// ------------------------------------------------------------------------------------------
+__global__ void fpx_kernel(const float* fov_deg, const float* f_px_in, int W, float* f_px, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (f_px_in) {
+    f_px[b] = f_px_in[b];
+  } else {
+    const float rad = fov_deg[b] * static_cast<float>(3.14159265358979323846 / 180.0);
+    f_px[b] = (0.5f * W) / tanf(0.5f * rad);
+  }
+}
+
+__global__ void depth_epilogue_kernel(const float* __restrict__ canon, const float* __restrict__ f_px, int B, int H,
+                                      int W, float* __restrict__ depth) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W;
+  if (idx >= total) return;
+  const int ox = static_cast<int>(idx % W), oy = static_cast<int>((idx / W) % H);
+  const int b = static_cast<int>(idx / (static_cast<long long>(H) * W));
+  const float scale = static_cast<float>(W) / f_px[b];
+  const float* src = canon + static_cast<long long>(b) * IMG * IMG;
+  float inv;
+  if (H == IMG && W == IMG) {
+    inv = src[static_cast<long long>(oy) * IMG + ox] * scale;
+  } else {
+    const float sh = static_cast<float>(IMG) / H, sw = static_cast<float>(IMG) / W;
+    float fy = __fsub_rn(__fmul_rn(sh, oy + 0.5f), 0.5f);
+    float fx = __fsub_rn(__fmul_rn(sw, ox + 0.5f), 0.5f);
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    int y0 = min(static_cast<int>(fy), IMG - 1), x0 = min(static_cast<int>(fx), IMG - 1);
+    const int y1 = y0 + (y0 < IMG - 1 ? 1 : 0), x1 = x0 + (x0 < IMG - 1 ? 1 : 0);
+    const float ly1 = fminf(fmaxf(fy - y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - x0, 0.f), 1.f);
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float p00 = src[static_cast<long long>(y0) * IMG + x0] * scale, p01 = src[static_cast<long long>(y0) * IMG + x1] * scale;
+    const float p10 = src[static_cast<long long>(y1) * IMG + x0] * scale, p11 = src[static_cast<long long>(y1) * IMG + x1] * scale;
+    const float t0 = __fadd_rn(__fmul_rn(lx0, p00), __fmul_rn(lx1, p01));
+    const float t1 = __fadd_rn(__fmul_rn(lx0, p10), __fmul_rn(lx1, p11));
+    inv = __fadd_rn(__fmul_rn(ly0, t0), __fmul_rn(ly1, t1));
+  }
+  depth[idx] = 1.0f / fminf(fmaxf(inv, 1e-4f), 1e4f);
+}
+
+// ------------------------------------------------------------------------------------------
+// depth -> 3D unprojection with row-major stream compaction:
+// img_to_normalized_pointcloud.py:819-856 (+ colours :1226)
+// ------------------------------------------------------------------------------------------
+constexpr int UNP_T = 256, UNP_PER = 4, UNP_BLK = UNP_T * UNP_PER;
+
+__device__ __forceinline__ bool depth_valid(float d) { return !isnan(d) && d > 0.f; }
+
+__global__ void unproject_count_kernel(const float* __restrict__ depth, long long n, int* __restrict__ counts) {
+  const long long base = static_cast<long long>(blockIdx.x) * UNP_BLK;
+  int c = 0;
+#pragma unroll
+  for (int it = 0; it < UNP_PER; ++it) {
+    const long long p = base + it * UNP_T + threadIdx.x;
+    c += (p < n && depth_valid(depth[p])) ? 1 : 0;
+  }
+  __shared__ int red[UNP_T / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int i = 0; i < UNP_T / 32; ++i) s += red[i];
+    counts[blockIdx.x] = s;
+  }
+}
+
+// exclusive scan of counts (in place -> offsets are written to `offsets`), single block
+__global__ void unproject_scan_kernel(const int* __restrict__ counts, long long* __restrict__ offsets, int nblk,
+                                      int64_t* __restrict__ n_valid) {
+  __shared__ long long warp_tot[32];
+  __shared__ long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += 1024) {
+    const int i = base + threadIdx.x;
+    long long v = i < nblk ? counts[i] : 0;
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      long long w = warp_tot[threadIdx.x];
+      long long wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (threadIdx.x >= o) wi += t;
+      }
+      warp_tot[threadIdx.x] = wi - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    const long long excl = carry + warp_tot[threadIdx.x >> 5] + incl - v;
+    if (i < nblk) offsets[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_valid = carry;
+}
+
+__global__ void unproject_write_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int H, int W,
+                                       const float* __restrict__ f_px, const long long* __restrict__ offsets,
+                                       float* __restrict__ xyz, float* __restrict__ rgb_out,
+                                       uint8_t* __restrict__ valid_mask) {
+  __shared__ int warp_cnt[UNP_T / 32];
+  __shared__ int running;
+  const long long n = static_cast<long long>(H) * W;
+  const long long base = static_cast<long long>(blockIdx.x) * UNP_BLK;
+  const float f = f_px[0];
+  const float cx = 0.5f * W, cy = 0.5f * H;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  const long long blk_off = offsets[blockIdx.x];
+  for (int it = 0; it < UNP_PER; ++it) {
+    const long long p = base + it * UNP_T + threadIdx.x;
+    float d = 0.f;
+    bool ok = false;
+    if (p < n) {
+      d = depth[p];
+      ok = depth_valid(d);
+      if (valid_mask) valid_mask[p] = ok ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int before = running;
+    for (int i = 0; i < wid; ++i) before += warp_cnt[i];
+    if (ok) {
+      const long long dst = blk_off + before + __popc(bal & ((1u << lane) - 1));
+      const int u = static_cast<int>(p % W), v = static_cast<int>(p / W);
+      // x = -(u - W/2) * z / f ; y = -(v - H/2) * z / f ; z = d
+      xyz[dst * 3 + 0] = __fdiv_rn(__fmul_rn(-(static_cast<float>(u) - cx), d), f);
+      xyz[dst * 3 + 1] = __fdiv_rn(__fmul_rn(-(static_cast<float>(v) - cy), d), f);
+      xyz[dst * 3 + 2] = d;
+      if (rgb && rgb_out) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb_out[dst * 3 + c] = __fdiv_rn(static_cast<float>(rgb[p * 3 + c]), 255.f);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int s = 0;
+      for (int i = 0; i < UNP_T / 32; ++i) s += warp_cnt[i];
+      running += s;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// colourise / 16-bit export: generate_depth_maps.py:15-44, 128-143
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__global__ void minmax_init_kernel(unsigned* mm) {
+  mm[0] = 0xffffffffu;
+  mm[1] = 0u;
+}
+__global__ void minmax_kernel(const float* __restrict__ d, long long n, unsigned* mm) {
+  unsigned lo = 0xffffffffu, hi = 0u;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = d[i];
+    if (!isnan(v)) {
+      const unsigned o = f2ord(v);
+      lo = min(lo, o), hi = max(hi, o);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+  }
+}
+__global__ void colorize_kernel(const float* __restrict__ d, long long n, const unsigned* __restrict__ mm,
+                                const uint8_t* __restrict__ lut, void* __restrict__ out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
+  const float v = d[i];
+  const float norm = __fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo));
+  if (lut) {
+    uint8_t* o = reinterpret_cast<uint8_t*>(out) + i * 3;
+    if (isnan(norm)) {
+      o[0] = o[1] = o[2] = 0;
+      return;
+    }
+    const float c = fminf(fmaxf(norm, 0.f), 1.f);
+    int k = static_cast<int>(c * 256.f);
+    k = k > 255 ? 255 : k;
+    o[0] = lut[k * 3], o[1] = lut[k * 3 + 1], o[2] = lut[k * 3 + 2];
+  } else {
+    reinterpret_cast<uint16_t*>(out)[i] = static_cast<uint16_t>(static_cast<int>(norm * 65535.f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = from_f<TO>(to_f(in[i]));
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // over NCHW out
+  const long long total = static_cast<long long>(B) * C * H * W;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % W), y = static_cast<int>((i / W) % H);
+  const int c = static_cast<int>((i / (static_cast<long long>(W) * H)) % C);
+  const long long b = i / (static_cast<long long>(W) * H * C);
+  out[i] = to_f(in[((b * H + y) * W + x) * C + c]);
+}
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int H, int W) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // over NHWC out
+  const long long total = static_cast<long long>(B) * C * H * W;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C), x = static_cast<int>((i / C) % W);
+  const int y = static_cast<int>((i / (static_cast<long long>(C) * W)) % H);
+  const long long b = i / (static_cast<long long>(C) * W * H);
+  out[i] = in[((b * C + c) * H + y) * W + x];
+}
+template <typename T>
+__global__ void pack_ohwi_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int I, int KH, int KW) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // over (o, ky, kx, ci)
+  const long long total = static_cast<long long>(O) * I * KH * KW;
+  if (i >= total) return;
+  const int ci = static_cast<int>(i % I), kx = static_cast<int>((i / I) % KW);
+  const int ky = static_cast<int>((i / (static_cast<long long>(I) * KW)) % KH);
+  const long long o = i / (static_cast<long long>(I) * KW * KH);
+  out[i] = from_f<T>(w[((o * I + ci) * KH + ky) * KW + kx]);
+}
+template <typename T>
+__global__ void pack_convT_kernel(const float* __restrict__ w, T* __restrict__ out, int I, int O) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // over ((dy,dx,o), ci)
+  const long long total = 4LL * I * O;
+  if (i >= total) return;
+  const int ci = static_cast<int>(i % I);
+  const int o = static_cast<int>((i / I) % O);
+  const int q = static_cast<int>(i / (static_cast<long long>(I) * O));
+  out[i] = from_f<T>(w[((static_cast<long long>(ci) * O + o) * 2 + (q >> 1)) * 2 + (q & 1)]);
+}
+__global__ void pack_hwio_kernel(const float* __restrict__ w, float* __restrict__ out, int O, int I, int KH, int KW) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // over (ky, kx, ci, o)
+  const long long total = static_cast<long long>(O) * I * KH * KW;
+  if (i >= total) return;
+  const int o = static_cast<int>(i % O), ci = static_cast<int>((i / O) % I);
+  const int kx = static_cast<int>((i / (static_cast<long long>(O) * I)) % KW);
+  const int ky = static_cast<int>(i / (static_cast<long long>(O) * I * KW));
+  out[i] = w[((static_cast<long long>(o) * I + ci) * KH + ky) * KW + kx];
+}
+
+}  // namespace
+
+// ============================================================================ host wrappers
+void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * 3 * IMG * IMG;
+  resize_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, src_fmt, B, H, W, x);
+  DP_LAUNCH_CHECK();
+}
+
+template <typename T>
+void split_im2col(const float* x, int B, T* A35, T* A1, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * 35 * 576 * 96;
+  split_im2col_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(x, B, A35, A1);
+  DP_LAUNCH_CHECK();
+}
+template void split_im2col<float>(const float*, int, float*, float*, cudaStream_t);
+template void split_im2col<bf16>(const float*, int, bf16*, bf16*, cudaStream_t);
+
+void im2col_to_ref_patches(const float* A35, int B, float* patches, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * 35 * 3 * 384 * 384;
+  im2col_to_ref_kernel<<<blocks_for(total, 256), 256, 0, s>>>(A35, B, patches);
+  DP_LAUNCH_CHECK();
+}
+
+void write_cls_rows(float* resid, const float* cls, const float* pos, int nseq, cudaStream_t s) {
+  cls_rows_kernel<<<blocks_for(static_cast<long long>(nseq) * 1024, 256), 256, 0, s>>>(resid, cls, pos, nseq);
+  DP_LAUNCH_CHECK();
+}
+
+template <typename T>
+void layernorm_rows(const float* in, T* out, const float* w, const float* b, long long n_out, RowMap map, int ln,
+                    cudaStream_t s) {
+  layernorm_kernel<T><<<blocks_for(n_out, 8), 256, 0, s>>>(in, out, w, b, n_out, map, ln);
+  DP_LAUNCH_CHECK();
+}
+template void layernorm_rows<float>(const float*, float*, const float*, const float*, long long, RowMap, int, cudaStream_t);
+template void layernorm_rows<bf16>(const float*, bf16*, const float*, const float*, long long, RowMap, int, cudaStream_t);
+
+void merge_rows_f32(const float* in, float* out, int B, int C, RowMap map, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * map.S * map.S * C;
+  merge_f32_kernel<<<blocks_for(total, 256), 256, 0, s>>>(in, out, total, C, map);
+  DP_LAUNCH_CHECK();
+}
+
+template <typename T>
+void conv_direct(const T* x, const float* w_hwio, const float* bias, T* y, int B, int H, int W, int Cin, int Cout,
+                 int k, int stride, int pad, int relu, const T* add_tokens, cudaStream_t s) {
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const size_t smem = static_cast<size_t>(k) * k * Cin * sizeof(float);
+  const int threads = Cout < 32 ? 32 : (Cout > 256 ? 256 : Cout);
+  conv_direct_kernel<T><<<B * Ho * Wo, threads, smem, s>>>(x, w_hwio, bias, y, H, W, Cin, Cout, k, stride, pad, Ho, Wo,
+                                                          relu, add_tokens);
+  DP_LAUNCH_CHECK();
+}
+template void conv_direct<float>(const float*, const float*, const float*, float*, int, int, int, int, int, int, int,
+                                 int, int, const float*, cudaStream_t);
+template void conv_direct<bf16>(const bf16*, const float*, const float*, bf16*, int, int, int, int, int, int, int, int,
+                                int, const bf16*, cudaStream_t);
+
+template <typename T>
+void fov_final(const T* x, const float* w_hwio, const float* bias, float* fov_deg, int B, cudaStream_t s) {
+  fov_final_kernel<T><<<B, 256, 0, s>>>(x, w_hwio, bias, fov_deg);
+  DP_LAUNCH_CHECK();
+}
+template void fov_final<float>(const float*, const float*, const float*, float*, int, cudaStream_t);
+template void fov_final<bf16>(const bf16*, const float*, const float*, float*, int, cudaStream_t);
+
+void compute_fpx(const float* fov_deg, const float* f_px_in, int W, float* f_px, int B, cudaStream_t s) {
+  fpx_kernel<<<1, 64, 0, s>>>(fov_deg, f_px_in, W, f_px, B);
+  DP_LAUNCH_CHECK();
+}
+
+void depth_epilogue(const float* canon, const float* f_px, int B, int H, int W, float* depth, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * H * W;
+  depth_epilogue_kernel<<<blocks_for(total, 256), 256, 0, s>>>(canon, f_px, B, H, W, depth);
+  DP_LAUNCH_CHECK();
+}
+
+size_t unproject_scratch_ints(int H, int W) {
+  const long long nblk = (static_cast<long long>(H) * W + UNP_BLK - 1) / UNP_BLK;
+  return static_cast<size_t>(nblk) * 3 + 8;  // int counts + int64 offsets
+}
+
+void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float* f_px, float* xyz, float* rgb_out,
+               uint8_t* valid_mask, int64_t* n_valid, int* scratch, cudaStream_t s) {
+  const long long n = static_cast<long long>(H) * W;
+  const int nblk = static_cast<int>((n + UNP_BLK - 1) / UNP_BLK);
+  int* counts = scratch;
+  long long* offsets = reinterpret_cast<long long*>(scratch + ((nblk + 1) & ~1));
+  unproject_count_kernel<<<nblk, UNP_T, 0, s>>>(depth, n, counts);
+  DP_LAUNCH_CHECK();
+  unproject_scan_kernel<<<1, 1024, 0, s>>>(counts, offsets, nblk, n_valid);
+  DP_LAUNCH_CHECK();
+  unproject_write_kernel<<<nblk, UNP_T, 0, s>>>(depth, rgb, H, W, f_px, offsets, xyz, rgb_out, valid_mask);
+  DP_LAUNCH_CHECK();
+}
+
+void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, float* minmax, cudaStream_t s) {
+  const long long n = static_cast<long long>(H) * W;
+  unsigned* mm = reinterpret_cast<unsigned*>(minmax);
+  minmax_init_kernel<<<1, 1, 0, s>>>(mm);
+  DP_LAUNCH_CHECK();
+  minmax_kernel<<<592, 256, 0, s>>>(depth, n, mm);
+  DP_LAUNCH_CHECK();
+  colorize_kernel<<<blocks_for(n, 256), 256, 0, s>>>(depth, n, mm, lut, out);
+  DP_LAUNCH_CHECK();
+}
+
+template <typename TI, typename TO>
+void convert(const TI* in, TO* out, long long n, cudaStream_t s) {
+  convert_kernel<TI, TO><<<blocks_for(n, 256), 256, 0, s>>>(in, out, n);
+  DP_LAUNCH_CHECK();
+}
+template void convert<float, float>(const float*, float*, long long, cudaStream_t);
+template void convert<float, bf16>(const float*, bf16*, long long, cudaStream_t);
+template void convert<bf16, float>(const bf16*, float*, long long, cudaStream_t);
+
+template <typename T>
+void nhwc_to_nchw_f32(const T* in, float* out, int B, int H, int W, int C, cudaStream_t s) {
+  nhwc_to_nchw_kernel<T><<<blocks_for(static_cast<long long>(B) * H * W * C, 256), 256, 0, s>>>(in, out, B, H, W, C);
+  DP_LAUNCH_CHECK();
+}
+template void nhwc_to_nchw_f32<float>(const float*, float*, int, int, int, int, cudaStream_t);
+template void nhwc_to_nchw_f32<bf16>(const bf16*, float*, int, int, int, int, cudaStream_t);
+
+void nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W, cudaStream_t s) {
+  nchw_to_nhwc_kernel<<<blocks_for(static_cast<long long>(B) * H * W * C, 256), 256, 0, s>>>(in, out, B, C, H, W);
+  DP_LAUNCH_CHECK();
+}
+
+template <typename T>
+void pack_oihw_to_ohwi(const float* w, T* out, int O, int I, int KH, int KW, cudaStream_t s) {
+  pack_ohwi_kernel<T><<<blocks_for(static_cast<long long>(O) * I * KH * KW, 256), 256, 0, s>>>(w, out, O, I, KH, KW);
+  DP_LAUNCH_CHECK();
+}
+template void pack_oihw_to_ohwi<float>(const float*, float*, int, int, int, int, cudaStream_t);
+template void pack_oihw_to_ohwi<bf16>(const float*, bf16*, int, int, int, int, cudaStream_t);
+
+template <typename T>
+void pack_convT_iohw(const float* w, T* out, int I, int O, cudaStream_t s) {
+  pack_convT_kernel<T><<<blocks_for(4LL * I * O, 256), 256, 0, s>>>(w, out, I, O);
+  DP_LAUNCH_CHECK();
+}
+template void pack_convT_iohw<float>(const float*, float*, int, int, cudaStream_t);
+template void pack_convT_iohw<bf16>(const float*, bf16*, int, int, cudaStream_t);
+
+void pack_oihw_to_hwio_f32(const float* w, float* out, int O, int I, int KH, int KW, cudaStream_t s) {
+  pack_hwio_kernel<<<blocks_for(static_cast<long long>(O) * I * KH * KW, 256), 256, 0, s>>>(w, out, O, I, KH, KW);
+  DP_LAUNCH_CHECK();
+}
+
+}  // namespace dp

@@ -1,0 +1,78 @@
+// HBM-bound kernels of the Depth Pro engine: resize, pyramid/split/im2col gather, LayerNorm
+// (+ merge gather), small direct convolutions, metric-depth epilogue, unprojection, colourise,
+// weight repacking and layout conversion helpers.  Declarations only; see kernels.cu.
+#pragma once
+#include "common.cuh"
+
+namespace dp {
+
+// ---- preprocessing ------------------------------------------------------------------
+// src (u8 HWC or f32 CHW, B images of HxW) -> x (B,3,1536,1536) f32, bilinear align_corners=False.
+void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x, cudaStream_t s);
+
+// x (B,3,1536,1536) f32 -> patch-embed im2col rows.  Frame-major order: row =
+// ((b*35 + patch)*576 + ty*24 + tx), col = c*256 + ky*16 + kx.  patch 0..24 = 5x5 windows of the
+// full image (stride 288), 25..33 = 3x3 windows of the 2x box-mean image (stride 192),
+// 34 = the 4x-downsampled image.  `A35` gets all 35 patches, `A1` (optional) only patch 34.
+template <typename T>
+void split_im2col(const float* x, int B, T* A35, T* A1, cudaStream_t s);
+// im2col rows (fp32) -> patches (35B,3,384,384) in the reference's patch-major / batch-minor order.
+void im2col_to_ref_patches(const float* A35, int B, float* patches, cudaStream_t s);
+
+// ---- tokens ---------------------------------------------------------------------------
+// resid[(r*577)*1024 + n] = cls[n] + pos[n] for every sequence r.
+void write_cls_rows(float* resid, const float* cls, const float* pos, int nseq, cudaStream_t s);
+
+struct RowMap {
+  int mode = 0;       // 0 identity, 1 merge gather (dest pixel -> source token)
+  int S = 0;          // dest grid side (96 / 48 / 24)
+  int steps = 1;      // patches per side
+  int pad = 0;        // tokens cropped on interior edges
+  int patch_base = 0; // first patch of this pyramid level inside a frame's 35
+  int sb = 35, sp = 1;  // source sequence index = b*sb + patch*sp
+};
+// LayerNorm over C=1024 (eps 1e-6) of gathered rows; `ln` == 0 copies/converts only.
+// in: fp32 rows of width 1024; out: T rows (n_out x 1024).
+template <typename T>
+void layernorm_rows(const float* in, T* out, const float* w, const float* b, long long n_out,
+                    RowMap map, int ln, cudaStream_t s);
+// generic-width gather without LN (used by dp_merge): in (nseq,577,C) f32 -> out (B,S,S,C) f32
+void merge_rows_f32(const float* in, float* out, int B, int C, RowMap map, cudaStream_t s);
+
+// ---- small direct convolution (FOV head) ------------------------------------------------
+// NHWC in (B,H,W,Cin) of type T, weights HWIO fp32 (k,k,Cin,Cout), out NHWC (B,Ho,Wo,Cout) of T.
+// v = conv + bias; relu optional; then + addend (tokens (B,577,Cout) skipping cls if add_tokens).
+template <typename T>
+void conv_direct(const T* x, const float* w_hwio, const float* bias, T* y, int B, int H, int W, int Cin,
+                 int Cout, int k, int stride, int pad, int relu, const T* add_tokens, cudaStream_t s);
+// final 6x6 valid conv over (B,6,6,32) -> fov_deg[B] (fp32)
+template <typename T>
+void fov_final(const T* x, const float* w_hwio, const float* bias, float* fov_deg, int B, cudaStream_t s);
+
+// ---- metric depth epilogue ----------------------------------------------------------------
+// f_px[b] = f_px_in ? f_px_in[b] : 0.5*W / tan(0.5*deg2rad(fov_deg[b]))   (depth_pro.py:282-283)
+void compute_fpx(const float* fov_deg, const float* f_px_in, int W, float* f_px, int B, cudaStream_t s);
+// depth[b,y,x] = 1 / clamp(resize(canon * (W / f_px[b]))[y,x], 1e-4, 1e4)    (depth_pro.py:285-293)
+void depth_epilogue(const float* canon, const float* f_px, int B, int H, int W, float* depth, cudaStream_t s);
+
+// ---- video add-on ---------------------------------------------------------------------------
+void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float* f_px, float* xyz,
+               float* rgb_out, uint8_t* valid_mask, int64_t* n_valid, int* scratch, cudaStream_t s);
+size_t unproject_scratch_ints(int H, int W);
+void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, float* minmax, cudaStream_t s);
+
+// ---- layout / dtype helpers ---------------------------------------------------------------
+template <typename TI, typename TO>
+void convert(const TI* in, TO* out, long long n, cudaStream_t s);
+// NHWC (B,H,W,C) of T -> NCHW fp32
+template <typename T>
+void nhwc_to_nchw_f32(const T* in, float* out, int B, int H, int W, int C, cudaStream_t s);
+void nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W, cudaStream_t s);
+// weight repacks (fp32 source in PyTorch layout)
+template <typename T>
+void pack_oihw_to_ohwi(const float* w, T* out, int O, int I, int KH, int KW, cudaStream_t s);  // conv
+template <typename T>
+void pack_convT_iohw(const float* w, T* out, int I, int O, cudaStream_t s);  // (I,O,2,2) -> ((dy,dx,o), i)
+void pack_oihw_to_hwio_f32(const float* w, float* out, int O, int I, int KH, int KW, cudaStream_t s);
+
+}  // namespace dp
