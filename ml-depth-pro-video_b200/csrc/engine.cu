@@ -1,0 +1,713 @@
+// Depth Pro engine implementation (see engine.cuh).  Reference call stack followed:
+//   DepthPro.infer            src/depth_pro/depth_pro.py:243-298
+//   DepthPro.forward          src/depth_pro/depth_pro.py:218-241
+//   DepthProEncoder.forward   src/depth_pro/network/encoder.py:233-332
+//   timm forward_features     (third party; wired at network/vit_factory.py:97-110)
+//   MultiresConvDecoder       src/depth_pro/network/decoder.py:74-93, 166-180
+//   FOVNetwork.forward        src/depth_pro/network/fov.py:56-82
+#include "engine.cuh"
+
+#include <cstring>
+
+#include "attention.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace dp {
+
+int64_t g_launches = 0;
+
+namespace {
+
+constexpr int IMG = 1536, EMB = 1024, SEQ = 577;
+
+void add_vit(std::map<std::string, std::vector<int64_t>>& m, const std::string& p) {
+  m[p + "cls_token"] = {1, 1, EMB};
+  m[p + "pos_embed"] = {1, SEQ, EMB};
+  m[p + "patch_embed.proj.weight"] = {EMB, 3, 16, 16};
+  m[p + "patch_embed.proj.bias"] = {EMB};
+  for (int i = 0; i < 24; ++i) {
+    const std::string b = p + "blocks." + std::to_string(i) + ".";
+    m[b + "norm1.weight"] = {EMB};
+    m[b + "norm1.bias"] = {EMB};
+    m[b + "attn.qkv.weight"] = {3 * EMB, EMB};
+    m[b + "attn.qkv.bias"] = {3 * EMB};
+    m[b + "attn.proj.weight"] = {EMB, EMB};
+    m[b + "attn.proj.bias"] = {EMB};
+    m[b + "ls1.gamma"] = {EMB};
+    m[b + "norm2.weight"] = {EMB};
+    m[b + "norm2.bias"] = {EMB};
+    m[b + "mlp.fc1.weight"] = {4 * EMB, EMB};
+    m[b + "mlp.fc1.bias"] = {4 * EMB};
+    m[b + "mlp.fc2.weight"] = {EMB, 4 * EMB};
+    m[b + "mlp.fc2.bias"] = {EMB};
+    m[b + "ls2.gamma"] = {EMB};
+  }
+  m[p + "norm.weight"] = {EMB};
+  m[p + "norm.bias"] = {EMB};
+}
+
+// name -> shape of the reference state_dict (pinned by tests/golden/state_dict_manifest.json)
+std::map<std::string, std::vector<int64_t>> build_manifest() {
+  std::map<std::string, std::vector<int64_t>> m;
+  add_vit(m, "encoder.patch_encoder.");
+  add_vit(m, "encoder.image_encoder.");
+  add_vit(m, "fov.encoder.0.");
+  m["encoder.upsample_latent0.0.weight"] = {256, EMB, 1, 1};
+  for (int i = 1; i <= 3; ++i) m["encoder.upsample_latent0." + std::to_string(i) + ".weight"] = {256, 256, 2, 2};
+  m["encoder.upsample_latent1.0.weight"] = {256, EMB, 1, 1};
+  for (int i = 1; i <= 2; ++i) m["encoder.upsample_latent1." + std::to_string(i) + ".weight"] = {256, 256, 2, 2};
+  const int dims[3] = {512, 1024, 1024};
+  for (int i = 0; i < 3; ++i) {
+    const std::string n = "encoder.upsample" + std::to_string(i);
+    m[n + ".0.weight"] = {dims[i], EMB, 1, 1};
+    m[n + ".1.weight"] = {dims[i], dims[i], 2, 2};
+  }
+  m["encoder.upsample_lowres.weight"] = {EMB, 1024, 2, 2};
+  m["encoder.upsample_lowres.bias"] = {1024};
+  m["encoder.fuse_lowres.weight"] = {1024, 2048, 1, 1};
+  m["encoder.fuse_lowres.bias"] = {1024};
+  const int cd[5] = {0, 256, 512, 1024, 1024};
+  for (int i = 1; i <= 4; ++i) m["decoder.convs." + std::to_string(i) + ".weight"] = {256, cd[i], 3, 3};
+  for (int f = 0; f < 5; ++f) {
+    const std::string p = "decoder.fusions." + std::to_string(f) + ".";
+    for (const char* rn : {"resnet1", "resnet2"})
+      for (const char* c : {"1", "3"}) {
+        m[p + rn + ".residual." + c + ".weight"] = {256, 256, 3, 3};
+        m[p + rn + ".residual." + c + ".bias"] = {256};
+      }
+    if (f != 0) m[p + "deconv.weight"] = {256, 256, 2, 2};
+    m[p + "out_conv.weight"] = {256, 256, 1, 1};
+    m[p + "out_conv.bias"] = {256};
+  }
+  m["head.0.weight"] = {128, 256, 3, 3};
+  m["head.0.bias"] = {128};
+  m["head.1.weight"] = {128, 128, 2, 2};
+  m["head.1.bias"] = {128};
+  m["head.2.weight"] = {32, 128, 3, 3};
+  m["head.2.bias"] = {32};
+  m["head.4.weight"] = {1, 32, 1, 1};
+  m["head.4.bias"] = {1};
+  m["fov.encoder.1.weight"] = {128, EMB};
+  m["fov.encoder.1.bias"] = {128};
+  m["fov.downsample.0.weight"] = {128, 256, 3, 3};
+  m["fov.downsample.0.bias"] = {128};
+  m["fov.head.0.weight"] = {64, 128, 3, 3};
+  m["fov.head.0.bias"] = {64};
+  m["fov.head.2.weight"] = {32, 64, 3, 3};
+  m["fov.head.2.bias"] = {32};
+  m["fov.head.4.weight"] = {1, 32, 6, 6};
+  m["fov.head.4.bias"] = {1};
+  return m;
+}
+
+bool ends_with(const std::string& s, const std::string& suf) {
+  return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+bool starts_with(const std::string& s, const std::string& pre) { return s.compare(0, pre.size(), pre) == 0; }
+
+// ConvTranspose2d weights are (Cin, Cout, 2, 2)
+bool is_convT(const std::string& n) {
+  if (n == "encoder.upsample_lowres.weight" || n == "head.1.weight") return true;
+  if (ends_with(n, "deconv.weight")) return true;
+  if (starts_with(n, "encoder.upsample") && ends_with(n, ".weight")) {
+    const size_t e = n.size() - 7;              // position of ".weight"
+    const size_t d = n.rfind('.', e - 1);       // dot before the layer index
+    const std::string idx = n.substr(d + 1, e - d - 1);
+    return !idx.empty() && isdigit(idx[0]) && std::stoi(idx) >= 1;
+  }
+  return false;
+}
+
+}  // namespace
+
+// ============================================================================ lifecycle
+Engine::Engine(int device, int prec, int max_batch) : device_(device), prec_(prec), max_batch_(max_batch) {
+  DP_CHECK(prec == FP32 || prec == BF16, "precision must be 0 (fp32) or 1 (bf16)");
+  DP_CHECK(max_batch >= 1 && max_batch <= 64, "max_batch out of range");
+  int count = 0;
+  DP_CUDA(cudaGetDeviceCount(&count));
+  DP_CHECK(device >= 0 && device < count, "no such CUDA device (this engine has no CPU fallback)");
+  DP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DP_CUDA(cudaGetDeviceProperties(&prop, device));
+  DP_CHECK(prop.major == 10, "depthpro_b200 is built for sm_100a (Blackwell B200) only; found sm_" +
+                                 std::to_string(prop.major) + std::to_string(prop.minor));
+  manifest_ = build_manifest();
+  DP_CUDA(cudaStreamCreateWithFlags(&host_stream_, cudaStreamNonBlocking));
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  for (void* p : allocs_) cudaFree(p);
+  for (auto& kv : packed_) cudaFree(kv.second.ptr);
+  if (stage_) cudaFree(stage_);
+  if (himg_) cudaFree(himg_);
+  if (hdepth_) cudaFree(hdepth_);
+  if (host_stream_) cudaStreamDestroy(host_stream_);
+  tmap_cache_clear();
+}
+
+void* Engine::alloc(size_t bytes) {
+  void* p = nullptr;
+  DP_CUDA(cudaMalloc(&p, (bytes + 255) & ~size_t(255)));
+  allocs_.push_back(p);
+  return p;
+}
+
+void Engine::set_weight(const std::string& name, const void* data, const int64_t* shape, int ndim, bool on_device) {
+  DP_CUDA(cudaSetDevice(device_));
+  auto it = manifest_.find(name);
+  if (it == manifest_.end()) throw Error("unexpected key in state_dict: " + name);
+  const auto& ms = it->second;
+  DP_CHECK(static_cast<int>(ms.size()) == ndim, "rank mismatch for " + name);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    DP_CHECK(ms[i] == shape[i], "shape mismatch for " + name);
+    n *= static_cast<size_t>(shape[i]);
+  }
+  cudaStream_t s = nullptr;
+  const float* src = reinterpret_cast<const float*>(data);
+  if (!on_device) {
+    if (stage_bytes_ < n * 4) {
+      if (stage_) DP_CUDA(cudaFree(stage_));
+      DP_CUDA(cudaMalloc(&stage_, n * 4));
+      stage_bytes_ = n * 4;
+    }
+    DP_CUDA(cudaMemcpy(stage_, data, n * 4, cudaMemcpyHostToDevice));
+    src = stage_;
+  }
+  const bool bf = prec_ == BF16;
+  Packed& pk = packed_[name];
+  auto ensure = [&](size_t bytes) {
+    if (pk.bytes != bytes) {
+      if (pk.ptr) DP_CUDA(cudaFree(pk.ptr));
+      DP_CUDA(cudaMalloc(&pk.ptr, bytes));
+      pk.bytes = bytes;
+    }
+  };
+  const bool fov_conv = ndim == 4 && (starts_with(name, "fov.downsample") || starts_with(name, "fov.head"));
+  if (ndim == 4 && is_convT(name)) {
+    ensure(n * esz());
+    if (bf) pack_convT_iohw<bf16>(src, reinterpret_cast<bf16*>(pk.ptr), (int)shape[0], (int)shape[1], s);
+    else pack_convT_iohw<float>(src, reinterpret_cast<float*>(pk.ptr), (int)shape[0], (int)shape[1], s);
+  } else if (fov_conv) {
+    ensure(n * 4);
+    pack_oihw_to_hwio_f32(src, reinterpret_cast<float*>(pk.ptr), (int)shape[0], (int)shape[1], (int)shape[2], (int)shape[3], s);
+  } else if (ndim == 4 && shape[2] == 3 && name != "head.4.weight") {
+    ensure(n * esz());
+    if (bf) pack_oihw_to_ohwi<bf16>(src, reinterpret_cast<bf16*>(pk.ptr), (int)shape[0], (int)shape[1], 3, 3, s);
+    else pack_oihw_to_ohwi<float>(src, reinterpret_cast<float*>(pk.ptr), (int)shape[0], (int)shape[1], 3, 3, s);
+  } else if ((ndim == 2 || ndim == 4) && name != "head.4.weight") {
+    // Linear (N,K); 1x1 conv (O,I,1,1); patch-embed conv (O, 3*16*16): already [N, K] K-major
+    ensure(n * esz());
+    if (bf) convert<float, bf16>(src, reinterpret_cast<bf16*>(pk.ptr), (long long)n, s);
+    else convert<float, float>(src, reinterpret_cast<float*>(pk.ptr), (long long)n, s);
+  } else {
+    ensure(n * 4);
+    convert<float, float>(src, reinterpret_cast<float*>(pk.ptr), (long long)n, s);
+  }
+  DP_CUDA(cudaStreamSynchronize(s));
+}
+
+int Engine::missing_weights() const {
+  int miss = 0;
+  for (auto& kv : manifest_)
+    if (!packed_.count(kv.first)) ++miss;
+  return miss;
+}
+
+const void* Engine::W(const std::string& name) const {
+  auto it = packed_.find(name);
+  if (it == packed_.end()) throw Error("missing key in state_dict: " + name);
+  return it->second.ptr;
+}
+const float* Engine::F(const std::string& name) const { return reinterpret_cast<const float*>(W(name)); }
+
+VitWeights Engine::vit_weights(const std::string& p) const {
+  VitWeights w;
+  w.cls = F(p + "cls_token");
+  w.pos = F(p + "pos_embed");
+  w.pe_w = W(p + "patch_embed.proj.weight");
+  w.pe_b = F(p + "patch_embed.proj.bias");
+  w.norm_w = F(p + "norm.weight");
+  w.norm_b = F(p + "norm.bias");
+  for (int i = 0; i < 24; ++i) {
+    const std::string b = p + "blocks." + std::to_string(i) + ".";
+    auto& k = w.blk[i];
+    k.n1w = F(b + "norm1.weight"), k.n1b = F(b + "norm1.bias");
+    k.qkv_w = W(b + "attn.qkv.weight"), k.qkv_b = F(b + "attn.qkv.bias");
+    k.proj_w = W(b + "attn.proj.weight"), k.proj_b = F(b + "attn.proj.bias");
+    k.g1 = F(b + "ls1.gamma");
+    k.n2w = F(b + "norm2.weight"), k.n2b = F(b + "norm2.bias");
+    k.fc1_w = W(b + "mlp.fc1.weight"), k.fc1_b = F(b + "mlp.fc1.bias");
+    k.fc2_w = W(b + "mlp.fc2.weight"), k.fc2_b = F(b + "mlp.fc2.bias");
+    k.g2 = F(b + "ls2.gamma");
+  }
+  return w;
+}
+
+void Engine::finalize() {
+  DP_CUDA(cudaSetDevice(device_));
+  if (missing_weights() != 0) {
+    for (auto& kv : manifest_)
+      if (!packed_.count(kv.first)) throw Error("missing key in state_dict: " + kv.first);
+  }
+  vit_patch_ = vit_weights("encoder.patch_encoder.");
+  vit_image_ = vit_weights("encoder.image_encoder.");
+  vit_fov_ = vit_weights("fov.encoder.0.");
+  if (finalized_) return;  // workspace already allocated; weights re-bound above
+
+  const size_t e = esz();
+  const size_t MB = static_cast<size_t>(max_batch_);
+  const size_t T = MB * 35 * SEQ, Ts = MB * SEQ;
+  xbuf_ = (float*)alloc(MB * 3 * IMG * IMG * 4);
+  canon_ = (float*)alloc(MB * IMG * IMG * 4);
+  fov_ = (float*)alloc(MB * 4);
+  fpx_ = (float*)alloc(MB * 4);
+  fpx_in_ = (float*)alloc(MB * 4);
+  A35_ = alloc(MB * 35 * 576 * 768 * e);
+  A1_ = alloc(MB * 576 * 768 * e);
+  resid_ = (float*)alloc(T * EMB * 4);
+  xn_ = alloc(T * EMB * e);
+  qkv_ = alloc(T * 3 * EMB * e);
+  attn_ = alloc(T * EMB * e);
+  hid_ = alloc(T * 4 * EMB * e);
+  resid_s_ = (float*)alloc(Ts * EMB * 4);
+  xn_s_ = alloc(Ts * EMB * e);
+  qkv_s_ = alloc(Ts * 3 * EMB * e);
+  attn_s_ = alloc(Ts * EMB * e);
+  hid_s_ = alloc(Ts * 4 * EMB * e);
+  lat0m_ = alloc(MB * 96 * 96 * EMB * e);
+  lat1m_ = alloc(MB * 96 * 96 * EMB * e);
+  x0m_ = alloc(MB * 96 * 96 * EMB * e);
+  x1m_ = alloc(MB * 48 * 48 * EMB * e);
+  x2m_ = alloc(MB * 24 * 24 * EMB * e);
+  globm_ = alloc(MB * 24 * 24 * EMB * e);
+  fovtok_ = alloc(MB * 24 * 24 * EMB * e);
+  // per-frame decoder workspace
+  const size_t P96 = 96 * 96, P192 = 192 * 192, P384 = 384 * 384, P768 = 768 * 768, P48 = 48 * 48, P24 = 24 * 24;
+  u0a_ = alloc(P96 * 256 * e), u0b_ = alloc(P192 * 256 * e), u0c_ = alloc(P384 * 256 * e);
+  enc0_ = alloc(P768 * 256 * e), enc0r_ = alloc(P768 * 256 * e);
+  u1a_ = alloc(P96 * 256 * e), u1b_ = alloc(P192 * 256 * e), enc1_ = alloc(P384 * 256 * e);
+  u2a_ = alloc(P96 * 512 * e), enc2_ = alloc(P192 * 512 * e);
+  u3a_ = alloc(P48 * 1024 * e), enc3_ = alloc(P96 * 1024 * e);
+  u4a_ = alloc(P24 * 1024 * e), cat_ = alloc(P48 * 2048 * e), enc4_ = alloc(P48 * 1024 * e);
+  lowres_ = alloc(P48 * 256 * e), lowres_r_ = alloc(P48 * 256 * e);
+  x1_ = alloc(P768 * 256 * e), x1r_ = alloc(P768 * 256 * e), t_ = alloc(P768 * 256 * e);
+  x_ = alloc(P768 * 256 * e), xr_ = alloc(P768 * 256 * e), x2_ = alloc(P768 * 256 * e), y_ = alloc(P768 * 256 * e);
+  const size_t fs[5] = {P768, P768, P384, P192, P96};  // feat_[i] = output of fusion i
+  for (int i = 0; i < 5; ++i) feat_[i] = alloc(fs[i] * 256 * e);
+  h0_ = alloc(P768 * 128 * e);
+  h1_ = alloc(static_cast<size_t>(IMG) * IMG * 128 * e);
+  fovlin_ = alloc(P24 * 128 * e), fov_a_ = alloc(P24 * 128 * e), fov_b_ = alloc(12 * 12 * 64 * e),
+  fov_c_ = alloc(6 * 6 * 32 * e);
+  colorize_mm_ = (float*)alloc(64);
+  finalized_ = true;
+}
+
+// ============================================================================ small entry points
+void Engine::preprocess(const void* img, int B, int H, int W, int src_fmt, float* x, cudaStream_t s) {
+  DP_CHECK(B >= 1 && H >= 1 && W >= 1, "bad image shape");
+  DP_CHECK(src_fmt == 0 || src_fmt == 1, "bad src_fmt");
+  resize_to_1536(img, src_fmt, B, H, W, x, s);
+}
+
+void Engine::split(const float* x, int B, float* patches, cudaStream_t s) {
+  float* tmp = nullptr;
+  const size_t n = static_cast<size_t>(B) * 35 * 576 * 768;
+  DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp), n * 4, s));
+  split_im2col<float>(x, B, tmp, nullptr, s);
+  im2col_to_ref_patches(tmp, B, patches, s);
+  DP_CUDA(cudaFreeAsync(tmp, s));
+}
+
+void Engine::merge(const float* tokens, int B, int steps, int padding, int C, float* merged, cudaStream_t s) {
+  DP_CHECK(steps >= 1 && padding >= 0 && 2 * padding < 24, "bad merge geometry");
+  RowMap m;
+  m.mode = 1, m.steps = steps, m.pad = padding, m.patch_base = 0;
+  m.S = steps == 1 ? 24 : (24 - padding) * 2 + (24 - 2 * padding) * (steps - 2);
+  m.sb = 1, m.sp = B;  // reference order: patch-major, batch-minor (encoder.py:200)
+  float* tmp = nullptr;
+  const size_t n = static_cast<size_t>(B) * m.S * m.S * C;
+  DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp), n * 4, s));
+  // gather works on rows of width C with 577 tokens per sequence
+  merge_rows_f32(tokens, tmp, B, C, m, s);
+  nhwc_to_nchw_f32<float>(tmp, merged, B, m.S, m.S, C, s);
+  DP_CUDA(cudaFreeAsync(tmp, s));
+}
+
+// ============================================================================ ViT
+template <typename T>
+void Engine::run_vit(const VitWeights& w, const T* A, int nseq, float* resid, T* xn, T* qkv, T* attn, T* hid, bool hooks,
+                     int B, cudaStream_t s) {
+  const int M = nseq * SEQ;
+  {  // patch embed (timm PatchEmbed conv k16 s16 as GEMM) + cls + pos_embed
+    GemmOp op;
+    op.M = nseq * 576, op.N = EMB, op.K = 768, op.A = A, op.lda = 768, op.Wt = w.pe_w, op.bias = w.pe_b;
+    op.out = resid, op.out_f32 = 1, op.out_mode = O_PATCH_EMBED, op.ldo = EMB, op.pos = w.pos;
+    gemm(prec_, op, s);
+    write_cls_rows(resid, w.cls, w.pos, nseq, s);
+  }
+  for (int i = 0; i < 24; ++i) {
+    const auto& k = w.blk[i];
+    layernorm_rows<T>(resid, xn, k.n1w, k.n1b, M, RowMap(), 1, s);
+    {
+      GemmOp op;
+      op.M = M, op.N = 3 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.Wt = k.qkv_w, op.bias = k.qkv_b;
+      op.out = qkv, op.ldo = 3 * EMB;
+      gemm(prec_, op, s);
+    }
+    if (prec_ == BF16) attention_bf16((const bf16*)qkv, (bf16*)attn, nseq, s);
+    else attention_f32((const float*)qkv, (float*)attn, nseq, s);
+    {
+      GemmOp op;
+      op.M = M, op.N = EMB, op.K = EMB, op.A = attn, op.lda = EMB, op.Wt = k.proj_w, op.bias = k.proj_b;
+      op.gamma = k.g1, op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
+      gemm(prec_, op, s);
+    }
+    layernorm_rows<T>(resid, xn, k.n2w, k.n2b, M, RowMap(), 1, s);
+    {
+      GemmOp op;
+      op.M = M, op.N = 4 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.Wt = k.fc1_w, op.bias = k.fc1_b;
+      op.act = ACT_GELU, op.out = hid, op.ldo = 4 * EMB;
+      gemm(prec_, op, s);
+    }
+    {
+      GemmOp op;
+      op.M = M, op.N = EMB, op.K = 4 * EMB, op.A = hid, op.lda = 4 * EMB, op.Wt = k.fc2_w, op.bias = k.fc2_b;
+      op.gamma = k.g2, op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
+      gemm(prec_, op, s);
+    }
+    if (hooks && (i == 5 || i == 11)) {
+      // forward hooks on blocks 5 / 11 (encoder.py:133-144): pre-norm residual stream of the 25
+      // level-0 patches, cls dropped, merged with padding 3 (encoder.py:268-289)
+      RowMap m;
+      m.mode = 1, m.S = 96, m.steps = 5, m.pad = 3, m.patch_base = 0;
+      layernorm_rows<T>(resid, (T*)(i == 5 ? lat0m_ : lat1m_), nullptr, nullptr, (long long)B * 96 * 96, m, 0, s);
+    }
+  }
+}
+
+// ============================================================================ forward
+template <typename T>
+void Engine::forward_impl(const float* x, int B, float* canon, float* fov_deg, cudaStream_t s) {
+  split_im2col<T>(x, B, (T*)A35_, (T*)A1_, s);
+
+  // patch encoder over 35*B sequences (encoder.py:266), then final norm fused with the merges
+  run_vit<T>(vit_patch_, (const T*)A35_, 35 * B, resid_, (T*)xn_, (T*)qkv_, (T*)attn_, (T*)hid_, true, B, s);
+  {
+    RowMap m;
+    m.mode = 1, m.S = 96, m.steps = 5, m.pad = 3, m.patch_base = 0;
+    layernorm_rows<T>(resid_, (T*)x0m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 96 * 96, m, 1, s);
+    m.S = 48, m.steps = 3, m.pad = 6, m.patch_base = 25;
+    layernorm_rows<T>(resid_, (T*)x1m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 48 * 48, m, 1, s);
+    m.S = 24, m.steps = 1, m.pad = 0, m.patch_base = 34;
+    layernorm_rows<T>(resid_, (T*)x2m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 24 * 24, m, 1, s);
+  }
+  // image encoder on the 384^2 image (encoder.py:308-311)
+  RowMap ms;
+  ms.mode = 1, ms.S = 24, ms.steps = 1, ms.pad = 0, ms.patch_base = 0, ms.sb = 1, ms.sp = 1;
+  run_vit<T>(vit_image_, (const T*)A1_, B, resid_s_, (T*)xn_s_, (T*)qkv_s_, (T*)attn_s_, (T*)hid_s_, false, B, s);
+  layernorm_rows<T>(resid_s_, (T*)globm_, vit_image_.norm_w, vit_image_.norm_b, (long long)B * 24 * 24, ms, 1, s);
+  // fov encoder on the same image (fov.py:70-77)
+  run_vit<T>(vit_fov_, (const T*)A1_, B, resid_s_, (T*)xn_s_, (T*)qkv_s_, (T*)attn_s_, (T*)hid_s_, false, B, s);
+  layernorm_rows<T>(resid_s_, (T*)fovtok_, vit_fov_.norm_w, vit_fov_.norm_b, (long long)B * 24 * 24, ms, 1, s);
+
+  for (int f = 0; f < B; ++f) decode_frame<T>(f, canon + static_cast<size_t>(f) * IMG * IMG, fov_deg + f, s);
+  last_B_ = B;
+}
+
+template <typename T>
+void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
+  auto frame = [&](void* base, size_t elems_per_frame) { return (T*)base + static_cast<size_t>(f) * elems_per_frame; };
+  const T* lat0m = frame(lat0m_, 96 * 96 * EMB);
+  const T* lat1m = frame(lat1m_, 96 * 96 * EMB);
+  const T* x0m = frame(x0m_, 96 * 96 * EMB);
+  const T* x1m = frame(x1m_, 48 * 48 * EMB);
+  const T* x2m = frame(x2m_, 24 * 24 * EMB);
+  const T* globm = frame(globm_, 24 * 24 * EMB);
+  const T* fovtok = frame(fovtok_, 24 * 24 * EMB);
+
+  auto conv1x1 = [&](const void* in, int S, int Cin, const std::string& wname, int Cout, void* out, const float* bias) {
+    GemmOp op;
+    op.M = S * S, op.N = Cout, op.K = Cin, op.A = in, op.lda = Cin, op.Wt = W(wname), op.bias = bias;
+    op.out = out, op.ldo = Cout;
+    gemm(prec_, op, s);
+  };
+  // ConvTranspose2d k2 s2 on an SxS grid: GEMM with N = 4*Cout + pixel-shuffle scatter
+  auto convT = [&](const void* in, int S, int Cin, const std::string& wname, int Cout, void* out, int ldo, int col_off,
+                   const float* bias, void* out_relu) {
+    GemmOp op;
+    op.M = S * S, op.N = 4 * Cout, op.K = Cin, op.A = in, op.lda = Cin, op.Wt = W(wname);
+    op.bias = bias, op.bias_mod = bias ? Cout : 0;
+    op.B = 1, op.H = S, op.W = S, op.cout = Cout, op.out_mode = O_CONVT2X2;
+    op.out = out, op.out_relu = out_relu, op.ldo = ldo, op.col_off = col_off;
+    gemm(prec_, op, s);
+  };
+  auto conv3x3 = [&](const void* in, int S, int Cin, const std::string& wname, int Cout, const float* bias, int act,
+                     const void* res, const void* res2, void* out, void* out_relu) {
+    GemmOp op;
+    op.M = S * S, op.N = Cout, op.K = 9 * Cin, op.A = in, op.a_mode = A_CONV3X3, op.B = 1, op.H = S, op.W = S, op.C = Cin;
+    op.Wt = W(wname), op.bias = bias, op.act = act, op.res = res, op.res2 = res2, op.ldres = Cout;
+    op.out = out, op.out_relu = out_relu, op.ldo = Cout;
+    gemm(prec_, op, s);
+  };
+
+  // ---- encoder.py:314-324: project + upsample every level
+  conv1x1(lat0m, 96, EMB, "encoder.upsample_latent0.0.weight", 256, u0a_, nullptr);
+  convT(u0a_, 96, 256, "encoder.upsample_latent0.1.weight", 256, u0b_, 256, 0, nullptr, nullptr);
+  convT(u0b_, 192, 256, "encoder.upsample_latent0.2.weight", 256, u0c_, 256, 0, nullptr, nullptr);
+  convT(u0c_, 384, 256, "encoder.upsample_latent0.3.weight", 256, enc0_, 256, 0, nullptr, enc0r_);
+  conv1x1(lat1m, 96, EMB, "encoder.upsample_latent1.0.weight", 256, u1a_, nullptr);
+  convT(u1a_, 96, 256, "encoder.upsample_latent1.1.weight", 256, u1b_, 256, 0, nullptr, nullptr);
+  convT(u1b_, 192, 256, "encoder.upsample_latent1.2.weight", 256, enc1_, 256, 0, nullptr, nullptr);
+  conv1x1(x0m, 96, EMB, "encoder.upsample0.0.weight", 512, u2a_, nullptr);
+  convT(u2a_, 96, 512, "encoder.upsample0.1.weight", 512, enc2_, 512, 0, nullptr, nullptr);
+  conv1x1(x1m, 48, EMB, "encoder.upsample1.0.weight", 1024, u3a_, nullptr);
+  convT(u3a_, 48, 1024, "encoder.upsample1.1.weight", 1024, enc3_, 1024, 0, nullptr, nullptr);
+  conv1x1(x2m, 24, EMB, "encoder.upsample2.0.weight", 1024, u4a_, nullptr);
+  // torch.cat((x2_features, x_global_features), dim=1): both ConvT outputs land in one 2048-wide map
+  convT(u4a_, 24, 1024, "encoder.upsample2.1.weight", 1024, cat_, 2048, 0, nullptr, nullptr);
+  convT(globm, 24, EMB, "encoder.upsample_lowres.weight", 1024, cat_, 2048, 1024, F("encoder.upsample_lowres.bias"), nullptr);
+  conv1x1(cat_, 48, 2048, "encoder.fuse_lowres.weight", 1024, enc4_, F("encoder.fuse_lowres.bias"));
+
+  // ---- decoder.py:74-93
+  conv3x3(enc4_, 48, 1024, "decoder.convs.4.weight", 256, nullptr, ACT_NONE, nullptr, nullptr, lowres_, lowres_r_);
+  const int S_of[5] = {768, 384, 192, 96, 48};
+  const void* encs[5] = {enc0_, enc1_, enc2_, enc3_, enc4_};
+  const int C_of[5] = {256, 256, 512, 1024, 1024};
+  for (int i = 4; i >= 0; --i) {
+    const int S = S_of[i];
+    const std::string p = "decoder.fusions." + std::to_string(i) + ".";
+    const void *xin, *xin_r;
+    if (i == 4) {
+      xin = lowres_, xin_r = lowres_r_;  // fusions[-1](features): no skip input, resnet1 unused (decoder.py:89)
+    } else {
+      const void *a, *a_r;
+      if (i == 0) {
+        a = enc0_, a_r = enc0r_;  // convs[0] is Identity (decoder.py:38-42)
+      } else {
+        conv3x3(encs[i], S, C_of[i], "decoder.convs." + std::to_string(i) + ".weight", 256, nullptr, ACT_NONE, nullptr,
+                nullptr, x1_, x1r_);
+        a = x1_, a_r = x1r_;
+      }
+      // x = x0 + resnet1(x1)   (decoder.py:170-172, 111-118)
+      conv3x3(a_r, S, 256, p + "resnet1.residual.1.weight", 256, F(p + "resnet1.residual.1.bias"), ACT_RELU, nullptr,
+              nullptr, t_, nullptr);
+      conv3x3(t_, S, 256, p + "resnet1.residual.3.weight", 256, F(p + "resnet1.residual.3.bias"), ACT_NONE, a,
+              feat_[i + 1], x_, xr_);
+      xin = x_, xin_r = xr_;
+    }
+    // x = resnet2(x)
+    conv3x3(xin_r, S, 256, p + "resnet2.residual.1.weight", 256, F(p + "resnet2.residual.1.bias"), ACT_RELU, nullptr,
+            nullptr, t_, nullptr);
+    conv3x3(t_, S, 256, p + "resnet2.residual.3.weight", 256, F(p + "resnet2.residual.3.bias"), ACT_NONE, xin, nullptr,
+            x2_, nullptr);
+    if (i != 0) {
+      convT(x2_, S, 256, p + "deconv.weight", 256, y_, 256, 0, nullptr, nullptr);
+      conv1x1(y_, 2 * S, 256, p + "out_conv.weight", 256, feat_[i], F(p + "out_conv.bias"));
+    } else {
+      conv1x1(x2_, S, 256, p + "out_conv.weight", 256, feat_[0], F(p + "out_conv.bias"));
+    }
+  }
+
+  // ---- depth head (depth_pro.py:182-204)
+  conv3x3(feat_[0], 768, 256, "head.0.weight", 128, F("head.0.bias"), ACT_NONE, nullptr, nullptr, h0_, nullptr);
+  convT(h0_, 768, 128, "head.1.weight", 128, h1_, 128, 0, F("head.1.bias"), nullptr);
+  {
+    GemmOp op;
+    op.M = IMG * IMG, op.N = 32, op.K = 9 * 128, op.A = h1_, op.a_mode = A_CONV3X3, op.B = 1, op.H = IMG, op.W = IMG, op.C = 128;
+    op.Wt = W("head.2.weight"), op.bias = F("head.2.bias"), op.act = ACT_RELU;
+    op.out = canon, op.out_f32 = 1, op.out_mode = O_DOT_RELU, op.dot_w = F("head.4.weight"), op.dot_b = F("head.4.bias");
+    gemm(prec_, op, s);
+  }
+
+  // ---- FOV head (fov.py:56-82)
+  {
+    GemmOp op;  // Linear 1024 -> 128 on the 576 non-cls tokens (cls is dropped at fov.py:77)
+    op.M = 576, op.N = 128, op.K = EMB, op.A = fovtok, op.lda = EMB, op.Wt = W("fov.encoder.1.weight");
+    op.bias = F("fov.encoder.1.bias"), op.out = fovlin_, op.ldo = 128;
+    gemm(prec_, op, s);
+  }
+  conv_direct<T>((const T*)lowres_, F("fov.downsample.0.weight"), F("fov.downsample.0.bias"), (T*)fov_a_, 1, 48, 48, 256,
+                 128, 3, 2, 1, 1, (const T*)fovlin_, s);
+  conv_direct<T>((const T*)fov_a_, F("fov.head.0.weight"), F("fov.head.0.bias"), (T*)fov_b_, 1, 24, 24, 128, 64, 3, 2, 1, 1,
+                 nullptr, s);
+  conv_direct<T>((const T*)fov_b_, F("fov.head.2.weight"), F("fov.head.2.bias"), (T*)fov_c_, 1, 12, 12, 64, 32, 3, 2, 1, 1,
+                 nullptr, s);
+  fov_final<T>((const T*)fov_c_, F("fov.head.4.weight"), F("fov.head.4.bias"), fov_deg, 1, s);
+}
+
+void Engine::forward(const float* x, int B, float* canon, float* fov_deg, cudaStream_t s) {
+  DP_CHECK(finalized_, "dp_engine_finalize has not been called");
+  DP_CHECK(B >= 1 && B <= max_batch_, "batch exceeds max_batch");
+  DP_CUDA(cudaSetDevice(device_));
+  if (prec_ == BF16) forward_impl<bf16>(x, B, canon, fov_deg, s);
+  else forward_impl<float>(x, B, canon, fov_deg, s);
+}
+
+void Engine::infer(const void* img, int B, int H, int W, int src_fmt, const float* f_px_host, float* depth,
+                   float* f_px_out, cudaStream_t s) {
+  DP_CHECK(finalized_, "dp_engine_finalize has not been called");
+  DP_CHECK(B >= 1 && B <= max_batch_, "batch exceeds max_batch");
+  DP_CUDA(cudaSetDevice(device_));
+  const float* x = xbuf_;
+  if (src_fmt == 0 && H == IMG && W == IMG) x = reinterpret_cast<const float*>(img);  // already at network resolution
+  else preprocess(img, B, H, W, src_fmt, xbuf_, s);
+  forward(x, B, canon_, fov_, s);
+  const float* fin = nullptr;
+  if (f_px_host) {
+    DP_CUDA(cudaMemcpyAsync(fpx_in_, f_px_host, B * 4, cudaMemcpyHostToDevice, s));
+    fin = fpx_in_;
+  }
+  compute_fpx(fov_, fin, W, f_px_out ? f_px_out : fpx_, B, s);
+  depth_epilogue(canon_, f_px_out ? f_px_out : fpx_, B, H, W, depth, s);
+}
+
+void Engine::infer_host(const void* img_host, int B, int H, int W, int src_fmt, const float* f_px_host, float* depth_host,
+                        float* f_px_out_host) {
+  DP_CUDA(cudaSetDevice(device_));
+  const size_t in_bytes = static_cast<size_t>(B) * H * W * 3 * (src_fmt == 1 ? 1 : 4);
+  const size_t out_bytes = static_cast<size_t>(B) * H * W * 4;
+  if (himg_bytes_ < in_bytes) {
+    if (himg_) DP_CUDA(cudaFree(himg_));
+    DP_CUDA(cudaMalloc(&himg_, in_bytes));
+    himg_bytes_ = in_bytes;
+  }
+  if (hdepth_bytes_ < out_bytes) {
+    if (hdepth_) DP_CUDA(cudaFree(hdepth_));
+    DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&hdepth_), out_bytes));
+    hdepth_bytes_ = out_bytes;
+  }
+  cudaStream_t s = host_stream_;
+  DP_CUDA(cudaMemcpyAsync(himg_, img_host, in_bytes, cudaMemcpyHostToDevice, s));
+  infer(himg_, B, H, W, src_fmt, f_px_host, hdepth_, fpx_, s);
+  DP_CUDA(cudaMemcpyAsync(depth_host, hdepth_, out_bytes, cudaMemcpyDeviceToHost, s));
+  if (f_px_out_host) DP_CUDA(cudaMemcpyAsync(f_px_out_host, fpx_, B * 4, cudaMemcpyDeviceToHost, s));
+  DP_CUDA(cudaStreamSynchronize(s));
+}
+
+void Engine::unproject(const float* depth, const uint8_t* rgb, int H, int W, const float* f_px_dev, float* xyz,
+                       float* rgb_out, uint8_t* valid_mask, int64_t* n_valid, cudaStream_t s) {
+  DP_CUDA(cudaSetDevice(device_));
+  const size_t need = unproject_scratch_ints(H, W);
+  if (unproject_scratch_ints_ < need) {
+    unproject_scratch_ = (int*)alloc(need * 4);
+    unproject_scratch_ints_ = need;
+  }
+  dp::unproject(depth, rgb, H, W, f_px_dev, xyz, rgb_out, valid_mask, n_valid, unproject_scratch_, s);
+}
+
+void Engine::colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, cudaStream_t s) {
+  DP_CUDA(cudaSetDevice(device_));
+  if (!colorize_mm_) colorize_mm_ = (float*)alloc(64);
+  dp::colorize(depth, H, W, lut, out, colorize_mm_, s);
+}
+
+// ============================================================================ taps
+template <typename T>
+int64_t Engine::tap_impl(const std::string& stage, float* out, int64_t capacity, cudaStream_t s) {
+  struct Map { const char* name; void* ptr; int S, C; bool batched; };
+  const Map maps[] = {
+      {"lat0_merged", lat0m_, 96, EMB, true}, {"lat1_merged", lat1m_, 96, EMB, true}, {"x0_merged", x0m_, 96, EMB, true},
+      {"x1_merged", x1m_, 48, EMB, true},     {"x2_tokens", x2m_, 24, EMB, true},     {"global_tokens", globm_, 24, EMB, true},
+      {"enc0", enc0_, 768, 256, false},       {"enc1", enc1_, 384, 256, false},       {"enc2", enc2_, 192, 512, false},
+      {"enc3", enc3_, 96, 1024, false},       {"enc4", enc4_, 48, 1024, false},       {"lowres", lowres_, 48, 256, false},
+      {"decoder_out", feat_[0], 768, 256, false},
+  };
+  for (const Map& m : maps) {
+    if (stage == m.name) {
+      const int B = m.batched ? last_B_ : 1;
+      const int64_t n = static_cast<int64_t>(B) * m.S * m.S * m.C;
+      DP_CHECK(n <= capacity, "tap buffer too small");
+      nhwc_to_nchw_f32<T>((const T*)m.ptr, out, B, m.S, m.S, m.C, s);
+      return n;
+    }
+  }
+  throw Error("unknown tap stage: " + stage);
+}
+
+int64_t Engine::tap(const std::string& stage, float* out, int64_t capacity, cudaStream_t s) {
+  DP_CHECK(finalized_ && last_B_ > 0, "dp_tap needs a previous dp_forward");
+  DP_CUDA(cudaSetDevice(device_));
+  return prec_ == BF16 ? tap_impl<bf16>(stage, out, capacity, s) : tap_impl<float>(stage, out, capacity, s);
+}
+
+// ============================================================================ unit-test entries
+namespace {
+template <typename T>
+T* to_dev(const float* src, size_t n, cudaStream_t s) {
+  T* p = nullptr;
+  DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), s));
+  convert<float, T>(src, p, (long long)n, s);
+  return p;
+}
+}  // namespace
+
+void Engine::gemm_test(int backend, const float* A, const float* Wt, const float* bias, float* C, int M, int N, int K,
+                       int act, cudaStream_t s) {
+  DP_CUDA(cudaSetDevice(device_));
+  GemmOp op;
+  op.M = M, op.N = N, op.K = K, op.lda = K, op.bias = bias, op.act = act, op.out = C, op.out_f32 = 1, op.ldo = N;
+  if (backend == BF16) {
+    bf16* a = to_dev<bf16>(A, (size_t)M * K, s);
+    bf16* w = to_dev<bf16>(Wt, (size_t)N * K, s);
+    op.A = a, op.Wt = w;
+    gemm_tc(op, s);
+    DP_CUDA(cudaFreeAsync(a, s));
+    DP_CUDA(cudaFreeAsync(w, s));
+    DP_CUDA(cudaStreamSynchronize(s));
+    tmap_cache_clear();  // the temporaries' tensor maps must not be reused
+  } else {
+    op.A = A, op.Wt = Wt;
+    gemm_simt(op, s);
+  }
+}
+
+void Engine::conv3x3_test(int backend, const float* x, const float* w, const float* bias, float* y, int B, int H, int W_,
+                          int Cin, int Cout, cudaStream_t s) {
+  DP_CUDA(cudaSetDevice(device_));
+  GemmOp op;
+  op.M = B * H * W_, op.N = Cout, op.K = 9 * Cin, op.a_mode = A_CONV3X3, op.B = B, op.H = H, op.W = W_, op.C = Cin;
+  op.bias = bias, op.out = y, op.out_f32 = 1, op.ldo = Cout;
+  const size_t nw = (size_t)Cout * Cin * 9;
+  if (backend == BF16) {
+    bf16* a = to_dev<bf16>(x, (size_t)B * H * W_ * Cin, s);
+    bf16* wp = nullptr;
+    DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wp), nw * 2, s));
+    pack_oihw_to_ohwi<bf16>(w, wp, Cout, Cin, 3, 3, s);
+    op.A = a, op.Wt = wp;
+    gemm_tc(op, s);
+    DP_CUDA(cudaFreeAsync(a, s));
+    DP_CUDA(cudaFreeAsync(wp, s));
+    DP_CUDA(cudaStreamSynchronize(s));
+    tmap_cache_clear();
+  } else {
+    float* wp = nullptr;
+    DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wp), nw * 4, s));
+    pack_oihw_to_ohwi<float>(w, wp, Cout, Cin, 3, 3, s);
+    op.A = x, op.Wt = wp;
+    gemm_simt(op, s);
+    DP_CUDA(cudaFreeAsync(wp, s));
+  }
+}
+
+void Engine::attention_test(int backend, const float* qkv, float* out, int n, cudaStream_t s) {
+  DP_CUDA(cudaSetDevice(device_));
+  if (backend == BF16) {
+    const size_t nq = (size_t)n * SEQ * 3 * EMB, no = (size_t)n * SEQ * EMB;
+    bf16* q = to_dev<bf16>(qkv, nq, s);
+    bf16* o = nullptr;
+    DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&o), no * 2, s));
+    attention_bf16(q, o, n, s);
+    convert<bf16, float>(o, out, (long long)no, s);
+    DP_CUDA(cudaFreeAsync(q, s));
+    DP_CUDA(cudaFreeAsync(o, s));
+  } else {
+    attention_f32(qkv, out, n, s);
+  }
+}
+
+}  // namespace dp

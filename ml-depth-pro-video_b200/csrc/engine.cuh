@@ -1,0 +1,114 @@
+// Depth Pro engine: owns packed weights + workspace of one GPU and runs the forward graph
+// (src/depth_pro/depth_pro.py:218-298 of the reference) as a fixed sequence of kernel launches.
+#pragma once
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace dp {
+
+struct VitWeights {
+  const float *cls, *pos, *pe_b, *norm_w, *norm_b;
+  const void* pe_w;
+  struct Block {
+    const float *n1w, *n1b, *qkv_b, *proj_b, *g1, *n2w, *n2b, *fc1_b, *fc2_b, *g2;
+    const void *qkv_w, *proj_w, *fc1_w, *fc2_w;
+  } blk[24];
+};
+
+struct Packed {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+class Engine {
+ public:
+  Engine(int device, int prec, int max_batch);
+  ~Engine();
+
+  void set_weight(const std::string& name, const void* data, const int64_t* shape, int ndim, bool on_device);
+  int missing_weights() const;
+  void finalize();
+
+  void preprocess(const void* img, int B, int H, int W, int src_fmt, float* x, cudaStream_t s);
+  void split(const float* x, int B, float* patches, cudaStream_t s);
+  void merge(const float* tokens, int B, int steps, int padding, int C, float* merged, cudaStream_t s);
+  void forward(const float* x, int B, float* canon, float* fov_deg, cudaStream_t s);
+  void infer(const void* img, int B, int H, int W, int src_fmt, const float* f_px_host, float* depth, float* f_px_out,
+             cudaStream_t s);
+  void infer_host(const void* img_host, int B, int H, int W, int src_fmt, const float* f_px_host, float* depth_host,
+                  float* f_px_out_host);
+  void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float* f_px_dev, float* xyz, float* rgb_out,
+                 uint8_t* valid_mask, int64_t* n_valid, cudaStream_t s);
+  void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, cudaStream_t s);
+  int64_t tap(const std::string& stage, float* out, int64_t capacity, cudaStream_t s);
+
+  void gemm_test(int backend, const float* A, const float* Wt, const float* bias, float* C, int M, int N, int K, int act,
+                 cudaStream_t s);
+  void conv3x3_test(int backend, const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
+                    int Cout, cudaStream_t s);
+  void attention_test(int backend, const float* qkv, float* out, int n, cudaStream_t s);
+
+  int device() const { return device_; }
+  int prec() const { return prec_; }
+
+ private:
+  template <typename T>
+  void forward_impl(const float* x, int B, float* canon, float* fov_deg, cudaStream_t s);
+  template <typename T>
+  void run_vit(const VitWeights& w, const T* A, int nseq, float* resid, T* xn, T* qkv, T* attn, T* hid, bool hooks, int B,
+               cudaStream_t s);
+  template <typename T>
+  void decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s);
+  template <typename T>
+  int64_t tap_impl(const std::string& stage, float* out, int64_t capacity, cudaStream_t s);
+
+  void* alloc(size_t bytes);
+  const void* W(const std::string& name) const;   // packed weight (activation dtype)
+  const float* F(const std::string& name) const;  // packed fp32 tensor
+  VitWeights vit_weights(const std::string& prefix) const;
+  size_t esz() const { return prec_ == BF16 ? 2 : 4; }
+
+  int device_, prec_, max_batch_;
+  bool finalized_ = false;
+  std::map<std::string, std::vector<int64_t>> manifest_;
+  std::unordered_map<std::string, Packed> packed_;
+  std::vector<void*> allocs_;
+  float* stage_ = nullptr;  // staging buffer for host -> device weight upload
+  size_t stage_bytes_ = 0;
+
+  VitWeights vit_patch_, vit_image_, vit_fov_;
+
+  // ---- workspace (activation dtype unless noted)
+  float* xbuf_ = nullptr;      // (max_batch,3,1536,1536) f32
+  float* canon_ = nullptr;     // (max_batch,1536,1536) f32
+  float* fov_ = nullptr;       // (max_batch) f32
+  float* fpx_ = nullptr;       // (max_batch) f32
+  float* fpx_in_ = nullptr;    // (max_batch) f32
+  void *A35_, *A1_;
+  float *resid_, *resid_s_;    // residual streams f32 (patch encoder; small encoders)
+  void *xn_, *qkv_, *attn_, *hid_;
+  void *xn_s_, *qkv_s_, *attn_s_, *hid_s_;
+  void *lat0m_, *lat1m_, *x0m_, *x1m_, *x2m_, *globm_, *fovtok_;  // merged maps (max_batch frames)
+  // per-frame decoder workspace
+  void *u0a_, *u0b_, *u0c_, *enc0_, *enc0r_, *u1a_, *u1b_, *enc1_, *u2a_, *enc2_, *u3a_, *enc3_, *u4a_, *cat_, *enc4_;
+  void *lowres_, *lowres_r_, *x1_, *x1r_, *t_, *x_, *xr_, *x2_, *y_, *feat_[5];
+  void *h0_, *h1_;
+  void *fovlin_, *fov_a_, *fov_b_, *fov_c_;
+  int last_B_ = 0;
+  // host-call staging
+  void* himg_ = nullptr;
+  size_t himg_bytes_ = 0;
+  float* hdepth_ = nullptr;
+  size_t hdepth_bytes_ = 0;
+  float* colorize_mm_ = nullptr;
+  int* unproject_scratch_ = nullptr;
+  size_t unproject_scratch_ints_ = 0;
+  cudaStream_t host_stream_ = nullptr;
+};
+
+}  // namespace dp

@@ -245,7 +245,7 @@ __global__ void conv_direct_kernel(const T* __restrict__ x, const float* __restr
     for (int e = 0; e < nel; ++e) acc = fmaf(patch[e], w[static_cast<long long>(e) * Cout + co], acc);
     acc += bias[co];
     if (relu) acc = fmaxf(acc, 0.f);
-    if (add_tokens) acc += to_f(add_tokens[(static_cast<long long>(b) * 577 + 1 + oy * Wo + ox) * Cout + co]);
+    if (add_tokens) acc += to_f(add_tokens[static_cast<long long>(o) * Cout + co]);
     y[static_cast<long long>(o) * Cout + co] = from_f<T>(acc);
   }
 }

@@ -41,7 +41,7 @@ void merge_rows_f32(const float* in, float* out, int B, int C, RowMap map, cudaS
 
 // ---- small direct convolution (FOV head) ------------------------------------------------
 // NHWC in (B,H,W,Cin) of type T, weights HWIO fp32 (k,k,Cin,Cout), out NHWC (B,Ho,Wo,Cout) of T.
-// v = conv + bias; relu optional; then + addend (tokens (B,577,Cout) skipping cls if add_tokens).
+// v = conv + bias; relu optional; then + add_tokens (same NHWC layout as y) if not null.
 template <typename T>
 void conv_direct(const T* x, const float* w_hwio, const float* bias, T* y, int B, int H, int W, int Cin,
                  int Cout, int k, int stride, int pad, int relu, const T* add_tokens, cudaStream_t s);

@@ -1,0 +1,71 @@
+"""ctypes binding of libdepthpro_b200.so (C-ABI declared in include/depthpro_b200.h).
+
+The library is built in-tree by ``ml-depth-pro-video_b200/build.py`` (nvcc, sm_100a).  There is
+no fallback: if it is missing or no B200 is visible, the product path raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdepthpro_b200.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+SRC_F32_CHW, SRC_U8_HWC = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+
+# name -> (restype, argtypes); mirrors include/depthpro_b200.h one to one
+SIGNATURES = {
+    "dp_last_error": (C.c_char_p, []),
+    "dp_version": (_i, []),
+    "dp_engine_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),
+    "dp_engine_destroy": (_i, [_vp]),
+    "dp_engine_set_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _i]),
+    "dp_engine_missing_weights": (_i, [_vp]),
+    "dp_engine_finalize": (_i, [_vp]),
+    "dp_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "dp_split": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "dp_merge": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "dp_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "dp_infer": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dp_infer_host": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "dp_unproject": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dp_colorize": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "dp_tap": (_i, [_vp, C.c_char_p, _vp, _i64, C.POINTER(_i64), _vp]),
+    "dp_gemm_test": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "dp_conv3x3_test": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dp_attention_test": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
+    "dp_launch_count": (_i64, [_vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python ml-depth-pro-video_b200/build.py` "
+                "(there is no CPU / PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError("depthpro_b200: " + load().dp_last_error().decode(errors="replace"))
+
+
+def ptr(t) -> int:
+    """Device / host pointer of a tensor, or NULL for None."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,273 @@
+"""Drop-in replacement for the reference's ``depth_pro.depth_pro`` module.
+
+Same public surface as ``/root/reference/src/depth_pro/depth_pro.py``:
+``DepthProConfig`` (:26-36), ``DEFAULT_MONODEPTH_CONFIG_DICT`` (:39-46),
+``create_model_and_transforms(config, device, precision) -> (model, transform)`` (:72-151) and
+``DepthPro`` with ``.img_size`` (:213-216), ``.forward(x)`` (:218-241), ``.infer(x, f_px,
+interpolation_mode)`` (:243-298), ``.eval()``, ``.state_dict()`` / ``.load_state_dict()`` with the
+reference's key names.  All compute runs in the sm_100a engine behind the C-ABI
+(``include/depthpro_b200.h``); there is no PyTorch / CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import logging
+from dataclasses import dataclass
+from typing import Mapping, Optional, Tuple, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _capi, weights
+
+LOGGER = logging.getLogger(__name__)
+
+ViTPreset = str
+_PRESETS = ("dinov2l16_384",)
+IMG_SIZE = 1536
+
+
+@dataclass
+class DepthProConfig:
+    """Configuration for DepthPro (same fields as the reference's dataclass)."""
+
+    patch_encoder_preset: ViTPreset
+    image_encoder_preset: ViTPreset
+    decoder_features: int
+
+    checkpoint_uri: Optional[str] = None
+    fov_encoder_preset: Optional[ViTPreset] = None
+    use_fov_head: bool = True
+
+
+DEFAULT_MONODEPTH_CONFIG_DICT = DepthProConfig(
+    patch_encoder_preset="dinov2l16_384",
+    image_encoder_preset="dinov2l16_384",
+    checkpoint_uri="./checkpoints/depth_pro.pt",
+    decoder_features=256,
+    use_fov_head=True,
+    fov_encoder_preset="dinov2l16_384",
+)
+
+
+class _Node(nn.Module):
+    """Parameter container; the tree of _Nodes reproduces the reference's module names."""
+
+
+def _precision_code(precision: torch.dtype) -> int:
+    if precision == torch.float32:
+        return _capi.PREC_FP32
+    if precision in (torch.bfloat16, torch.float16):
+        if precision == torch.float16:
+            LOGGER.warning("float16 requested: the B200 engine's reduced-precision mode is bfloat16 "
+                           "(fp32 accumulate); running that.")
+        return _capi.PREC_BF16
+    raise ValueError(f"unsupported precision {precision}; use torch.float32 or torch.bfloat16")
+
+
+class DepthPro(nn.Module):
+    """Depth Pro network backed by the B200 engine."""
+
+    def __init__(self, device: torch.device, precision: torch.dtype = torch.float32, max_batch: int = 1):
+        super().__init__()
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(
+                f"depth_pro (B200 engine) needs a CUDA device, got '{device}': there is no CPU fallback")
+        if not torch.cuda.is_available():
+            raise RuntimeError("depth_pro (B200 engine): no CUDA device is visible; there is no CPU fallback")
+        self._device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        self._precision = precision
+        self._prec_code = _precision_code(precision)
+        self._max_batch = int(max_batch)
+        self._engine = None
+        self._dirty = True
+        for name, shape in weights.manifest().items():
+            node: nn.Module = self
+            parts = name.split(".")
+            for p in parts[:-1]:
+                if not hasattr(node, p):
+                    node.add_module(p, _Node())
+                node = getattr(node, p)
+            node.register_parameter(
+                parts[-1], nn.Parameter(torch.empty(shape, dtype=torch.float32, device=self._device),
+                                        requires_grad=False))
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._mark_dirty())
+
+    # ------------------------------------------------------------------ weights / engine
+    def _mark_dirty(self):
+        self._dirty = True
+
+    def init_weights(self, recipe: str = "stress", seed: int = 1234) -> "DepthPro":
+        """Seeded random init (no checkpoint offline): 'stress' = recipe B, 'reference' = the
+        reference's own (degenerate) distributions.  See weights.py."""
+        fn = {"stress": weights.stress_tensor, "reference": weights.reference_like_tensor}[recipe]
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                p.copy_(fn(name, tuple(p.shape), seed))
+        self._dirty = True
+        return self
+
+    def _ensure_engine(self, batch: int):
+        lib = _capi.load()
+        if self._engine is not None and batch > self._max_batch:
+            _capi.check(lib.dp_engine_destroy(self._engine))
+            self._engine = None
+        if self._engine is None:
+            self._max_batch = max(self._max_batch, batch)
+            h = ctypes.c_void_p()
+            _capi.check(lib.dp_engine_create(self._device.index, self._prec_code, self._max_batch, ctypes.byref(h)))
+            self._engine = h
+            self._dirty = True
+        if self._dirty:
+            torch.cuda.synchronize(self._device)
+            for name, p in self.named_parameters():
+                t = p.detach()
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.float().contiguous()
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
+                _capi.check(lib.dp_engine_set_weight(self._engine, name.encode(), t.data_ptr(), shape, t.dim(),
+                                                     1 if t.is_cuda else 0))
+            _capi.check(lib.dp_engine_finalize(self._engine))
+            self._dirty = False
+        return lib
+
+    def __del__(self):
+        try:
+            if getattr(self, "_engine", None) is not None:
+                _capi.load().dp_engine_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self._device).cuda_stream
+
+    # ------------------------------------------------------------------ reference API
+    @property
+    def img_size(self) -> int:
+        """Internal image size of the network (depth_pro.py:213-216)."""
+        return IMG_SIZE
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """(B,3,1536,1536) -> (canonical inverse depth (B,1,1536,1536), fov_deg (B,1,1,1))."""
+        _, _, H, W = x.shape
+        assert H == self.img_size and W == self.img_size
+        x = x.to(device=self._device, dtype=torch.float32).contiguous()
+        B = x.shape[0]
+        lib = self._ensure_engine(B)
+        canon = torch.empty((B, 1, IMG_SIZE, IMG_SIZE), dtype=torch.float32, device=self._device)
+        fov = torch.empty((B, 1, 1, 1), dtype=torch.float32, device=self._device)
+        with torch.cuda.device(self._device):
+            _capi.check(lib.dp_forward(self._engine, x.data_ptr(), B, canon.data_ptr(), fov.data_ptr(), self._stream()))
+        return canon, fov
+
+    @torch.no_grad()
+    def infer(self, x: torch.Tensor, f_px: Optional[Union[float, torch.Tensor]] = None,
+              interpolation_mode="bilinear") -> Mapping[str, torch.Tensor]:
+        """Depth [m] and focal length [px] for an image (depth_pro.py:243-298).
+
+        ``x`` is the reference's transformed tensor (float CHW / BCHW in [-1,1]); additionally a
+        uint8 HWC / BHWC tensor or ndarray straight from ``load_rgb`` is accepted, in which case
+        ToTensor + Normalize are fused into the resize kernel.
+        """
+        if interpolation_mode != "bilinear":
+            raise NotImplementedError("the B200 engine implements interpolation_mode='bilinear' only")
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        u8 = x.dtype == torch.uint8
+        if len(x.shape) == 3:
+            x = x.unsqueeze(0)
+        if u8:
+            B, H, W, ch = x.shape
+            assert ch == 3, "uint8 input must be HWC with 3 channels"
+            x = x.to(self._device).contiguous()
+            fmt = _capi.SRC_U8_HWC
+        else:
+            B, ch, H, W = x.shape
+            assert ch == 3
+            x = x.to(device=self._device, dtype=torch.float32).contiguous()
+            fmt = _capi.SRC_F32_CHW
+        lib = self._ensure_engine(B)
+        depth = torch.empty((B, H, W), dtype=torch.float32, device=self._device)
+        f_out = torch.empty((B,), dtype=torch.float32, device=self._device)
+        f_host = None
+        if f_px is not None:
+            f_t = torch.as_tensor(f_px).detach().to("cpu", torch.float32).reshape(-1)
+            if f_t.numel() == 1:
+                f_t = f_t.expand(B)
+            assert f_t.numel() == B, "f_px must be a scalar or one value per image"
+            f_host = f_t.contiguous()
+        with torch.cuda.device(self._device):
+            _capi.check(lib.dp_infer(self._engine, x.data_ptr(), B, H, W, fmt,
+                                     None if f_host is None else f_host.data_ptr(),
+                                     depth.data_ptr(), f_out.data_ptr(), self._stream()))
+        if f_px is None:
+            focal = f_out.squeeze()
+        else:
+            focal = f_px.squeeze() if torch.is_tensor(f_px) else torch.as_tensor(np.asarray(f_px)).squeeze()
+        return {"depth": depth.squeeze(), "focallength_px": focal}
+
+    # ------------------------------------------------------------------ engine-level extras
+    def tap(self, stage: str) -> torch.Tensor:
+        """Stage tensor of the last forward as float32 in the reference's NCHW layout (tests)."""
+        lib = self._ensure_engine(1)
+        cap = 768 * 768 * 256 * max(1, self._max_batch)
+        out = torch.empty(cap, dtype=torch.float32, device=self._device)
+        n = ctypes.c_int64()
+        _capi.check(lib.dp_tap(self._engine, stage.encode(), out.data_ptr(), cap, ctypes.byref(n), self._stream()))
+        return out[: n.value]
+
+    def launch_count(self) -> int:
+        return int(_capi.load().dp_launch_count(self._engine))
+
+
+def create_backbone_model(preset: ViTPreset):
+    """Kept for signature compatibility (depth_pro.py:49-69): validates the preset only."""
+    if preset not in _PRESETS:
+        raise KeyError(f"Preset {preset} not found.")
+    return None, preset
+
+
+def create_model_and_transforms(
+    config: DepthProConfig = DEFAULT_MONODEPTH_CONFIG_DICT,
+    device: torch.device = torch.device("cpu"),
+    precision: torch.dtype = torch.float32,
+):
+    """Create a DepthPro model and load weights from ``config.checkpoint_uri`` (depth_pro.py:72-151).
+
+    ``device`` must be a CUDA device (B200).  With ``checkpoint_uri=None`` the parameters get the
+    reference's (degenerate) random-init distributions; call ``model.init_weights('stress')`` for
+    the conditioned recipe used by the parity tests and the benchmark.
+    """
+    from torchvision.transforms import Compose, ConvertImageDtype, Lambda, Normalize, ToTensor
+
+    for preset in (config.patch_encoder_preset, config.image_encoder_preset):
+        create_backbone_model(preset)
+    if not (config.use_fov_head and config.fov_encoder_preset is not None):
+        raise NotImplementedError("the B200 engine implements the default config (FOV head with its own encoder)")
+    create_backbone_model(config.fov_encoder_preset)
+    if config.decoder_features != 256:
+        raise NotImplementedError("the B200 engine implements decoder_features=256")
+
+    model = DepthPro(device=device, precision=precision)
+    transform = Compose([
+        ToTensor(),
+        Lambda(lambda x: x.to(device)),
+        Normalize([0.5, 0.5, 0.5], [0.5, 0.5, 0.5]),
+        ConvertImageDtype(torch.float32),  # the engine takes fp32 input in every precision mode
+    ])
+
+    if config.checkpoint_uri is not None:
+        state_dict = torch.load(config.checkpoint_uri, map_location="cpu")
+        missing_keys, unexpected_keys = model.load_state_dict(state_dict=state_dict, strict=True)
+        if len(unexpected_keys) != 0:
+            raise KeyError(f"Found unexpected keys when loading monodepth: {unexpected_keys}")
+        missing_keys = [key for key in missing_keys if "fc_norm" not in key]
+        if len(missing_keys) != 0:
+            raise KeyError(f"Keys are missing when loading monodepth: {missing_keys}")
+    else:
+        model.init_weights("reference", seed=0)
+    return model, transform

@@ -1,0 +1,100 @@
+"""-m gpu: GEMM / conv / attention cores through the C-ABI vs plain PyTorch fp32 references."""
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_common import engine, lib, relerr, stream
+from depth_pro import _capi
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _gemm(backend, A, W, bias, act):
+    M, K = A.shape
+    N = W.shape[0]
+    C = torch.empty(M, N, device=DEV)
+    _capi.check(lib().dp_gemm_test(engine(), backend, A.data_ptr(), W.data_ptr(),
+                                   None if bias is None else bias.data_ptr(), C.data_ptr(), M, N, K, act, stream()))
+    torch.cuda.synchronize()
+    return C
+
+
+def _ref_gemm(A, W, bias, act):
+    C = A.double() @ W.double().t()
+    if bias is not None:
+        C = C + bias.double()
+    if act == _capi.ACT_RELU:
+        C = F.relu(C)
+    elif act == _capi.ACT_GELU:
+        C = F.gelu(C)
+    return C
+
+
+@pytest.mark.parametrize("M,N,K,act", [(128, 128, 64, 0), (300, 384, 256, 2), (1155, 1024, 1024, 0), (577, 32, 1152, 1),
+                                       (20195, 3072, 1024, 0)])
+def test_gemm_fp32(M, N, K, act):
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    got = _gemm(0, A, W, b, act)
+    assert relerr(got, _ref_gemm(A, W, b, act)) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K,act", [(128, 256, 64, 0), (128, 128, 64, 0), (128, 32, 64, 0), (256, 256, 256, 0),
+                                       (300, 384, 256, 2), (1155, 1024, 1024, 1), (577, 32, 1152, 1),
+                                       (20195, 3072, 1024, 0), (20195, 1024, 4096, 0)])
+def test_gemm_bf16_tcgen05(M, N, K, act):
+    g = torch.Generator(device=DEV).manual_seed(M + N + 1)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    got = _gemm(1, A, W, b, act)
+    # the kernel rounds A and W to bf16 and accumulates in fp32: compare against exactly that
+    ref = _ref_gemm(A.bfloat16().float(), W.bfloat16().float(), b, act)
+    assert relerr(got, ref) < 2e-5
+
+
+def _conv(backend, x_nchw, w, bias):
+    B, Cin, H, W_ = x_nchw.shape
+    Cout = w.shape[0]
+    x = x_nchw.permute(0, 2, 3, 1).contiguous()
+    y = torch.empty(B, H, W_, Cout, device=DEV)
+    _capi.check(lib().dp_conv3x3_test(engine(), backend, x.data_ptr(), w.contiguous().data_ptr(),
+                                      None if bias is None else bias.data_ptr(), y.data_ptr(), B, H, W_, Cin, Cout,
+                                      stream()))
+    torch.cuda.synchronize()
+    return y.permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 128), (2, 24, 48, 128, 32), (1, 48, 48, 1024, 256),
+                                            (1, 96, 96, 256, 256)])
+def test_conv3x3(backend, B, H, W, Cin, Cout):
+    g = torch.Generator(device=DEV).manual_seed(H + Cin)
+    x = torch.randn(B, Cin, H, W, device=DEV, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device=DEV, generator=g)
+    got = _conv(backend, x, w, b)
+    if backend == 1:
+        ref = F.conv2d(x.bfloat16().double(), w.bfloat16().double(), b.double(), padding=1)
+        tol = 2e-5
+    else:
+        ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+        tol = 2e-6
+    assert relerr(got, ref) < tol
+
+
+@pytest.mark.parametrize("backend,n,tol", [(0, 2, 2e-6), (1, 3, 1.5e-2)])
+def test_attention(backend, n, tol):
+    g = torch.Generator(device=DEV).manual_seed(n)
+    qkv = torch.randn(n, 577, 3072, device=DEV, generator=g)
+    out = torch.empty(n, 577, 1024, device=DEV)
+    _capi.check(lib().dp_attention_test(engine(), backend, qkv.data_ptr(), out.data_ptr(), n, stream()))
+    torch.cuda.synchronize()
+    src = qkv.bfloat16().double() if backend == 1 else qkv.double()
+    q, k, v = src.reshape(n, 577, 3, 16, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n, 577, 1024)
+    assert relerr(out, ref) < tol

@@ -1,0 +1,167 @@
+"""-m gpu: HBM-bound kernels through the C-ABI vs the oracle (bit-exact indexing, <= 2 ulp resize)."""
+
+import ctypes
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import depthpro_oracle as O
+from gpu_common import engine, lib, stream
+from depth_pro import _capi
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _preprocess(img, fmt, B, H, W):
+    x = torch.empty(B, 3, 1536, 1536, device=DEV)
+    _capi.check(lib().dp_preprocess(engine(), img.data_ptr(), B, H, W, fmt, x.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    return x.cpu()
+
+
+def _ulp_err(a, b):
+    # error in units of the fp32 spacing at max(|b|, 2^-6) (inputs live in [-1, 1])
+    scale = torch.maximum(b.abs(), torch.tensor(2.0 ** -6))
+    ulp = 2.0 ** (torch.floor(torch.log2(scale)) - 23)
+    return float(((a - b).abs() / ulp).max())
+
+
+@pytest.mark.parametrize("H,W", [(1080, 1920), (2160, 3840), (384, 640), (1536, 1536), (1537, 1535)])
+def test_resize_f32(H, W):
+    g = torch.Generator().manual_seed(H * 7 + W)
+    x = torch.rand(1, 3, H, W, generator=g) * 2 - 1
+    ref = x if (H, W) == (1536, 1536) else F.interpolate(x, size=(1536, 1536), mode="bilinear", align_corners=False)
+    got = _preprocess(x.to(DEV), _capi.SRC_F32_CHW, 1, H, W)
+    assert _ulp_err(got, ref) <= 2.0
+
+
+def test_resize_u8_fused_transform():
+    frame = O.synthetic_frame_u8(3)
+    ref = F.interpolate(O.transform_u8(frame)[None], size=(1536, 1536), mode="bilinear", align_corners=False)
+    got = _preprocess(torch.from_numpy(frame).to(DEV), _capi.SRC_U8_HWC, 1, 1080, 1920)
+    assert _ulp_err(got, ref) <= 2.0
+    # batch of 2 frames
+    frames = np.stack([O.synthetic_frame_u8(0, 270, 480), O.synthetic_frame_u8(1, 270, 480)])
+    ref2 = F.interpolate(torch.stack([O.transform_u8(f) for f in frames]), size=(1536, 1536), mode="bilinear",
+                         align_corners=False)
+    got2 = _preprocess(torch.from_numpy(frames).to(DEV), _capi.SRC_U8_HWC, 2, 270, 480)
+    assert _ulp_err(got2, ref2) <= 2.0
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_split_bit_exact(B, golden_dir):
+    """pyramid + split + cat (encoder.py:151-188, 253-263): patches identical to the oracle's."""
+    x = torch.stack([O.synthetic_image_1536(seed=10 + b) for b in range(B)])
+    x0, x1, x2 = O.create_pyramid(x)
+    ref = torch.cat((O.split(x0, 0.25), O.split(x1, 0.5), x2), dim=0)
+    out = torch.empty(35 * B, 3, 384, 384, device=DEV)
+    _capi.check(lib().dp_split(engine(), x.to(DEV).data_ptr(), B, out.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    got = out.cpu()
+    # level 0 is pure indexing -> bit exact; levels 1/2 are exact closed forms of the bilinear pyramid
+    assert torch.equal(got[: 25 * B], ref[: 25 * B])
+    assert torch.equal(got, ref)
+
+
+def test_split_index_golden(golden_dir):
+    """Index-coded image through the CUDA split == the reference's own split (golden corners + digest)."""
+    gold = np.load(os.path.join(golden_dir, "split_merge_index.npz"))
+    # float32 represents integers < 2^24 exactly: encode (row, col) in two channels
+    ys, xs = torch.meshgrid(torch.arange(1536.0), torch.arange(1536.0), indexing="ij")
+    x = torch.stack([ys, xs, ys * 0])[None]
+    out = torch.empty(35, 3, 384, 384, device=DEV)
+    _capi.check(lib().dp_split(engine(), x.to(DEV).data_ptr(), 1, out.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    got = out.cpu()
+    flat = (got[:25, 0] * 1536 + got[:25, 1]).to(torch.int32)  # level-0 patches as flat indices
+    assert np.array_equal(flat[:, 0, 0].numpy(), gold["split_1536_corner"])
+    assert np.array_equal(flat[:, -1, -1].numpy(), gold["split_1536_last"])
+    digest = np.frombuffer(hashlib.sha256(flat[:, None].contiguous().numpy().tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(digest, gold["split_1536_sha256"])
+
+
+@pytest.mark.parametrize("steps,pad,B", [(5, 3, 1), (3, 6, 1), (5, 3, 2), (3, 6, 2), (1, 0, 2)])
+def test_merge_bit_exact(steps, pad, B, golden_dir):
+    """reshape_feature + merge (encoder.py:190-231) on index-coded tokens, vs oracle and golden."""
+    n = steps * steps * B
+    C = 8
+    tok = torch.arange(n * 577 * C, dtype=torch.float32).reshape(n, 577, C)
+    ref = O.merge(O.reshape_feature(tok), B, pad) if steps > 1 else O.reshape_feature(tok)
+    S = ref.shape[-1]
+    out = torch.empty(B, C, S, S, device=DEV)
+    _capi.check(lib().dp_merge(engine(), tok.to(DEV).data_ptr(), B, steps, pad, C, out.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref)
+    if steps > 1:
+        gold = np.load(os.path.join(golden_dir, "split_merge_index.npz"))
+        key = f"merge_{steps}x{steps}_pad{pad}" + ("_b2" if B == 2 else "")
+        # golden value = patch*576 + token (cls-free); ours = ((seq*577 + 1 + token)*C + c)
+        got_idx = (out.cpu()[:, 0] / C).to(torch.int64)
+        seq, t = got_idx // 577, got_idx % 577 - 1
+        mine = (seq * 576 + t).to(torch.int32).numpy()
+        assert np.array_equal(mine if B == 2 else mine[0], gold[key])
+
+
+def test_depth_to_3d_golden(golden_dir):
+    """dp_unproject vs the reference's depth_to_3d output (NaN / <=0 entries, row-major compaction)."""
+    gold = np.load(os.path.join(golden_dir, "depth_to_3d.npz"))
+    depth = torch.from_numpy(gold["depth"]).to(DEV)
+    H, W = depth.shape
+    f = torch.tensor([float(gold["f"])], device=DEV)
+    xyz = torch.zeros(H * W, 3, device=DEV)
+    mask = torch.zeros(H, W, dtype=torch.uint8, device=DEV)
+    n = torch.zeros(1, dtype=torch.int64, device=DEV)
+    _capi.check(lib().dp_unproject(engine(), depth.data_ptr(), None, H, W, f.data_ptr(), xyz.data_ptr(), None,
+                                   mask.data_ptr(), n.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    assert int(n) == gold["points"].shape[0]
+    assert np.array_equal(mask.cpu().numpy().astype(bool), gold["valid"])
+    got = xyz[: int(n)].cpu().double().numpy()
+    denom = np.maximum(np.abs(gold["points"]), 1e-3)
+    assert np.max(np.abs(got - gold["points"]) / denom) <= 1e-6
+
+
+@pytest.mark.parametrize("H,W", [(1080, 1920), (2160, 3840), (33, 1025)])
+def test_unproject_vs_oracle(H, W):
+    g = torch.Generator().manual_seed(H)
+    depth = torch.rand(H, W, generator=g) * 50 + 0.1
+    depth[torch.rand(H, W, generator=g) < 0.02] = float("nan")
+    depth[torch.rand(H, W, generator=g) < 0.02] = 0.0
+    rgb = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8)
+    f = 1234.5
+    pts, valid = O.depth_to_3d(depth.numpy(), f, W, H)
+    d = depth.to(DEV)
+    xyz = torch.zeros(H * W, 3, device=DEV)
+    col = torch.zeros(H * W, 3, device=DEV)
+    n = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ft = torch.tensor([f], device=DEV)
+    _capi.check(lib().dp_unproject(engine(), d.data_ptr(), rgb.to(DEV).data_ptr(), H, W, ft.data_ptr(), xyz.data_ptr(),
+                                   col.data_ptr(), None, n.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    assert int(n) == pts.shape[0]
+    got = xyz[: int(n)].cpu().double().numpy()
+    assert np.max(np.abs(got - pts) / np.maximum(np.abs(pts), 1e-3)) <= 1e-6
+    ref_col = rgb.numpy().reshape(-1, 3)[valid.flatten()] / 255.0
+    assert np.max(np.abs(col[: int(n)].cpu().double().numpy() - ref_col)) <= 1e-7
+
+
+def test_colorize_and_u16():
+    H, W = 270, 480
+    g = torch.Generator().manual_seed(3)
+    depth = torch.rand(H, W, generator=g) * 30 + 0.5
+    lut = torch.randint(0, 256, (256, 3), generator=g, dtype=torch.uint8)
+    norm = O.normalize_depth(depth.numpy())
+    idx = np.minimum((norm * 256).astype(np.int64), 255)
+    ref = lut.numpy()[idx]
+    out = torch.zeros(H, W, 3, dtype=torch.uint8, device=DEV)
+    _capi.check(lib().dp_colorize(engine(), depth.to(DEV).data_ptr(), H, W, lut.to(DEV).data_ptr(), out.data_ptr(), stream()))
+    out16 = torch.zeros(H, W, dtype=torch.int16, device=DEV)
+    _capi.check(lib().dp_colorize(engine(), depth.to(DEV).data_ptr(), H, W, None, out16.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert np.array_equal(out16.cpu().numpy().view(np.uint16), O.depth_to_u16(depth.numpy()))

@@ -1,0 +1,148 @@
+"""-m gpu: the full Depth Pro path through the drop-in API vs the CPU oracle and the golden
+fixtures produced by the unmodified reference (tests/golden/reference_outputs.npz).
+
+Tolerances are BASELINE.md §4: fp32 per-pixel depth rel-err <= 1e-4 and f_px <= 1e-4;
+bf16 median abs-rel <= 5e-3 (p99 reported), f_px <= 1e-2; multi-frame batches bit-identical
+to single frames.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import depth_pro
+import depthpro_oracle as O
+from depth_pro import weights
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+SEED = 1234
+
+
+@pytest.fixture(scope="module")
+def state_dict():
+    return weights.stress_init(SEED)
+
+
+@pytest.fixture(scope="module")
+def oracle_run(state_dict):
+    torch.set_num_threads(os.cpu_count())
+    x = O.synthetic_image_1536(1)
+    taps = {}
+    out = O.infer(state_dict, x, taps=taps)
+    return x, out, taps
+
+
+def _model(state_dict, precision):
+    m = depth_pro.DepthPro(device=DEV, precision=precision)
+    m.load_state_dict(state_dict, strict=True)
+    return m.eval()
+
+
+@pytest.fixture(scope="module")
+def model_fp32(state_dict):
+    return _model(state_dict, torch.float32)
+
+
+@pytest.fixture(scope="module")
+def model_bf16(state_dict):
+    return _model(state_dict, torch.bfloat16)
+
+
+def _pix_rel(a, b):
+    return ((a.double() - b.double()).abs() / b.double().abs().clamp_min(1e-30))
+
+
+def test_oracle_matches_golden(oracle_run, golden_dir):
+    """The oracle on THIS host reproduces the reference's outputs recorded in the build container."""
+    _, out, taps = oracle_run
+    gold = np.load(os.path.join(golden_dir, "reference_outputs.npz"))
+    g = torch.from_numpy(gold["depth_1536"])
+    assert float(_pix_rel(out["depth"][::16, ::16], g).max()) <= 2e-5
+    assert abs(float(out["focallength_px"]) - float(gold["f_px_1536"])) / float(gold["f_px_1536"]) <= 2e-5
+
+
+def test_fp32_vs_oracle(model_fp32, oracle_run, golden_dir):
+    x, ref, taps = oracle_run
+    pred = model_fp32.infer(x.to(DEV))
+    depth = pred["depth"].cpu()
+    rel = _pix_rel(depth, ref["depth"])
+    f_rel = abs(float(pred["focallength_px"]) - float(ref["focallength_px"])) / float(ref["focallength_px"])
+    print(f"fp32: depth rel-err max {float(rel.max()):.3e} median {float(rel.median()):.3e}; f_px rel {f_rel:.3e}")
+    # stage taps first: they localise a failure
+    for name in ("lat0_merged", "lat1_merged", "x0_merged", "x1_merged", "x2_tokens", "global_tokens",
+                 "enc0", "enc1", "enc2", "enc3", "enc4", "lowres", "decoder_out"):
+        r = taps[name]
+        got = model_fp32.tap(name).cpu().reshape(r.shape)
+        err = float((got - r).abs().max() / r.abs().max())
+        print(f"  tap {name:14s} max-abs-err/absmax {err:.3e}")
+        assert err <= 1e-4, name
+    assert float(rel.max()) <= 1e-4
+    assert f_rel <= 1e-4
+    assert pred["depth"].shape == (1536, 1536) and pred["focallength_px"].dim() == 0
+    # against the reference's own recorded output
+    gold = np.load(os.path.join(golden_dir, "reference_outputs.npz"))
+    assert float(_pix_rel(depth[::16, ::16], torch.from_numpy(gold["depth_1536"])).max()) <= 1e-4
+    canon, fov = model_fp32.forward(x[None].to(DEV))
+    assert canon.shape == (1, 1, 1536, 1536) and fov.shape == (1, 1, 1, 1)
+    assert float(_pix_rel(canon[0, 0, ::16, ::16].cpu(), torch.from_numpy(gold["canon_1536"])).max()) <= 1e-4
+    assert abs(float(fov) - float(gold["fov_deg_1536"][0])) / float(gold["fov_deg_1536"][0]) <= 1e-4
+
+
+def test_fp32_1080p_u8_vs_golden(model_fp32, golden_dir):
+    """uint8 frame -> fused transform + resize -> infer -> resize back (generate_depth_maps.py:113-121)."""
+    gold = np.load(os.path.join(golden_dir, "reference_outputs.npz"))
+    frame = O.synthetic_frame_u8(0)
+    pred = model_fp32.infer(torch.from_numpy(frame))
+    assert pred["depth"].shape == (1080, 1920)
+    rel = _pix_rel(pred["depth"].cpu()[::16, ::16], torch.from_numpy(gold["depth_1080p"]))
+    f_rel = abs(float(pred["focallength_px"]) - float(gold["f_px_1080p"])) / float(gold["f_px_1080p"])
+    print(f"fp32 1080p: depth rel-err max {float(rel.max()):.3e}; f_px rel {f_rel:.3e}")
+    assert float(rel.max()) <= 1e-4 and f_rel <= 1e-4
+    # same frame through the reference-style transformed float tensor
+    pred_f = model_fp32.infer(O.transform_u8(frame).to(DEV))
+    assert torch.equal(pred_f["depth"], pred["depth"])
+    # caller-supplied focal length (depth_pro.py:285-286)
+    pred3 = model_fp32.infer(torch.from_numpy(frame), f_px=torch.tensor(1234.5))
+    rel3 = _pix_rel(pred3["depth"].cpu()[::16, ::16], torch.from_numpy(gold["depth_1080p_fpx1234_5"]))
+    assert float(rel3.max()) <= 1e-4
+    assert float(pred3["focallength_px"]) == 1234.5
+
+
+def test_bf16_vs_oracle(model_bf16, oracle_run):
+    x, ref, taps = oracle_run
+    pred = model_bf16.infer(x.to(DEV))
+    depth = pred["depth"].cpu()
+    ok = (ref["depth"] < 1e4 - 1) & (depth < 1e4 - 1)  # pixels not clamped on either side
+    rel = _pix_rel(depth, ref["depth"])[ok]
+    f_rel = abs(float(pred["focallength_px"]) - float(ref["focallength_px"])) / float(ref["focallength_px"])
+    q = torch.quantile(rel[:: max(1, rel.numel() // 1_000_000)].float(), torch.tensor([0.5, 0.9, 0.99]))
+    print(f"bf16: depth abs-rel median {float(q[0]):.3e} p90 {float(q[1]):.3e} p99 {float(q[2]):.3e} "
+          f"max {float(rel.max()):.3e}; f_px rel {f_rel:.3e}; clamp mismatch {float((~ok).float().mean()):.2e}")
+    for name in ("lat0_merged", "x0_merged", "global_tokens", "enc0", "enc4", "lowres", "decoder_out"):
+        r = taps[name]
+        got = model_bf16.tap(name).cpu().reshape(r.shape)
+        print(f"  tap {name:14s} rms-err/rms {float((got - r).pow(2).mean().sqrt() / r.pow(2).mean().sqrt()):.3e}")
+    assert float(q[0]) <= 5e-3
+    assert f_rel <= 1e-2
+    assert float((~ok).float().mean()) <= 1e-3
+
+
+def test_batch_is_bit_identical(model_bf16):
+    """Frames are independent units: a 2-frame batch must equal two single-frame calls bit for bit."""
+    frames = np.stack([O.synthetic_frame_u8(i, 540, 960) for i in range(2)])
+    both = model_bf16.infer(torch.from_numpy(frames))
+    for i in range(2):
+        one = model_bf16.infer(torch.from_numpy(frames[i]))
+        assert torch.equal(both["depth"][i], one["depth"])
+        assert torch.equal(both["focallength_px"][i], one["focallength_px"])
+
+
+def test_errors():
+    with pytest.raises(RuntimeError):
+        depth_pro.create_model_and_transforms(device=torch.device("cpu"))
+    with pytest.raises(KeyError):
+        depth_pro.depth_pro.create_backbone_model("nope")
