@@ -121,6 +121,15 @@ int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float*
 int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, int n,
                       void* stream);
 
+/* Per-launch CUDA-event profiling of the hot kernels (used by bench.py for the roofline line).
+ * Classes: 0 tcgen05 GEMM, 1 tcgen05 conv3x3, 2 attention, 3 LayerNorm, 4 fp32 CUDA-core GEMM.
+ * `work` is algorithmic FLOPs (classes 0,1,2,4) or bytes (class 3).  Arrays hold 5 entries.
+ * dp_profile_collect synchronises the device and sums everything since dp_profile_enable(e,1). */
+#define DP_NUM_KERNEL_CLASSES 5
+int dp_profile_enable(dp_engine* e, int on);
+int dp_profile_collect(dp_engine* e, double* ms_by_class, double* work_by_class,
+                       int64_t* launches_by_class);
+
 /* Kernel launches issued by this engine since creation (bench.py's `gpu_launches`). */
 int64_t dp_launch_count(dp_engine* e);
 

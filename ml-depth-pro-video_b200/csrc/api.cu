@@ -96,6 +96,18 @@ int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float*
 int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, int n, void* stream) {
   return guard([&] { E(e)->attention_test(backend, qkv, out, n, S(stream)); });
 }
+int dp_profile_enable(dp_engine* e, int on) {
+  (void)e;
+  return guard([&] { dp::prof_enable(on != 0); });
+}
+int dp_profile_collect(dp_engine* e, double* ms_by_class, double* work_by_class, int64_t* launches_by_class) {
+  (void)e;
+  return guard([&] {
+    long long l[dp::KC_COUNT];
+    dp::prof_collect(ms_by_class, work_by_class, l);
+    for (int i = 0; i < dp::KC_COUNT; ++i) launches_by_class[i] = l[i];
+  });
+}
 int64_t dp_launch_count(dp_engine* e) {
   (void)e;
   return dp::g_launches;

@@ -35,6 +35,26 @@ struct Error : std::runtime_error {
 extern int64_t g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }
 
+// ---- optional per-launch profiling with CUDA events (bench.py roofline numbers) ----------
+enum KernelClass {
+  KC_GEMM_TC = 0,   // tcgen05 GEMM (dense contraction), work = flops
+  KC_CONV_TC = 1,   // tcgen05 implicit-GEMM 3x3 conv, work = flops
+  KC_ATTENTION = 2, // work = flops (4*N^2*d per head)
+  KC_LAYERNORM = 3, // work = bytes
+  KC_GEMM_SIMT = 4, // fp32 CUDA-core GEMM / conv, work = flops
+  KC_COUNT = 5
+};
+void prof_begin(cudaStream_t s, int cls, double work);  // no-ops unless profiling is enabled
+void prof_end(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s;
+  ProfScope(cudaStream_t s_, int cls, double work) : s(s_) { prof_begin(s, cls, work); }
+  ~ProfScope() { prof_end(s); }
+};
+void prof_enable(bool on);
+// sums since prof_enable(true); synchronises the device
+void prof_collect(double* ms_by_class, double* work_by_class, long long* launches_by_class);
+
 #define DP_LAUNCH_CHECK()                \
   do {                                   \
     ::dp::count_launch();                \

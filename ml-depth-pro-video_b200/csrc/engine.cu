@@ -17,6 +17,53 @@ namespace dp {
 
 int64_t g_launches = 0;
 
+// ---------------------------------------------------------------------------- profiler
+namespace {
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cls;
+  double work;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t new_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  DP_CUDA(cudaEventCreate(&e));
+  return e;
+}
+}  // namespace
+
+void prof_enable(bool on) {
+  for (auto& r : g_prof) g_event_pool.push_back(r.a), g_event_pool.push_back(r.b);
+  g_prof.clear();
+  g_prof_on = on;
+}
+void prof_begin(cudaStream_t s, int cls, double work) {
+  if (!g_prof_on) return;
+  ProfRec r{new_event(), new_event(), cls, work};
+  DP_CUDA(cudaEventRecord(r.a, s));
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t s) {
+  if (!g_prof_on) return;
+  DP_CUDA(cudaEventRecord(g_prof.back().b, s));
+}
+void prof_collect(double* ms, double* work, long long* launches) {
+  DP_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < KC_COUNT; ++i) ms[i] = 0, work[i] = 0, launches[i] = 0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    DP_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t, work[r.cls] += r.work, launches[r.cls] += 1;
+  }
+}
+
 namespace {
 
 constexpr int IMG = 1536, EMB = 1024, SEQ = 577;
@@ -352,22 +399,31 @@ void Engine::run_vit(const VitWeights& w, const T* A, int nseq, float* resid, T*
   }
   for (int i = 0; i < 24; ++i) {
     const auto& k = w.blk[i];
-    layernorm_rows<T>(resid, xn, k.n1w, k.n1b, M, RowMap(), 1, s);
+    {
+      ProfScope ps(s, KC_LAYERNORM, static_cast<double>(M) * EMB * (4 + sizeof(T)));
+      layernorm_rows<T>(resid, xn, k.n1w, k.n1b, M, RowMap(), 1, s);
+    }
     {
       GemmOp op;
       op.M = M, op.N = 3 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.Wt = k.qkv_w, op.bias = k.qkv_b;
       op.out = qkv, op.ldo = 3 * EMB;
       gemm(prec_, op, s);
     }
-    if (prec_ == BF16) attention_bf16((const bf16*)qkv, (bf16*)attn, nseq, s);
-    else attention_f32((const float*)qkv, (float*)attn, nseq, s);
+    {
+      ProfScope ps(s, KC_ATTENTION, 4.0 * SEQ * SEQ * 64 * 16 * nseq);
+      if (prec_ == BF16) attention_bf16((const bf16*)qkv, (bf16*)attn, nseq, s);
+      else attention_f32((const float*)qkv, (float*)attn, nseq, s);
+    }
     {
       GemmOp op;
       op.M = M, op.N = EMB, op.K = EMB, op.A = attn, op.lda = EMB, op.Wt = k.proj_w, op.bias = k.proj_b;
       op.gamma = k.g1, op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
       gemm(prec_, op, s);
     }
-    layernorm_rows<T>(resid, xn, k.n2w, k.n2b, M, RowMap(), 1, s);
+    {
+      ProfScope ps(s, KC_LAYERNORM, static_cast<double>(M) * EMB * (4 + sizeof(T)));
+      layernorm_rows<T>(resid, xn, k.n2w, k.n2b, M, RowMap(), 1, s);
+    }
     {
       GemmOp op;
       op.M = M, op.N = 4 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.Wt = k.fc1_w, op.bias = k.fc1_b;

@@ -11,8 +11,14 @@ void gemm_tc(const GemmOp& op, cudaStream_t stream);
 void tmap_cache_clear();
 
 inline void gemm(int prec, const GemmOp& op, cudaStream_t stream) {
-  if (prec == BF16) gemm_tc(op, stream);
-  else gemm_simt(op, stream);
+  const double flops = 2.0 * op.M * static_cast<double>(op.N) * op.K;
+  if (prec == BF16) {
+    ProfScope ps(stream, op.a_mode == A_CONV3X3 ? KC_CONV_TC : KC_GEMM_TC, flops);
+    gemm_tc(op, stream);
+  } else {
+    ProfScope ps(stream, KC_GEMM_SIMT, flops);
+    gemm_simt(op, stream);
+  }
 }
 
 }  // namespace dp

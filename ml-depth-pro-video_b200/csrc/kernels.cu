@@ -43,8 +43,11 @@ __global__ void resize_kernel(const void* __restrict__ src, int fmt, int B, int 
     return;
   }
   const float sh = static_cast<float>(H) / IMG, sw = static_cast<float>(W) / IMG;
-  float fy = __fsub_rn(__fmul_rn(sh, oy + 0.5f), 0.5f);
-  float fx = __fsub_rn(__fmul_rn(sw, ox + 0.5f), 0.5f);
+  // ATen's CPU kernels (x86-64 AVX2 / AVX-512 builds) contract scale*(dst+0.5)-0.5 into one FMA;
+  // the single rounding matters: the product is O(1e3), so an unfused multiply moves the source
+  // index by up to ~5e-5 whenever in/out is not exactly representable.
+  float fy = fmaf(sh, oy + 0.5f, -0.5f);
+  float fx = fmaf(sw, ox + 0.5f, -0.5f);
   fy = fy < 0.f ? 0.f : fy;
   fx = fx < 0.f ? 0.f : fx;
   int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
@@ -296,8 +299,8 @@ __global__ void depth_epilogue_kernel(const float* __restrict__ canon, const flo
     inv = src[static_cast<long long>(oy) * IMG + ox] * scale;
   } else {
     const float sh = static_cast<float>(IMG) / H, sw = static_cast<float>(IMG) / W;
-    float fy = __fsub_rn(__fmul_rn(sh, oy + 0.5f), 0.5f);
-    float fx = __fsub_rn(__fmul_rn(sw, ox + 0.5f), 0.5f);
+    float fy = fmaf(sh, oy + 0.5f, -0.5f);  // see resize_kernel
+    float fx = fmaf(sw, ox + 0.5f, -0.5f);
     fy = fy < 0.f ? 0.f : fy;
     fx = fx < 0.f ? 0.f : fx;
     int y0 = min(static_cast<int>(fy), IMG - 1), x0 = min(static_cast<int>(fx), IMG - 1);

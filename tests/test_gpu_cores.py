@@ -83,7 +83,7 @@ def test_conv3x3(backend, B, H, W, Cin, Cout):
         tol = 2e-5
     else:
         ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
-        tol = 2e-6
+        tol = 5e-6  # K up to 9216 fp32 accumulations
     assert relerr(got, ref) < tol
 
 

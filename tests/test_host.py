@@ -1,0 +1,93 @@
+"""CPU tests of the host side: manifest, seeded init, C-ABI symbol table, error behaviour, IO."""
+
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import depth_pro
+from depth_pro import _capi, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_manifest_matches_reference_state_dict(golden_dir):
+    gold = json.load(open(os.path.join(golden_dir, "state_dict_manifest.json")))
+    m = weights.manifest()
+    assert list(gold) == list(m)
+    assert all(tuple(gold[k]) == tuple(m[k]) for k in m)
+    assert sum(int(np.prod(s)) for s in m.values()) == 951_991_330
+
+
+def test_seeded_init_is_deterministic_and_order_free():
+    a = weights.stress_tensor("head.0.weight", (128, 256, 3, 3), 1234)
+    b = weights.stress_tensor("head.0.weight", (128, 256, 3, 3), 1234)
+    c = weights.stress_tensor("head.0.weight", (128, 256, 3, 3), 1235)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(float(a.std()) - 1 / (9 * 256) ** 0.5) < 1e-3
+    assert float(weights.stress_tensor("head.4.bias", (1,), 1)) == 2.0
+    assert float(weights.stress_tensor("fov.head.4.bias", (1,), 1)) == 60.0
+    g = weights.stress_tensor("encoder.patch_encoder.blocks.3.ls1.gamma", (1024,), 7)
+    assert 0.05 <= float(g.min()) and float(g.max()) <= 0.3
+    # ConvTranspose weights are (Cin, Cout, 2, 2): std 1/sqrt(Cin)
+    t = weights.stress_tensor("encoder.upsample0.1.weight", (512, 512, 2, 2), 3)
+    assert abs(float(t.std()) - 512 ** -0.5) < 1e-3
+
+
+def test_capi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "depthpro_b200.h")).read()
+    declared = set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    lib = _capi.load()  # loads without a GPU; no compute call is made here
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dp_version() >= 100
+
+
+def test_engine_create_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    rc = _capi.load().dp_engine_create(0, 0, 1, ctypes.byref(h))
+    assert rc != 0 and len(_capi.load().dp_last_error()) > 0
+    with pytest.raises(RuntimeError):
+        depth_pro.create_model_and_transforms(device=torch.device("cpu"))
+    with pytest.raises(RuntimeError):
+        depth_pro.DepthPro(device=torch.device("cuda:0"))
+
+
+def test_config_and_errors():
+    cfg = depth_pro.DEFAULT_MONODEPTH_CONFIG_DICT
+    assert cfg.patch_encoder_preset == "dinov2l16_384" and cfg.decoder_features == 256
+    assert cfg.checkpoint_uri == "./checkpoints/depth_pro.pt" and cfg.use_fov_head
+    with pytest.raises(KeyError):
+        depth_pro.depth_pro.create_backbone_model("unknown_preset")
+    with pytest.raises(ValueError):
+        depth_pro.depth_pro._precision_code(torch.int8)
+
+
+def test_load_rgb_contract(tmp_path):
+    from PIL import Image
+
+    arr = (np.random.default_rng(0).random((20, 30, 4)) * 255).astype(np.uint8)
+    p = tmp_path / "a.png"
+    Image.fromarray(arr, "RGBA").save(p)
+    img, icc, f_px = depth_pro.load_rgb(p)
+    assert img.dtype == np.uint8 and img.shape == (20, 30, 3) and f_px is None
+    assert np.array_equal(img, arr[:, :, :3])
+    gray = tmp_path / "g.png"
+    Image.fromarray(arr[:, :, 0], "L").save(gray)
+    assert depth_pro.load_rgb(gray)[0].shape == (20, 30, 3)
+    assert abs(depth_pro.utils.fpx_from_f35(36, 24, 50) - 50.0) < 1e-9
+
+
+def test_synthetic_generators_match_oracle_copy():
+    import depthpro_oracle as O
+    from depth_pro import synthetic
+
+    assert torch.equal(synthetic.synthetic_image_1536(3), O.synthetic_image_1536(3))
+    assert np.array_equal(synthetic.synthetic_frame_u8(2, 90, 160), O.synthetic_frame_u8(2, 90, 160))
