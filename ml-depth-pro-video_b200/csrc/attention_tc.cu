@@ -1,0 +1,300 @@
+// Flash attention on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Problem: 16 heads x 64, 577 tokens per sequence, softmax(Q K^T / 8) V, no mask (timm Attention ->
+// F.scaled_dot_product_attention, wired at src/depth_pro/network/vit_factory.py:97-110).
+// qkv is (nseq*577, 3072) bf16 with columns [q | k | v], each 16 heads x 64; out is (nseq*577, 1024).
+//
+// One persistent CTA per SM loops over work items (sequence, head, 128-row query tile); keys are
+// processed in 5 blocks of 128 (640 >= 577, the tail is masked).  Warp roles:
+//   warp 0     TMA producer : Q tile (once per item) and K/V blocks (3-deep ring), 128B swizzle.
+//   warp 1     MMA issuer   : S = Q K^T   (tcgen05.mma M128 N128 K16 x4, A/B K-major from smem),
+//                             O_j = P V   (M128 N64 K16 x8, A = P K-major from smem, B = V MN-major
+//                             straight from the TMA tile) into double-buffered TMEM.
+//   warp 2     TMEM allocator
+//   warps 4-7  softmax      : one thread per query row: tcgen05.ld the 128 scores, online softmax in
+//                             fp32 (exp2, log2e folded into the scale), write P as bf16 into the
+//                             swizzled smem tile the next MMA reads, accumulate O_j from TMEM into
+//                             registers with the running-max correction, final 1/l and bf16 store.
+// S and P are double buffered so Q K^T of block j+1 runs on the tensor pipe while the softmax warps
+// work on block j; the per-block P V products are NOT accumulated in TMEM (no read-modify-write of O
+// in tensor memory): each lands in its own TMEM buffer and is folded into registers one block later.
+#include "attention.cuh"
+#include "ptx.cuh"
+
+namespace dp {
+namespace {
+
+constexpr int SEQ = 577, HD = 64, NH = 16, LDQ = 3 * NH * HD, LDO = NH * HD;
+constexpr int QT = 128;                         // query rows per item
+constexpr int KB = 128;                         // keys per block
+constexpr int NB = (SEQ + KB - 1) / KB;         // 5 key blocks
+constexpr int NQT = (SEQ + QT - 1) / QT;        // 5 query tiles
+constexpr int KV_STAGES = 3;
+constexpr int THREADS = 256;
+constexpr uint32_t TILE_BYTES = 128 * 128;      // 128 rows x 64 bf16 = 16 KB
+constexpr uint32_t SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES + 4) + 1024 + 256;
+
+// idesc: D=f32, A=B=bf16, A K-major; B K-major (QK^T) or MN-major (PV: bit 16)
+constexpr uint32_t IDESC_QK = ptx::umma_idesc_bf16(128, 128);
+constexpr uint32_t IDESC_PV = ptx::umma_idesc_bf16(128, 64) | (1u << 16);
+
+// MN-major operand stored as rows of 64 bf16 (128 B, the MN dimension is contiguous) with the 128B
+// swizzle: 8-row (K) groups are 1024 B apart (SBO); one 64-element MN atom, so LBO is unused.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float ex2(float x) {  // MUFU ex2.approx: 2 ulp, -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int nseq) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TILE_BYTES;                    // KV_STAGES tiles
+  uint8_t* sV = sK + KV_STAGES * TILE_BYTES;        // KV_STAGES tiles
+  uint8_t* sP = sV + KV_STAGES * TILE_BYTES;        // 2 buffers x 2 k-chunks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * TILE_BYTES);
+  uint64_t* q_full = bars;                          // 1
+  uint64_t* q_empty = bars + 1;                     // 1
+  uint64_t* kv_full = bars + 2;                     // KV_STAGES
+  uint64_t* kv_empty = kv_full + KV_STAGES;         // KV_STAGES
+  uint64_t* s_full = kv_empty + KV_STAGES;          // 2
+  uint64_t* s_empty = s_full + 2;                   // 2
+  uint64_t* p_full = s_empty + 2;                   // 2
+  uint64_t* pv_done = p_full + 2;                   // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = nseq * NH * NQT;
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmQKV);
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    ptx::mbar_init(q_empty, 1);
+    for (int i = 0; i < KV_STAGES; ++i) ptx::mbar_init(&kv_full[i], 1), ptx::mbar_init(&kv_empty[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_empty[i], 128);
+      ptx::mbar_init(&p_full[i], 128);
+      ptx::mbar_init(&pv_done[i], 1);
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 256;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int qt = item % NQT, h = (item / NQT) % NH, seq = item / (NQT * NH);
+        const int row0 = seq * SEQ;
+        ptx::mbar_wait(q_empty, (it & 1) ^ 1);
+        ptx::mbar_expect_tx(q_full, TILE_BYTES);
+        ptx::tma_load_2d(sQ, &tmQKV, q_full, h * HD, row0 + qt * QT);
+        for (int j = 0; j < NB; ++j) {
+          const int gb = it * NB + j, st = gb % KV_STAGES;
+          ptx::mbar_wait(&kv_empty[st], ((gb / KV_STAGES) & 1) ^ 1);
+          ptx::mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+          ptx::tma_load_2d(sK + st * TILE_BYTES, &tmQKV, &kv_full[st], NH * HD + h * HD, row0 + j * KB);
+          ptx::tma_load_2d(sV + st * TILE_BYTES, &tmQKV, &kv_full[st], 2 * NH * HD + h * HD, row0 + j * KB);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int it = 0;
+      auto issue_pv = [&](int gb) {
+        const int b = gb & 1, st = gb % KV_STAGES;
+        ptx::mbar_wait(&p_full[b], (gb >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t p0 = ptx::smem_u32(sP + b * 2 * TILE_BYTES);
+        const uint32_t v0 = ptx::smem_u32(sV + st * TILE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < KB / 16; ++ks) {
+          const uint64_t da = ptx::umma_desc_sw128(p0 + (ks >> 2) * TILE_BYTES + (ks & 3) * 32);
+          const uint64_t db = umma_desc_mn_sw128(v0 + ks * 2048);
+          ptx::umma_bf16(tO + b * 64, da, db, IDESC_PV, ks != 0);
+        }
+        ptx::umma_commit(&pv_done[b]);
+        ptx::umma_commit(&kv_empty[st]);
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        ptx::mbar_wait(q_full, it & 1);
+        for (int j = 0; j < NB; ++j) {
+          const int gb = it * NB + j, b = gb & 1, st = gb % KV_STAGES;
+          ptx::mbar_wait(&kv_full[st], (gb / KV_STAGES) & 1);
+          ptx::mbar_wait(&s_empty[b], ((gb >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t q0 = ptx::smem_u32(sQ), k0 = ptx::smem_u32(sK + st * TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks)
+            ptx::umma_bf16(tS + b * 128, ptx::umma_desc_sw128(q0 + ks * 32), ptx::umma_desc_sw128(k0 + ks * 32),
+                           IDESC_QK, ks != 0);
+          ptx::umma_commit(&s_full[b]);
+          if (j == NB - 1) ptx::umma_commit(q_empty);  // Q no longer needed once the last QK^T retires
+          if (j > 0) issue_pv(gb - 1);
+        }
+        issue_pv(it * NB + NB - 1);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax / accumulate
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const float c = 0.125f * 1.4426950408889634f;  // softmax scale * log2(e)
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int qt = item % NQT, h = (item / NQT) % NH, seq = item / (NQT * NH);
+      const int q_row = qt * QT + row;
+      float o[HD];
+#pragma unroll
+      for (int d = 0; d < HD; ++d) o[d] = 0.f;
+      float m_run = -INFINITY, m_acc = -INFINITY, l = 0.f;
+      float m_hist[2] = {-INFINITY, -INFINITY};
+
+      auto acc_o = [&](int gb) {
+        const int b = gb & 1;
+        ptx::mbar_wait(&pv_done[b], (gb >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld32(tO + b * 64 + lane_addr, r0);
+        ptx::tmem_ld32(tO + b * 64 + 32 + lane_addr, r1);
+        ptx::tmem_ld_wait();
+        const float mj = m_hist[b];
+        const float alpha = ex2((m_acc - mj) * c);
+        m_acc = mj;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) {
+          o[d] = fmaf(o[d], alpha, __uint_as_float(r0[d]));
+          o[32 + d] = fmaf(o[32 + d], alpha, __uint_as_float(r1[d]));
+        }
+      };
+
+      for (int j = 0; j < NB; ++j) {
+        const int gb = it * NB + j, b = gb & 1;
+        if (j >= 2) acc_o(gb - 2);
+        // ---- scores of this block
+        ptx::mbar_wait(&s_full[b], (gb >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t sr[4][32];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld32(tS + b * 128 + ch * 32 + lane_addr, sr[ch]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&s_empty[b]);  // S[b] is in registers: the tensor pipe may overwrite it
+        const int key0 = j * KB;
+        float mx = m_run;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float v = __uint_as_float(sr[ch][e]);
+            if (j == NB - 1 && key0 + ch * 32 + e >= SEQ) v = -INFINITY;
+            sr[ch][e] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+          }
+        const float alpha = ex2((m_run - mx) * c);
+        m_run = mx;
+        m_hist[b] = mx;
+        const float mc = mx * c;
+        float rs = 0.f;
+        uint8_t* prow = sP + b * 2 * TILE_BYTES + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          // 32 keys -> 4 x 16-byte chunks of the k-chunk tile (ch >> 1), chunk index (ch & 1) * 4 + i
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const float p0 = ex2(fmaf(__uint_as_float(sr[ch][i * 8 + 2 * w]), c, -mc));
+              const float p1 = ex2(fmaf(__uint_as_float(sr[ch][i * 8 + 2 * w + 1]), c, -mc));
+              rs += p0 + p1;
+              pk[w] = pack_bf16(p0, p1);
+            }
+            const int chunk = (ch & 1) * 4 + i;
+            uint4* dst = reinterpret_cast<uint4*>(prow + (ch >> 1) * TILE_BYTES + ((chunk ^ (row & 7)) << 4));
+            *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        l = fmaf(l, alpha, rs);
+        ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&p_full[b]);
+      }
+      acc_o(it * NB + NB - 2);
+      acc_o(it * NB + NB - 1);
+      if (q_row < SEQ) {
+        const float inv = 1.f / l;
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(seq) * SEQ + q_row) * LDO + h * HD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4 t;
+          t.x = pack_bf16(o[8 * i] * inv, o[8 * i + 1] * inv);
+          t.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+          t.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+          t.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+          dst[i] = t;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                                    uint32_t box_rows);  // gemm_tc.cu
+
+void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
+  static bool configured = false;
+  static int sms = 0;
+  if (!configured) {
+    DP_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    int dev;
+    DP_CUDA(cudaGetDevice(&dev));
+    DP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  const CUtensorMap& tm = get_tmap_2d_bf16(qkv, LDQ, static_cast<uint64_t>(nseq) * SEQ, LDQ, 64, 128);
+  const int items = nseq * NH * NQT;
+  attention_tc_kernel<<<items < sms ? items : sms, THREADS, SMEM_BYTES, s>>>(tm, out, nseq);
+  DP_LAUNCH_CHECK();
+}
+
+}  // namespace dp

@@ -81,12 +81,27 @@ enum OutMode {
 
 // One GEMM / implicit-GEMM convolution launch, shared by the fp32 SIMT and bf16 tcgen05 cores.
 // Activations are `prec`-typed (float or bf16) unless stated; weights Wt are [N, K] K-major.
+//
+// Grouped launches: up to 3 row-groups stacked along M share one launch but use different
+// weights (the patch / image / fov ViT-L encoders run layer by layer as ONE GEMM each).  Group g
+// covers A rows [a_row_off, a_row_off + M) and output rows [o_row_off, o_row_off + M); tiles never
+// straddle a group.  With ngroups == 1 the group fields mirror the scalar fields below.
+struct GemmGroup {
+  int M = 0;
+  long long a_row_off = 0, o_row_off = 0;
+  const void* Wt = nullptr;
+  const float* bias = nullptr;
+  const float* gamma = nullptr;
+  const float* pos = nullptr;
+};
+
 struct GemmOp {
   int M = 0, N = 0, K = 0;
   // A
   const void* A = nullptr;
   int a_mode = A_ROWMAJOR;
   int lda = 0;
+  long long a_rows = 0;             // rows addressable behind A (grouped launches); 0 -> M
   int B = 1, H = 0, W = 0, C = 0;  // conv geometry (input grid); also the grid for O_CONVT2X2
   // W
   const void* Wt = nullptr;
@@ -109,6 +124,17 @@ struct GemmOp {
   const float* pos = nullptr;   // O_PATCH_EMBED: pos_embed (577, N) fp32
   const float* dot_w = nullptr; // O_DOT_RELU: head.4 weight (32), dot_b: bias (1)
   const float* dot_b = nullptr;
+  // groups
+  int ngroups = 1;
+  GemmGroup grp[3];
+
+  // fill grp[0] from the scalar fields (single-group launches)
+  void finish() {
+    if (ngroups == 1 && grp[0].M == 0) {
+      grp[0].M = M, grp[0].Wt = Wt, grp[0].bias = bias, grp[0].gamma = gamma, grp[0].pos = pos;
+    }
+    if (a_rows == 0) a_rows = M;
+  }
 };
 
 }  // namespace dp

@@ -7,6 +7,7 @@
 //   FOVNetwork.forward        src/depth_pro/network/fov.py:56-82
 #include "engine.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "attention.cuh"
@@ -181,6 +182,8 @@ Engine::Engine(int device, int prec, int max_batch) : device_(device), prec_(pre
   DP_CHECK(prop.major == 10, "depthpro_b200 is built for sm_100a (Blackwell B200) only; found sm_" +
                                  std::to_string(prop.major) + std::to_string(prop.minor));
   manifest_ = build_manifest();
+  const char* a = getenv("DEPTHPRO_ATTN");  // debugging switch: "mma" selects the mma.sync kernel
+  attn_legacy_ = a != nullptr && std::string(a) == "mma";
   DP_CUDA(cudaStreamCreateWithFlags(&host_stream_, cudaStreamNonBlocking));
 }
 
@@ -234,7 +237,7 @@ void Engine::set_weight(const std::string& name, const void* data, const int64_t
       pk.bytes = bytes;
     }
   };
-  const bool fov_conv = ndim == 4 && (starts_with(name, "fov.downsample") || starts_with(name, "fov.head"));
+  const bool fov_conv = name == "fov.head.4.weight";  // 6x6 valid conv, reduced by fov_final (fp32 HWIO)
   if (ndim == 4 && is_convT(name)) {
     ensure(n * esz());
     if (bf) pack_convT_iohw<bf16>(src, reinterpret_cast<bf16*>(pk.ptr), (int)shape[0], (int)shape[1], s);
@@ -308,24 +311,18 @@ void Engine::finalize() {
 
   const size_t e = esz();
   const size_t MB = static_cast<size_t>(max_batch_);
-  const size_t T = MB * 35 * SEQ, Ts = MB * SEQ;
+  const size_t T = MB * 37 * SEQ;  // 35 patch + 1 image + 1 fov sequence per frame
   xbuf_ = (float*)alloc(MB * 3 * IMG * IMG * 4);
   canon_ = (float*)alloc(MB * IMG * IMG * 4);
   fov_ = (float*)alloc(MB * 4);
   fpx_ = (float*)alloc(MB * 4);
   fpx_in_ = (float*)alloc(MB * 4);
-  A35_ = alloc(MB * 35 * 576 * 768 * e);
-  A1_ = alloc(MB * 576 * 768 * e);
+  A35_ = alloc(MB * 36 * 576 * 768 * e);
   resid_ = (float*)alloc(T * EMB * 4);
   xn_ = alloc(T * EMB * e);
   qkv_ = alloc(T * 3 * EMB * e);
   attn_ = alloc(T * EMB * e);
   hid_ = alloc(T * 4 * EMB * e);
-  resid_s_ = (float*)alloc(Ts * EMB * 4);
-  xn_s_ = alloc(Ts * EMB * e);
-  qkv_s_ = alloc(Ts * 3 * EMB * e);
-  attn_s_ = alloc(Ts * EMB * e);
-  hid_s_ = alloc(Ts * 4 * EMB * e);
   lat0m_ = alloc(MB * 96 * 96 * EMB * e);
   lat1m_ = alloc(MB * 96 * 96 * EMB * e);
   x0m_ = alloc(MB * 96 * 96 * EMB * e);
@@ -348,6 +345,7 @@ void Engine::finalize() {
   for (int i = 0; i < 5; ++i) feat_[i] = alloc(fs[i] * 256 * e);
   h0_ = alloc(P768 * 128 * e);
   h1_ = alloc(static_cast<size_t>(IMG) * IMG * 128 * e);
+  fovcol_ = alloc(P24 * 2304 * e);
   fovlin_ = alloc(P24 * 128 * e), fov_a_ = alloc(P24 * 128 * e), fov_b_ = alloc(12 * 12 * 64 * e),
   fov_c_ = alloc(6 * 6 * 32 * e);
   colorize_mm_ = (float*)alloc(64);
@@ -386,59 +384,109 @@ void Engine::merge(const float* tokens, int B, int steps, int padding, int C, fl
 }
 
 // ============================================================================ ViT
+// The three DINOv2 ViT-L/16 encoders (patch: 35*B sequences, image: B, fov: B) have identical
+// structure and different weights, so they run layer by layer as ONE grouped launch per op:
+// rows [0, 35B*577) use the patch-encoder weights, the next B*577 the image encoder's, the last
+// B*577 the fov encoder's.  The small encoders ride along for +5.7% tiles instead of 2 x 170
+// latency-bound launches.
 template <typename T>
-void Engine::run_vit(const VitWeights& w, const T* A, int nseq, float* resid, T* xn, T* qkv, T* attn, T* hid, bool hooks,
-                     int B, cudaStream_t s) {
-  const int M = nseq * SEQ;
+void Engine::run_vits(int B, cudaStream_t s) {
+  const VitWeights* vw[3] = {&vit_patch_, &vit_image_, &vit_fov_};
+  const int nseq_g[3] = {35 * B, B, B};
+  const int nseq = 37 * B;
+  const long long M = static_cast<long long>(nseq) * SEQ;
+  T* xn = (T*)xn_;
+  T* qkv = (T*)qkv_;
+  T* attn = (T*)attn_;
+  T* hid = (T*)hid_;
+  float* resid = resid_;
+
+  auto grouped = [&](GemmOp& op, int rows_per_seq, bool a_shared_small) {
+    op.ngroups = 3;
+    long long off = 0, aoff = 0;
+    for (int g = 0; g < 3; ++g) {
+      op.grp[g].M = nseq_g[g] * rows_per_seq;
+      op.grp[g].o_row_off = off;
+      op.grp[g].a_row_off = aoff;
+      off += op.grp[g].M;
+      // patch embed: the image and fov encoders read the SAME im2col rows (patch 34 of each frame)
+      if (!(a_shared_small && g == 1)) aoff += op.grp[g].M;
+    }
+    op.M = static_cast<int>(off);
+    op.a_rows = a_shared_small ? static_cast<long long>(36) * B * rows_per_seq : off;
+  };
+
   {  // patch embed (timm PatchEmbed conv k16 s16 as GEMM) + cls + pos_embed
     GemmOp op;
-    op.M = nseq * 576, op.N = EMB, op.K = 768, op.A = A, op.lda = 768, op.Wt = w.pe_w, op.bias = w.pe_b;
-    op.out = resid, op.out_f32 = 1, op.out_mode = O_PATCH_EMBED, op.ldo = EMB, op.pos = w.pos;
+    op.N = EMB, op.K = 768, op.A = A35_, op.lda = 768;
+    op.out = resid, op.out_f32 = 1, op.out_mode = O_PATCH_EMBED, op.ldo = EMB;
+    grouped(op, 576, true);
+    for (int g = 0; g < 3; ++g) op.grp[g].Wt = vw[g]->pe_w, op.grp[g].bias = vw[g]->pe_b, op.grp[g].pos = vw[g]->pos;
     gemm(prec_, op, s);
-    write_cls_rows(resid, w.cls, w.pos, nseq, s);
+    int seq0 = 0;
+    for (int g = 0; g < 3; ++g) {
+      write_cls_rows(resid + static_cast<long long>(seq0) * SEQ * EMB, vw[g]->cls, vw[g]->pos, nseq_g[g], s);
+      seq0 += nseq_g[g];
+    }
   }
+  LnGroups lg;
+  lg.n = 3;
+  lg.end[0] = 35LL * B * SEQ, lg.end[1] = 36LL * B * SEQ, lg.end[2] = M;
   for (int i = 0; i < 24; ++i) {
-    const auto& k = w.blk[i];
     {
       ProfScope ps(s, KC_LAYERNORM, static_cast<double>(M) * EMB * (4 + sizeof(T)));
-      layernorm_rows<T>(resid, xn, k.n1w, k.n1b, M, RowMap(), 1, s);
+      for (int g = 0; g < 3; ++g) lg.w[g] = vw[g]->blk[i].n1w, lg.b[g] = vw[g]->blk[i].n1b;
+      layernorm_rows_grouped<T>(resid, xn, lg, M, s);
     }
     {
       GemmOp op;
-      op.M = M, op.N = 3 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.Wt = k.qkv_w, op.bias = k.qkv_b;
-      op.out = qkv, op.ldo = 3 * EMB;
+      op.N = 3 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.out = qkv, op.ldo = 3 * EMB;
+      grouped(op, SEQ, false);
+      for (int g = 0; g < 3; ++g) op.grp[g].Wt = vw[g]->blk[i].qkv_w, op.grp[g].bias = vw[g]->blk[i].qkv_b;
       gemm(prec_, op, s);
     }
     {
       ProfScope ps(s, KC_ATTENTION, 4.0 * SEQ * SEQ * 64 * 16 * nseq);
-      if (prec_ == BF16) attention_bf16((const bf16*)qkv, (bf16*)attn, nseq, s);
-      else attention_f32((const float*)qkv, (float*)attn, nseq, s);
+      if (prec_ == BF16) {
+        if (attn_legacy_) attention_bf16((const bf16*)qkv, (bf16*)attn, nseq, s);
+        else attention_bf16_tc((const bf16*)qkv, (bf16*)attn, nseq, s);
+      } else {
+        attention_f32((const float*)qkv, (float*)attn, nseq, s);
+      }
     }
     {
       GemmOp op;
-      op.M = M, op.N = EMB, op.K = EMB, op.A = attn, op.lda = EMB, op.Wt = k.proj_w, op.bias = k.proj_b;
-      op.gamma = k.g1, op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
+      op.N = EMB, op.K = EMB, op.A = attn, op.lda = EMB;
+      op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
+      grouped(op, SEQ, false);
+      for (int g = 0; g < 3; ++g)
+        op.grp[g].Wt = vw[g]->blk[i].proj_w, op.grp[g].bias = vw[g]->blk[i].proj_b, op.grp[g].gamma = vw[g]->blk[i].g1;
       gemm(prec_, op, s);
     }
     {
       ProfScope ps(s, KC_LAYERNORM, static_cast<double>(M) * EMB * (4 + sizeof(T)));
-      layernorm_rows<T>(resid, xn, k.n2w, k.n2b, M, RowMap(), 1, s);
+      for (int g = 0; g < 3; ++g) lg.w[g] = vw[g]->blk[i].n2w, lg.b[g] = vw[g]->blk[i].n2b;
+      layernorm_rows_grouped<T>(resid, xn, lg, M, s);
     }
     {
       GemmOp op;
-      op.M = M, op.N = 4 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.Wt = k.fc1_w, op.bias = k.fc1_b;
-      op.act = ACT_GELU, op.out = hid, op.ldo = 4 * EMB;
+      op.N = 4 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.act = ACT_GELU, op.out = hid, op.ldo = 4 * EMB;
+      grouped(op, SEQ, false);
+      for (int g = 0; g < 3; ++g) op.grp[g].Wt = vw[g]->blk[i].fc1_w, op.grp[g].bias = vw[g]->blk[i].fc1_b;
       gemm(prec_, op, s);
     }
     {
       GemmOp op;
-      op.M = M, op.N = EMB, op.K = 4 * EMB, op.A = hid, op.lda = 4 * EMB, op.Wt = k.fc2_w, op.bias = k.fc2_b;
-      op.gamma = k.g2, op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
+      op.N = EMB, op.K = 4 * EMB, op.A = hid, op.lda = 4 * EMB;
+      op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
+      grouped(op, SEQ, false);
+      for (int g = 0; g < 3; ++g)
+        op.grp[g].Wt = vw[g]->blk[i].fc2_w, op.grp[g].bias = vw[g]->blk[i].fc2_b, op.grp[g].gamma = vw[g]->blk[i].g2;
       gemm(prec_, op, s);
     }
-    if (hooks && (i == 5 || i == 11)) {
-      // forward hooks on blocks 5 / 11 (encoder.py:133-144): pre-norm residual stream of the 25
-      // level-0 patches, cls dropped, merged with padding 3 (encoder.py:268-289)
+    if (i == 5 || i == 11) {
+      // forward hooks on blocks 5 / 11 of the PATCH encoder (encoder.py:133-144): pre-norm residual
+      // stream of the 25 level-0 patches, cls dropped, merged with padding 3 (encoder.py:268-289)
       RowMap m;
       m.mode = 1, m.S = 96, m.steps = 5, m.pad = 3, m.patch_base = 0;
       layernorm_rows<T>(resid, (T*)(i == 5 ? lat0m_ : lat1m_), nullptr, nullptr, (long long)B * 96 * 96, m, 0, s);
@@ -449,11 +497,9 @@ void Engine::run_vit(const VitWeights& w, const T* A, int nseq, float* resid, T*
 // ============================================================================ forward
 template <typename T>
 void Engine::forward_impl(const float* x, int B, float* canon, float* fov_deg, cudaStream_t s) {
-  split_im2col<T>(x, B, (T*)A35_, (T*)A1_, s);
-
-  // patch encoder over 35*B sequences (encoder.py:266), then final norm fused with the merges
-  run_vit<T>(vit_patch_, (const T*)A35_, 35 * B, resid_, (T*)xn_, (T*)qkv_, (T*)attn_, (T*)hid_, true, B, s);
-  {
+  split_im2col<T>(x, B, (T*)A35_, (T*)A35_ + static_cast<size_t>(B) * 35 * 576 * 768, s);
+  run_vits<T>(B, s);
+  {  // final norms fused with the merges (encoder.py:267-305), one launch per consumer
     RowMap m;
     m.mode = 1, m.S = 96, m.steps = 5, m.pad = 3, m.patch_base = 0;
     layernorm_rows<T>(resid_, (T*)x0m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 96 * 96, m, 1, s);
@@ -461,16 +507,14 @@ void Engine::forward_impl(const float* x, int B, float* canon, float* fov_deg, c
     layernorm_rows<T>(resid_, (T*)x1m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 48 * 48, m, 1, s);
     m.S = 24, m.steps = 1, m.pad = 0, m.patch_base = 34;
     layernorm_rows<T>(resid_, (T*)x2m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 24 * 24, m, 1, s);
+    // image encoder (encoder.py:308-311) and fov encoder (fov.py:70-77): sequences 35B.. and 36B..
+    RowMap ms;
+    ms.mode = 1, ms.S = 24, ms.steps = 1, ms.pad = 0, ms.patch_base = 0, ms.sb = 1, ms.sp = 1;
+    ms.seq_off = 35 * B;
+    layernorm_rows<T>(resid_, (T*)globm_, vit_image_.norm_w, vit_image_.norm_b, (long long)B * 24 * 24, ms, 1, s);
+    ms.seq_off = 36 * B;
+    layernorm_rows<T>(resid_, (T*)fovtok_, vit_fov_.norm_w, vit_fov_.norm_b, (long long)B * 24 * 24, ms, 1, s);
   }
-  // image encoder on the 384^2 image (encoder.py:308-311)
-  RowMap ms;
-  ms.mode = 1, ms.S = 24, ms.steps = 1, ms.pad = 0, ms.patch_base = 0, ms.sb = 1, ms.sp = 1;
-  run_vit<T>(vit_image_, (const T*)A1_, B, resid_s_, (T*)xn_s_, (T*)qkv_s_, (T*)attn_s_, (T*)hid_s_, false, B, s);
-  layernorm_rows<T>(resid_s_, (T*)globm_, vit_image_.norm_w, vit_image_.norm_b, (long long)B * 24 * 24, ms, 1, s);
-  // fov encoder on the same image (fov.py:70-77)
-  run_vit<T>(vit_fov_, (const T*)A1_, B, resid_s_, (T*)xn_s_, (T*)qkv_s_, (T*)attn_s_, (T*)hid_s_, false, B, s);
-  layernorm_rows<T>(resid_s_, (T*)fovtok_, vit_fov_.norm_w, vit_fov_.norm_b, (long long)B * 24 * 24, ms, 1, s);
-
   for (int f = 0; f < B; ++f) decode_frame<T>(f, canon + static_cast<size_t>(f) * IMG * IMG, fov_deg + f, s);
   last_B_ = B;
 }
@@ -587,12 +631,17 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
     op.bias = F("fov.encoder.1.bias"), op.out = fovlin_, op.ldo = 128;
     gemm(prec_, op, s);
   }
-  conv_direct<T>((const T*)lowres_, F("fov.downsample.0.weight"), F("fov.downsample.0.bias"), (T*)fov_a_, 1, 48, 48, 256,
-                 128, 3, 2, 1, 1, (const T*)fovlin_, s);
-  conv_direct<T>((const T*)fov_a_, F("fov.head.0.weight"), F("fov.head.0.bias"), (T*)fov_b_, 1, 24, 24, 128, 64, 3, 2, 1, 1,
-                 nullptr, s);
-  conv_direct<T>((const T*)fov_b_, F("fov.head.2.weight"), F("fov.head.2.bias"), (T*)fov_c_, 1, 12, 12, 64, 32, 3, 2, 1, 1,
-                 nullptr, s);
+  // the three stride-2 3x3 convs (24^2, 12^2, 6^2 outputs) as im2col + tensor-core GEMM
+  auto conv_s2 = [&](const void* in, int S, int Cin, const std::string& name, int Cout, const void* addend, void* out) {
+    im2col_nhwc<T>((const T*)in, (T*)fovcol_, 1, S, S, Cin, 3, 2, 1, s);
+    GemmOp op;
+    op.M = (S / 2) * (S / 2), op.N = Cout, op.K = 9 * Cin, op.A = fovcol_, op.lda = 9 * Cin, op.Wt = W(name + ".weight");
+    op.bias = F(name + ".bias"), op.act = ACT_RELU, op.res = addend, op.ldres = Cout, op.out = out, op.ldo = Cout;
+    gemm(prec_, op, s);
+  };
+  conv_s2(lowres_, 48, 256, "fov.downsample.0", 128, fovlin_, fov_a_);  // relu(conv) + tokens (fov.py:78-79)
+  conv_s2(fov_a_, 24, 128, "fov.head.0", 64, nullptr, fov_b_);
+  conv_s2(fov_b_, 12, 64, "fov.head.2", 32, nullptr, fov_c_);
   fov_final<T>((const T*)fov_c_, F("fov.head.4.weight"), F("fov.head.4.bias"), fov_deg, 1, s);
 }
 
@@ -752,13 +801,16 @@ void Engine::conv3x3_test(int backend, const float* x, const float* w, const flo
 
 void Engine::attention_test(int backend, const float* qkv, float* out, int n, cudaStream_t s) {
   DP_CUDA(cudaSetDevice(device_));
-  if (backend == BF16) {
+  if (backend >= BF16) {
     const size_t nq = (size_t)n * SEQ * 3 * EMB, no = (size_t)n * SEQ * EMB;
     bf16* q = to_dev<bf16>(qkv, nq, s);
     bf16* o = nullptr;
     DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&o), no * 2, s));
-    attention_bf16(q, o, n, s);
+    if (backend == 2) attention_bf16(q, o, n, s);
+    else attention_bf16_tc(q, o, n, s);
     convert<bf16, float>(o, out, (long long)no, s);
+    DP_CUDA(cudaStreamSynchronize(s));
+    tmap_cache_clear();
     DP_CUDA(cudaFreeAsync(q, s));
     DP_CUDA(cudaFreeAsync(o, s));
   } else {

@@ -60,8 +60,7 @@ class Engine {
   template <typename T>
   void forward_impl(const float* x, int B, float* canon, float* fov_deg, cudaStream_t s);
   template <typename T>
-  void run_vit(const VitWeights& w, const T* A, int nseq, float* resid, T* xn, T* qkv, T* attn, T* hid, bool hooks, int B,
-               cudaStream_t s);
+  void run_vits(int B, cudaStream_t s);
   template <typename T>
   void decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s);
   template <typename T>
@@ -75,6 +74,7 @@ class Engine {
 
   int device_, prec_, max_batch_;
   bool finalized_ = false;
+  bool attn_legacy_ = false;
   std::map<std::string, std::vector<int64_t>> manifest_;
   std::unordered_map<std::string, Packed> packed_;
   std::vector<void*> allocs_;
@@ -89,16 +89,15 @@ class Engine {
   float* fov_ = nullptr;       // (max_batch) f32
   float* fpx_ = nullptr;       // (max_batch) f32
   float* fpx_in_ = nullptr;    // (max_batch) f32
-  void *A35_, *A1_;
-  float *resid_, *resid_s_;    // residual streams f32 (patch encoder; small encoders)
+  void* A35_;                  // im2col rows: 35*B patch sequences, then B copies of patch 34 (image/fov encoders)
+  float* resid_;               // residual stream f32, 37 sequences per frame (35 patch + image + fov)
   void *xn_, *qkv_, *attn_, *hid_;
-  void *xn_s_, *qkv_s_, *attn_s_, *hid_s_;
   void *lat0m_, *lat1m_, *x0m_, *x1m_, *x2m_, *globm_, *fovtok_;  // merged maps (max_batch frames)
   // per-frame decoder workspace
   void *u0a_, *u0b_, *u0c_, *enc0_, *enc0r_, *u1a_, *u1b_, *enc1_, *u2a_, *enc2_, *u3a_, *enc3_, *u4a_, *cat_, *enc4_;
   void *lowres_, *lowres_r_, *x1_, *x1r_, *t_, *x_, *xr_, *x2_, *y_, *feat_[5];
   void *h0_, *h1_;
-  void *fovlin_, *fov_a_, *fov_b_, *fov_c_;
+  void *fovlin_, *fov_a_, *fov_b_, *fov_c_, *fovcol_;
   int last_B_ = 0;
   // host-call staging
   void* himg_ = nullptr;

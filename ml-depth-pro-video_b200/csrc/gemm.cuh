@@ -11,7 +11,12 @@ void gemm_tc(const GemmOp& op, cudaStream_t stream);
 void tmap_cache_clear();
 
 inline void gemm(int prec, const GemmOp& op, cudaStream_t stream) {
-  const double flops = 2.0 * op.M * static_cast<double>(op.N) * op.K;
+  double rows = op.M;
+  if (op.ngroups > 1) {
+    rows = 0;
+    for (int i = 0; i < op.ngroups; ++i) rows += op.grp[i].M;
+  }
+  const double flops = 2.0 * rows * static_cast<double>(op.N) * op.K;
   if (prec == BF16) {
     ProfScope ps(stream, op.a_mode == A_CONV3X3 ? KC_CONV_TC : KC_GEMM_TC, flops);
     gemm_tc(op, stream);

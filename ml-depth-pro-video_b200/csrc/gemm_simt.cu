@@ -14,21 +14,29 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-__global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmOp op) {
+struct GroupTiles {
+  int mt_start[4];
+};
+
+__global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmOp op, const GroupTiles gt) {
   __shared__ __align__(16) float sA[2][BK][BM + 4];
   __shared__ __align__(16) float sB[2][BK][BN + 4];
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const long long m0 = static_cast<long long>(blockIdx.y) * BM;
+  const int mt = blockIdx.y;
+  const int gi = (mt >= gt.mt_start[1] ? 1 : 0) + (mt >= gt.mt_start[2] ? 1 : 0);
+  const GemmGroup& gp = op.grp[gi];
+  const long long m0 = static_cast<long long>(mt - gt.mt_start[gi]) * BM;  // row inside the group
+  const int Mg = gp.M;
   const int n0 = blockIdx.x * BN;
   const float* __restrict__ A = reinterpret_cast<const float*>(op.A);
-  const float* __restrict__ Wt = reinterpret_cast<const float*>(op.Wt);
+  const float* __restrict__ Wt = reinterpret_cast<const float*>(gp.Wt);
 
   // loader mapping: thread -> (row lr, 8 consecutive k starting at lk)
   const int lr = tid & 127, lk = (tid >> 7) * 8;
-  const long long am = m0 + lr;
-  const bool a_ok = am < op.M;
+  const long long am = gp.a_row_off + m0 + lr;
+  const bool a_ok = m0 + lr < Mg;
   int py = 0, px = 0;
   long long pb = 0;
   if (op.a_mode == A_CONV3X3 && a_ok) {
@@ -115,8 +123,9 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmOp op) {
   const float* res2 = reinterpret_cast<const float*>(op.res2);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-    const bool mok = m < op.M;
+    const long long ml = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    const bool mok = ml < Mg;
+    const long long m = gp.o_row_off + ml;
     float dot = 0.f;
     long long orow = 0;
     int p = 0;
@@ -133,10 +142,10 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmOp op) {
       const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (!mok || n >= op.N) continue;
       float v = acc[i][j];
-      if (op.bias) v += op.bias[op.bias_mod ? n % op.bias_mod : n];
+      if (gp.bias) v += gp.bias[op.bias_mod ? n % op.bias_mod : n];
       if (op.act == ACT_RELU) v = fmaxf(v, 0.f);
       else if (op.act == ACT_GELU) v = gelu_erf(v);
-      if (op.gamma) v *= op.gamma[n];
+      if (gp.gamma) v *= gp.gamma[n];
       long long off;
       if (op.out_mode == O_ROWMAJOR) {
         off = m * op.ldo + op.col_off + n;
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmOp op) {
         const long long b = by / op.H;
         off = ((b * 2 * op.H + 2 * y + (q >> 1)) * (2LL * op.W) + 2 * x + (q & 1)) * op.ldo + op.col_off + co;
       } else if (op.out_mode == O_PATCH_EMBED) {
-        v += op.pos[(1 + p) * static_cast<long long>(op.N) + n];
+        v += gp.pos[(1 + p) * static_cast<long long>(op.N) + n];
         off = orow * op.ldo + n;
       } else {
         dot = fmaf(v, op.dot_w[n], dot);
@@ -171,13 +180,22 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmOp op) {
 
 }  // namespace
 
-void gemm_simt(const GemmOp& op, cudaStream_t stream) {
+void gemm_simt(const GemmOp& op_in, cudaStream_t stream) {
+  GemmOp op = op_in;
+  op.finish();
   DP_CHECK(op.K % BK == 0, "gemm_simt: K must be a multiple of 16");
-  if (op.a_mode == A_CONV3X3) DP_CHECK(op.C % BK == 0 && op.K == 9 * op.C, "gemm_simt: bad conv shape");
+  if (op.a_mode == A_CONV3X3) DP_CHECK(op.C % BK == 0 && op.K == 9 * op.C && op.ngroups == 1, "gemm_simt: bad conv shape");
   else DP_CHECK(op.lda % 4 == 0, "gemm_simt: lda must be a multiple of 4");
   if (op.out_mode == O_DOT_RELU) DP_CHECK(op.N == 32, "O_DOT_RELU needs N == 32");
-  dim3 grid((op.N + BN - 1) / BN, (op.M + BM - 1) / BM);
-  gemm_simt_kernel<<<grid, NT, 0, stream>>>(op);
+  GroupTiles gt{};
+  int mt = 0;
+  for (int i = 0; i < 3; ++i) {
+    gt.mt_start[i] = mt;
+    if (i < op.ngroups) mt += (op.grp[i].M + BM - 1) / BM;
+  }
+  for (int i = op.ngroups; i < 4; ++i) gt.mt_start[i] = mt;
+  dim3 grid((op.N + BN - 1) / BN, mt);
+  gemm_simt_kernel<<<grid, NT, 0, stream>>>(op, gt);
   DP_LAUNCH_CHECK();
 }
 

@@ -38,10 +38,28 @@ constexpr int TILE_W = 16, TILE_H = 8;  // conv: 128 rows = 8 x 16 output pixels
 struct TileGeom {
   int m_tiles, n_tiles, k_blocks;
   int tiles_x, tiles_y;  // conv only
+  int mt_start[4];       // first m-tile of every group (grouped launches), mt_start[ngroups] = m_tiles
+};
+struct WeightMaps {
+  CUtensorMap b[3];      // one weight tensor map per group
 };
 
+__device__ __forceinline__ int tile_group(const TileGeom& g, int mt) {
+  return (mt >= g.mt_start[1] ? 1 : 0) + (mt >= g.mt_start[2] ? 1 : 0);
+}
+
+// GELU (exact-erf form) for the bf16 path: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far
+// below bf16 output rounding) on the MUFU rcp / ex2 units instead of the ~30-instruction erff().
+// 1 + erf(x/sqrt2) is formed without cancellation: p*e for x < 0, 2 - p*e for x >= 0.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float pe = p * t * exp2f(-1.4426950408889634f * z * z);
+  return 0.5f * x * (x < 0.f ? pe : 2.0f - pe);
 }
 
 template <typename T>
@@ -91,10 +109,14 @@ __device__ __forceinline__ void store32(bf16* p, const float (&v)[32], bool relu
 }
 
 // Epilogue for one output row `m` (linear row / NHWC pixel index) and 32 columns starting at n0.
-__device__ __forceinline__ void epilogue_chunk(const GemmOp& op, long long m, int n0, float (&v)[32]) {
+// `m_local` is the row inside its group (patch-embed token placement), `resv` the residual values
+// for these 32 columns, already loaded (and converted) by the caller so that the HBM round trip
+// overlaps the accumulator wait.
+__device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup& gp, long long m, int n0,
+                                               float (&v)[32], const float (&resv)[32]) {
   float t[32];
-  if (op.bias) {
-    load32<float>(op.bias + (op.bias_mod ? n0 % op.bias_mod : n0), t);
+  if (gp.bias) {
+    load32<float>(gp.bias + (op.bias_mod ? n0 % op.bias_mod : n0), t);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += t[j];
   }
@@ -105,8 +127,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, long long m, in
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   }
-  if (op.gamma) {
-    load32<float>(op.gamma + n0, t);
+  if (gp.gamma) {
+    load32<float>(gp.gamma + n0, t);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= t[j];
   }
@@ -123,12 +145,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, long long m, in
     const long long orow = (b * 2 * op.H + 2 * y + (q >> 1)) * (2LL * op.W) + 2 * x + (q & 1);
     off = orow * op.ldo + op.col_off + co;
   } else if (op.out_mode == O_PATCH_EMBED) {
-    const long long patch = m / 576;
-    const int p = static_cast<int>(m - patch * 576);
-    load32<float>(op.pos + (1 + p) * static_cast<long long>(op.N) + n0, t);
+    const long long seq = m / 576;
+    const int p = static_cast<int>(m - seq * 576);
+    load32<float>(gp.pos + (1 + p) * static_cast<long long>(op.N) + n0, t);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += t[j];
-    off = (patch * 577 + 1 + p) * op.ldo + n0;
+    off = (seq * 577 + 1 + p) * op.ldo + n0;
   } else {  // O_DOT_RELU: (already bias + ReLU'd) 32-channel pixel -> 1 channel
     load32<float>(op.dot_w, t);
     float s = op.dot_b[0];
@@ -139,13 +161,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, long long m, in
   }
 
   if (op.res) {
-    const long long roff = m * op.ldres + n0;
-    if (op.res_f32)
-      load32<float>(reinterpret_cast<const float*>(op.res) + roff, t);
-    else
-      load32<bf16>(reinterpret_cast<const bf16*>(op.res) + roff, t);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += t[j];
+    for (int j = 0; j < 32; ++j) v[j] += resv[j];
   }
   if (op.res2) {
     load32<bf16>(reinterpret_cast<const bf16*>(op.res2) + m * op.ldres + n0, t);
@@ -161,9 +178,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, long long m, in
   if (op.out_relu) store32(reinterpret_cast<bf16*>(op.out_relu) + off, v, true);
 }
 
+__device__ __forceinline__ void load_res(const GemmOp& op, long long m, int n0, float (&r)[32]) {
+  const long long roff = m * op.ldres + n0;
+  if (op.res_f32) load32<float>(reinterpret_cast<const float*>(op.res) + roff, r);
+  else load32<bf16>(reinterpret_cast<const bf16*>(op.res) + roff, r);
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ WeightMaps tmW,
                const GemmOp op, const TileGeom g) {
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
@@ -188,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
-    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmW.b[0]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -218,13 +241,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % g.n_tiles, mt = t / g.n_tiles;
-        int b = 0, y0 = 0, x0 = 0;
+        int b = 0, y0 = 0, x0 = 0, a_row = 0;
+        const CUtensorMap* tmB = &tmW.b[0];
         if (op.a_mode == A_CONV3X3) {
           const int per_img = g.tiles_x * g.tiles_y;
           b = mt / per_img;
           const int r = mt - b * per_img;
           y0 = (r / g.tiles_x) * TILE_H;
           x0 = (r % g.tiles_x) * TILE_W;
+        } else {
+          const int gi = tile_group(g, mt);
+          a_row = static_cast<int>(op.grp[gi].a_row_off) + (mt - g.mt_start[gi]) * BM;
+          tmB = &tmW.b[gi];
         }
         for (int kb = 0; kb < g.k_blocks; ++kb) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
@@ -235,9 +263,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ky = tap / 3, kx = tap - ky * 3;
             ptx::tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b);
           } else {
-            ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, mt * BM);
+            ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, a_row);
           }
-          ptx::tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, nt * BN);
+          ptx::tma_load_2d(sB + s * B_BYTES, tmB, &full[s], kb * BK, nt * BN);
           if (++s == STAGES) s = 0, ph ^= 1;
         }
       }
@@ -283,6 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nt = t % g.n_tiles, mt = t / g.n_tiles;
       long long m;
       bool valid;
+      int gi = 0;
       if (op.a_mode == A_CONV3X3) {
         const int per_img = g.tiles_x * g.tiles_y;
         const int b = mt / per_img;
@@ -292,23 +321,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         m = (static_cast<long long>(b) * op.H + y) * op.W + x;
         valid = true;
       } else {
-        m = static_cast<long long>(mt) * BM + row;
-        valid = m < op.M;
+        gi = tile_group(g, mt);
+        const int m_local = (mt - g.mt_start[gi]) * BM + row;
+        valid = m_local < op.grp[gi].M;
+        m = op.grp[gi].o_row_off + m_local;
       }
+      const GemmGroup& gp = op.grp[gi];
+      const bool active = (BN >= 64 || grp == 0);
+      const bool has_res = op.res != nullptr && valid && active;
+      const int col0 = nt * BN + grp * COLS_PER_GRP;
+      float resv[32];
+      if (has_res) load_res(op, m, col0, resv);  // in flight while the MMA of this tile finishes
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
-      if (BN >= 64 || grp == 0) {
+      if (active) {
 #pragma unroll 1
         for (int c = 0; c < COLS_PER_GRP; c += 32) {
-          const int col = grp * COLS_PER_GRP + c;
           uint32_t r[32];
-          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col, r);
+          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + grp * COLS_PER_GRP + c, r);
+          float resn[32];
+          if (has_res && c + 32 < COLS_PER_GRP) load_res(op, m, col0 + c + 32, resn);
           ptx::tmem_ld_wait();
           if (valid) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_chunk(op, m, nt * BN + col, v);
+            epilogue_chunk(op, gp, m, col0 + c, v, resv);
+          }
+          if (has_res && c + 32 < COLS_PER_GRP) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) resv[j] = resn[j];
           }
         }
       }
@@ -397,7 +439,7 @@ int num_sms() {
 }
 
 template <int BN>
-void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB,
+void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const WeightMaps& tmW,
             cudaStream_t stream) {
   constexpr size_t SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
   static bool configured = false;
@@ -407,7 +449,7 @@ void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const C
   }
   const int tiles = g.m_tiles * g.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, SMEM, stream>>>(tmA, tmB, op, g);
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, SMEM, stream>>>(tmA, tmW, op, g);
   DP_LAUNCH_CHECK();
 }
 
@@ -415,45 +457,71 @@ void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const C
 
 void tmap_cache_clear() { tmap_cache().clear(); }
 
-void gemm_tc(const GemmOp& op, cudaStream_t stream) {
+// 2D row-major bf16 matrix (rows x cols, leading dimension ld_elems), 128B-swizzled box.
+const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                                    uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t str[1] = {ld_elems * 2};
+  const uint32_t box[2] = {box_cols, box_rows};
+  return get_tmap(ptr, 2, dims, str, box);
+}
+
+void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
+  GemmOp op = op_in;
+  op.finish();
   DP_CHECK(op.K % BK == 0, "gemm_tc: K must be a multiple of 64");
   int bn = 0;
   if (op.N % 256 == 0) bn = 256;
   else if (op.N % 128 == 0) bn = 128;
+  else if (op.N % 64 == 0) bn = 64;
   else if (op.N == 32) bn = 32;
   DP_CHECK(bn != 0, "gemm_tc: unsupported N");
   if (op.out_mode == O_DOT_RELU) DP_CHECK(op.N == 32, "O_DOT_RELU needs N == 32");
   if (op.out_mode == O_CONVT2X2) DP_CHECK(op.cout % 32 == 0 && op.N == 4 * op.cout, "bad ConvT shape");
+  DP_CHECK(op.ngroups >= 1 && op.ngroups <= 3, "gemm_tc: 1..3 groups");
 
   TileGeom g{};
   g.n_tiles = op.N / bn;
   g.k_blocks = op.K / BK;
   const CUtensorMap* tmA;
   if (op.a_mode == A_CONV3X3) {
+    DP_CHECK(op.ngroups == 1, "conv3x3 launches are not grouped");
     DP_CHECK(op.C % BK == 0 && op.K == 9 * op.C, "conv3x3: C must be a multiple of 64");
     DP_CHECK(op.W % TILE_W == 0 && op.H % TILE_H == 0, "conv3x3: H, W must be multiples of 8, 16");
     g.tiles_x = op.W / TILE_W;
     g.tiles_y = op.H / TILE_H;
     g.m_tiles = op.B * g.tiles_x * g.tiles_y;
+    g.mt_start[0] = 0, g.mt_start[1] = g.mt_start[2] = g.mt_start[3] = g.m_tiles;
     const uint64_t dims[4] = {(uint64_t)op.C, (uint64_t)op.W, (uint64_t)op.H, (uint64_t)op.B};
     const uint64_t str[3] = {(uint64_t)op.C * 2, (uint64_t)op.W * op.C * 2, (uint64_t)op.H * op.W * op.C * 2};
     const uint32_t box[4] = {BK, TILE_W, TILE_H, 1};
     tmA = &get_tmap(op.A, 4, dims, str, box);
   } else {
-    g.m_tiles = (op.M + BM - 1) / BM;
-    const uint64_t dims[2] = {(uint64_t)op.K, (uint64_t)op.M};
+    int mt = 0;
+    for (int i = 0; i < 3; ++i) {
+      g.mt_start[i] = mt;
+      if (i < op.ngroups) mt += (op.grp[i].M + BM - 1) / BM;
+    }
+    g.mt_start[3] = mt;
+    for (int i = op.ngroups; i < 3; ++i) g.mt_start[i] = mt;
+    g.m_tiles = mt;
+    // one map over every addressable row: a group's last tile may read rows of the next group
+    // (rows are independent; the epilogue masks them), the very last tile is zero-filled by TMA
+    const uint64_t dims[2] = {(uint64_t)op.K, (uint64_t)op.a_rows};
     const uint64_t str[1] = {(uint64_t)op.lda * 2};
     const uint32_t box[2] = {BK, BM};
     tmA = &get_tmap(op.A, 2, dims, str, box);
   }
+  WeightMaps tmW;
   const uint64_t wd[2] = {(uint64_t)op.K, (uint64_t)op.N};
   const uint64_t ws[1] = {(uint64_t)op.K * 2};
   const uint32_t wb[2] = {BK, (uint32_t)bn};
-  const CUtensorMap& tmB = get_tmap(op.Wt, 2, wd, ws, wb);
+  for (int i = 0; i < 3; ++i) tmW.b[i] = get_tmap(op.grp[i < op.ngroups ? i : 0].Wt, 2, wd, ws, wb);
 
-  if (bn == 256) launch<256>(op, g, *tmA, tmB, stream);
-  else if (bn == 128) launch<128>(op, g, *tmA, tmB, stream);
-  else launch<32>(op, g, *tmA, tmB, stream);
+  if (bn == 256) launch<256>(op, g, *tmA, tmW, stream);
+  else if (bn == 128) launch<128>(op, g, *tmA, tmW, stream);
+  else if (bn == 64) launch<64>(op, g, *tmA, tmW, stream);
+  else launch<32>(op, g, *tmA, tmW, stream);
 }
 
 }  // namespace dp

@@ -158,15 +158,19 @@ __device__ __forceinline__ long long map_row(const RowMap& m, long long d) {
   }
   const int ty = y - j * stride, tx = x - i * stride;
   const int patch = m.patch_base + j * m.steps + i;
-  return (b * m.sb + static_cast<long long>(patch) * m.sp) * 577 + 1 + ty * 24 + tx;
+  return (m.seq_off + b * m.sb + static_cast<long long>(patch) * m.sp) * 577 + 1 + ty * 24 + tx;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, T* __restrict__ out,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                        long long n_out, RowMap map, int ln) {
+                                                        long long n_out, RowMap map, int ln, LnGroups grp) {
   const long long d = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (d >= n_out) return;
+  if (grp.n > 1) {
+    const int gi = (d >= grp.end[0] ? 1 : 0) + (d >= grp.end[1] ? 1 : 0);
+    w = grp.w[gi], bias = grp.b[gi];
+  }
   const int lane = threadIdx.x & 31;
   const float4* src = reinterpret_cast<const float4*>(in + map_row(map, d) * 1024);
   float4 v[8];
@@ -251,6 +255,24 @@ __global__ void conv_direct_kernel(const T* __restrict__ x, const float* __restr
     if (add_tokens) acc += to_f(add_tokens[static_cast<long long>(o) * Cout + co]);
     y[static_cast<long long>(o) * Cout + co] = from_f<T>(acc);
   }
+}
+
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ cols, int B, int H, int W, int C, int k,
+                              int stride, int pad, int Ho, int Wo) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int K = k * k * C;
+  const long long total = static_cast<long long>(B) * Ho * Wo * K;
+  if (idx >= total) return;
+  const int kk = static_cast<int>(idx % K);
+  const long long m = idx / K;
+  const int c = kk % C, tap = kk / C;
+  const int ox = static_cast<int>(m % Wo), oy = static_cast<int>((m / Wo) % Ho);
+  const long long b = m / (static_cast<long long>(Wo) * Ho);
+  const int yy = oy * stride - pad + tap / k, xx = ox * stride - pad + tap % k;
+  T v = from_f<T>(0.f);
+  if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((b * H + yy) * W + xx) * C + c];
+  cols[idx] = v;
 }
 
 template <typename T>
@@ -577,9 +599,16 @@ void write_cls_rows(float* resid, const float* cls, const float* pos, int nseq, 
 template <typename T>
 void layernorm_rows(const float* in, T* out, const float* w, const float* b, long long n_out, RowMap map, int ln,
                     cudaStream_t s) {
-  layernorm_kernel<T><<<blocks_for(n_out, 8), 256, 0, s>>>(in, out, w, b, n_out, map, ln);
+  layernorm_kernel<T><<<blocks_for(n_out, 8), 256, 0, s>>>(in, out, w, b, n_out, map, ln, LnGroups());
   DP_LAUNCH_CHECK();
 }
+template <typename T>
+void layernorm_rows_grouped(const float* in, T* out, const LnGroups& g, long long n_out, cudaStream_t s) {
+  layernorm_kernel<T><<<blocks_for(n_out, 8), 256, 0, s>>>(in, out, g.w[0], g.b[0], n_out, RowMap(), 1, g);
+  DP_LAUNCH_CHECK();
+}
+template void layernorm_rows_grouped<float>(const float*, float*, const LnGroups&, long long, cudaStream_t);
+template void layernorm_rows_grouped<bf16>(const float*, bf16*, const LnGroups&, long long, cudaStream_t);
 template void layernorm_rows<float>(const float*, float*, const float*, const float*, long long, RowMap, int, cudaStream_t);
 template void layernorm_rows<bf16>(const float*, bf16*, const float*, const float*, long long, RowMap, int, cudaStream_t);
 
@@ -603,6 +632,16 @@ template void conv_direct<float>(const float*, const float*, const float*, float
                                  int, int, const float*, cudaStream_t);
 template void conv_direct<bf16>(const bf16*, const float*, const float*, bf16*, int, int, int, int, int, int, int, int,
                                 int, const bf16*, cudaStream_t);
+
+template <typename T>
+void im2col_nhwc(const T* x, T* cols, int B, int H, int W, int C, int k, int stride, int pad, cudaStream_t s) {
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * k * k * C;
+  im2col_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(x, cols, B, H, W, C, k, stride, pad, Ho, Wo);
+  DP_LAUNCH_CHECK();
+}
+template void im2col_nhwc<float>(const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+template void im2col_nhwc<bf16>(const bf16*, bf16*, int, int, int, int, int, int, int, cudaStream_t);
 
 template <typename T>
 void fov_final(const T* x, const float* w_hwio, const float* bias, float* fov_deg, int B, cudaStream_t s) {

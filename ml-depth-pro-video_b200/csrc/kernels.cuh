@@ -29,13 +29,23 @@ struct RowMap {
   int steps = 1;      // patches per side
   int pad = 0;        // tokens cropped on interior edges
   int patch_base = 0; // first patch of this pyramid level inside a frame's 35
-  int sb = 35, sp = 1;  // source sequence index = b*sb + patch*sp
+  int sb = 35, sp = 1;  // source sequence index = seq_off + b*sb + patch*sp
+  int seq_off = 0;
 };
 // LayerNorm over C=1024 (eps 1e-6) of gathered rows; `ln` == 0 copies/converts only.
 // in: fp32 rows of width 1024; out: T rows (n_out x 1024).
+// Grouped launches: rows [0, end[0]) use (w[0], b[0]), [end[0], end[1]) use (w[1], b[1]), ...
+struct LnGroups {
+  int n = 1;
+  long long end[3] = {0, 0, 0};
+  const float* w[3] = {nullptr, nullptr, nullptr};
+  const float* b[3] = {nullptr, nullptr, nullptr};
+};
 template <typename T>
 void layernorm_rows(const float* in, T* out, const float* w, const float* b, long long n_out,
                     RowMap map, int ln, cudaStream_t s);
+template <typename T>
+void layernorm_rows_grouped(const float* in, T* out, const LnGroups& g, long long n_out, cudaStream_t s);
 // generic-width gather without LN (used by dp_merge): in (nseq,577,C) f32 -> out (B,S,S,C) f32
 void merge_rows_f32(const float* in, float* out, int B, int C, RowMap map, cudaStream_t s);
 
@@ -45,6 +55,10 @@ void merge_rows_f32(const float* in, float* out, int B, int C, RowMap map, cudaS
 template <typename T>
 void conv_direct(const T* x, const float* w_hwio, const float* bias, T* y, int B, int H, int W, int Cin,
                  int Cout, int k, int stride, int pad, int relu, const T* add_tokens, cudaStream_t s);
+// im2col for small strided convolutions: NHWC (B,H,W,C) -> rows (B*Ho*Wo, k*k*C), tap-major
+// (column = (ky*k + kx)*C + c, matching the O(HW)I weight packing); out-of-image taps are zero.
+template <typename T>
+void im2col_nhwc(const T* x, T* cols, int B, int H, int W, int C, int k, int stride, int pad, cudaStream_t s);
 // final 6x6 valid conv over (B,6,6,32) -> fov_deg[B] (fp32)
 template <typename T>
 void fov_final(const T* x, const float* w_hwio, const float* bias, float* fov_deg, int B, cudaStream_t s);

@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+rm -f gpurun_out/summary.txt
+runall() { name=$1; shift; timeout $1 python -m pytest "${@:2}" -m gpu -q -rA --no-header -p no:cacheprovider > gpurun_out/$name.log 2>&1; echo "$name exit $?" >> gpurun_out/summary.txt; }
+runall t_attn 300 tests/test_gpu_cores.py::test_attention
+runall t_model 1200 tests/test_gpu_model.py -s -k "bf16 or batch"
+timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench_default exit $?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt; tail -25 gpurun_out/t_attn.log; grep -E "fp32|bf16|tap|PASS|FAIL|Error|error" gpurun_out/t_model.log | head -40; python -c "
+import json; d=json.load(open('gpurun_out/bench_default.json')); print(d['value'], d['ms_per_step'], d['clocks']); print(json.dumps(d['kernels'],indent=1))"
