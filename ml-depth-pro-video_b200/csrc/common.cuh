@@ -77,6 +77,9 @@ enum OutMode {
                      //   -> out[((b*2H + 2y+dy)*2W + 2x+dx)*ldo + col_off + co]
   O_PATCH_EMBED = 2, // m = patch*576 + p -> row patch*577 + 1 + p, plus pos_embed[1+p][n]
   O_DOT_RELU = 3,    // head.2 + ReLU + head.4 (1x1, 32->1) + ReLU: out[m] (fp32), N must be 32
+  O_HEAD_FUSED = 4,  // head.1 (ConvT 2x2) o head.2 (conv3x3) pre-composed into one 3x3 conv over the
+                     //   768^2 map with N = 4 parities x 32; per parity: + border-aware bias, ReLU,
+                     //   head.4 dot (32->1), ReLU -> out[(2y+py)*2W + 2x+px] (fp32)
 };
 
 // One GEMM / implicit-GEMM convolution launch, shared by the fp32 SIMT and bf16 tcgen05 cores.
@@ -124,6 +127,7 @@ struct GemmOp {
   const float* pos = nullptr;   // O_PATCH_EMBED: pos_embed (577, N) fp32
   const float* dot_w = nullptr; // O_DOT_RELU: head.4 weight (32), dot_b: bias (1)
   const float* dot_b = nullptr;
+  const float* head_cb = nullptr;  // O_HEAD_FUSED: [9][32] per-tap bias terms, then [32] full bias
   // groups
   int ngroups = 1;
   GemmGroup grp[3];

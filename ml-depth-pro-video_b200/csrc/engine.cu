@@ -192,6 +192,7 @@ Engine::~Engine() {
   cudaDeviceSynchronize();
   for (void* p : allocs_) cudaFree(p);
   for (auto& kv : packed_) cudaFree(kv.second.ptr);
+  for (auto& kv : raw_) cudaFree(kv.second.ptr);
   if (stage_) cudaFree(stage_);
   if (himg_) cudaFree(himg_);
   if (hdepth_) cudaFree(hdepth_);
@@ -229,6 +230,15 @@ void Engine::set_weight(const std::string& name, const void* data, const int64_t
     src = stage_;
   }
   const bool bf = prec_ == BF16;
+  if (bf && (name == "head.1.weight" || name == "head.1.bias" || name == "head.2.weight" || name == "head.2.bias")) {
+    Packed& rw = raw_[name];
+    if (rw.bytes != n * 4) {
+      if (rw.ptr) DP_CUDA(cudaFree(rw.ptr));
+      DP_CUDA(cudaMalloc(&rw.ptr, n * 4));
+      rw.bytes = n * 4;
+    }
+    DP_CUDA(cudaMemcpy(rw.ptr, src, n * 4, cudaMemcpyDeviceToDevice));
+  }
   Packed& pk = packed_[name];
   auto ensure = [&](size_t bytes) {
     if (pk.bytes != bytes) {
@@ -307,6 +317,15 @@ void Engine::finalize() {
   vit_patch_ = vit_weights("encoder.patch_encoder.");
   vit_image_ = vit_weights("encoder.image_encoder.");
   vit_fov_ = vit_weights("fov.encoder.0.");
+  if (prec_ == BF16) {
+    // exact-linear fusion head.1 o head.2 (no nonlinearity in between, depth_pro.py:182-201),
+    // composed in fp32 from the fp32 originals, then rounded to bf16 once
+    if (!head_wc_) head_wc_ = alloc(128 * 1152 * 2), head_cb_ = (float*)alloc(10 * 32 * 4);
+    auto R = [&](const char* k) { return reinterpret_cast<const float*>(raw_.at(k).ptr); };
+    compose_head(R("head.1.weight"), R("head.1.bias"), R("head.2.weight"), R("head.2.bias"), (bf16*)head_wc_, head_cb_,
+                 nullptr);
+    DP_CUDA(cudaStreamSynchronize(nullptr));
+  }
   if (finalized_) return;  // workspace already allocated; weights re-bound above
 
   const size_t e = esz();
@@ -344,7 +363,7 @@ void Engine::finalize() {
   const size_t fs[5] = {P768, P768, P384, P192, P96};  // feat_[i] = output of fusion i
   for (int i = 0; i < 5; ++i) feat_[i] = alloc(fs[i] * 256 * e);
   h0_ = alloc(P768 * 128 * e);
-  h1_ = alloc(static_cast<size_t>(IMG) * IMG * 128 * e);
+  h1_ = prec_ == BF16 ? nullptr : alloc(static_cast<size_t>(IMG) * IMG * 128 * e);  // bf16 mode fuses head.1 into head.2
   fovcol_ = alloc(P24 * 2304 * e);
   fovlin_ = alloc(P24 * 128 * e), fov_a_ = alloc(P24 * 128 * e), fov_b_ = alloc(12 * 12 * 64 * e),
   fov_c_ = alloc(6 * 6 * 32 * e);
@@ -615,8 +634,16 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
 
   // ---- depth head (depth_pro.py:182-204)
   conv3x3(feat_[0], 768, 256, "head.0.weight", 128, F("head.0.bias"), ACT_NONE, nullptr, nullptr, h0_, nullptr);
-  convT(h0_, 768, 128, "head.1.weight", 128, h1_, 128, 0, F("head.1.bias"), nullptr);
-  {
+  if (prec_ == BF16) {
+    // head.1 (ConvT) + head.2 (conv3x3) + ReLU + head.4 (1x1) + ReLU as ONE conv over the 768^2 map:
+    // the 604 MB 128x1536^2 intermediate is never materialised and 77 GF of ConvT work disappears
+    GemmOp op;
+    op.M = 768 * 768, op.N = 128, op.K = 9 * 128, op.A = h0_, op.a_mode = A_CONV3X3, op.B = 1, op.H = 768, op.W = 768, op.C = 128;
+    op.Wt = head_wc_, op.head_cb = head_cb_, op.out = canon, op.out_f32 = 1, op.out_mode = O_HEAD_FUSED;
+    op.dot_w = F("head.4.weight"), op.dot_b = F("head.4.bias");
+    gemm(prec_, op, s);
+  } else {
+    convT(h0_, 768, 128, "head.1.weight", 128, h1_, 128, 0, F("head.1.bias"), nullptr);
     GemmOp op;
     op.M = IMG * IMG, op.N = 32, op.K = 9 * 128, op.A = h1_, op.a_mode = A_CONV3X3, op.B = 1, op.H = IMG, op.W = IMG, op.C = 128;
     op.Wt = W("head.2.weight"), op.bias = F("head.2.bias"), op.act = ACT_RELU;

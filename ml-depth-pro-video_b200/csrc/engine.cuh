@@ -77,6 +77,7 @@ class Engine {
   bool attn_legacy_ = false;
   std::map<std::string, std::vector<int64_t>> manifest_;
   std::unordered_map<std::string, Packed> packed_;
+  std::unordered_map<std::string, Packed> raw_;  // fp32 originals needed for weight composition
   std::vector<void*> allocs_;
   float* stage_ = nullptr;  // staging buffer for host -> device weight upload
   size_t stage_bytes_ = 0;
@@ -97,6 +98,8 @@ class Engine {
   void *u0a_, *u0b_, *u0c_, *enc0_, *enc0r_, *u1a_, *u1b_, *enc1_, *u2a_, *enc2_, *u3a_, *enc3_, *u4a_, *cat_, *enc4_;
   void *lowres_, *lowres_r_, *x1_, *x1r_, *t_, *x_, *xr_, *x2_, *y_, *feat_[5];
   void *h0_, *h1_;
+  void* head_wc_ = nullptr;    // composed head.1 o head.2 weights (bf16 mode)
+  float* head_cb_ = nullptr;
   void *fovlin_, *fov_a_, *fov_b_, *fov_c_, *fovcol_;
   int last_B_ = 0;
   // host-call staging

@@ -16,6 +16,7 @@
 //   warps 4-11  epilogue      : tcgen05.ld (thread = one output row, 32 columns per load),
 //                               bias / GELU / ReLU / LayerScale / residual / pixel-shuffle
 //                               scatter, vectorised global stores; overlaps the next tile's MMA.
+#include <cstdlib>
 #include <unordered_map>
 #include <vector>
 
@@ -35,17 +36,21 @@ constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;
 constexpr int TILE_W = 16, TILE_H = 8;  // conv: 128 rows = 8 x 16 output pixels
 
+// m-tiles are scheduled in UNITS of CL tiles (CL = cluster size: the CTAs of a cluster run CL
+// adjacent m-tiles of the same n-tile in lockstep and share the weight tile by TMA multicast).
+// A unit never straddles a group: every group is padded to a whole number of units.
 struct TileGeom {
-  int m_tiles, n_tiles, k_blocks;
+  int m_units, n_tiles, k_blocks;
   int tiles_x, tiles_y;  // conv only
-  int mt_start[4];       // first m-tile of every group (grouped launches), mt_start[ngroups] = m_tiles
+  int unit_start[4];     // first unit of every group, unit_start[ngroups..3] = m_units
+  int tiles_in_group[3]; // real m-tiles per group (tiles beyond are padding: loaded, not stored)
 };
 struct WeightMaps {
   CUtensorMap b[3];      // one weight tensor map per group
 };
 
-__device__ __forceinline__ int tile_group(const TileGeom& g, int mt) {
-  return (mt >= g.mt_start[1] ? 1 : 0) + (mt >= g.mt_start[2] ? 1 : 0);
+__device__ __forceinline__ int unit_group(const TileGeom& g, int mu) {
+  return (mu >= g.unit_start[1] ? 1 : 0) + (mu >= g.unit_start[2] ? 1 : 0);
 }
 
 // GELU (exact-erf form) for the bf16 path: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far
@@ -151,6 +156,32 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += t[j];
     off = (seq * 577 + 1 + p) * op.ldo + n0;
+  } else if (op.out_mode == O_HEAD_FUSED) {
+    // chunk = one output parity (py, px) of coarse pixel m = (y, x); v = composed conv result.
+    const int par = n0 >> 5, py = par >> 1, px = par & 1;
+    const int x = static_cast<int>(m % op.W), y = static_cast<int>(m / op.W);
+    const int Y = 2 * y + py, X = 2 * x + px, HH = 2 * op.H, WW = 2 * op.W;
+    load32<float>(op.head_cb + 9 * 32, t);  // b2 + sum of all 9 tap terms (interior pixels)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += t[j];
+    if (Y == 0 || Y == HH - 1 || X == 0 || X == WW - 1) {
+      // zero padding of the fine-resolution conv: taps that fall outside carry no head.1 bias
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = Y + ky - 1, xx = X + kx - 1;
+          if (yy < 0 || yy >= HH || xx < 0 || xx >= WW) {
+            load32<float>(op.head_cb + (ky * 3 + kx) * 32, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] -= t[j];
+          }
+        }
+    }
+    load32<float>(op.dot_w, t);
+    float s = op.dot_b[0];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s = fmaf(fmaxf(v[j], 0.f), t[j], s);
+    reinterpret_cast<float*>(op.out)[static_cast<long long>(Y) * WW + X] = fmaxf(s, 0.f);
+    return;
   } else {  // O_DOT_RELU: (already bias + ReLU'd) 32-channel pixel -> 1 channel
     load32<float>(op.dot_w, t);
     float s = op.dot_b[0];
@@ -184,7 +215,7 @@ __device__ __forceinline__ void load_res(const GemmOp& op, long long m, int n0, 
   else load32<bf16>(reinterpret_cast<const bf16*>(op.res) + roff, r);
 }
 
-template <int BN>
+template <int BN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ WeightMaps tmW,
                const GemmOp op, const TileGeom g) {
@@ -207,7 +238,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = g.m_tiles * g.n_tiles;
+  const int total_units = g.m_units * g.n_tiles;
+  const int crank = CL > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;  // cluster index / number of clusters
+  constexpr uint16_t MC_MASK = (1u << CL) - 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -216,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&empty[s], CL);  // every CTA of the cluster must release a stage
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
@@ -230,7 +264,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // peers' barriers must be initialised before any remote arrive
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -239,19 +274,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % g.n_tiles, mt = t / g.n_tiles;
+      for (int t = cid; t < total_units; t += ncl) {
+        const int nt = t % g.n_tiles, mu = t / g.n_tiles;
         int b = 0, y0 = 0, x0 = 0, a_row = 0;
         const CUtensorMap* tmB = &tmW.b[0];
         if (op.a_mode == A_CONV3X3) {
+          const int mt = mu * CL + crank;  // padding tiles land beyond the last image: TMA zero-fills
           const int per_img = g.tiles_x * g.tiles_y;
           b = mt / per_img;
           const int r = mt - b * per_img;
           y0 = (r / g.tiles_x) * TILE_H;
           x0 = (r % g.tiles_x) * TILE_W;
         } else {
-          const int gi = tile_group(g, mt);
-          a_row = static_cast<int>(op.grp[gi].a_row_off) + (mt - g.mt_start[gi]) * BM;
+          const int gi = unit_group(g, mu);
+          const int lmt = (mu - g.unit_start[gi]) * CL + crank;
+          a_row = static_cast<int>(op.grp[gi].a_row_off) + lmt * BM;
           tmB = &tmW.b[gi];
         }
         for (int kb = 0; kb < g.k_blocks; ++kb) {
@@ -265,7 +302,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, a_row);
           }
-          ptx::tma_load_2d(sB + s * B_BYTES, tmB, &full[s], kb * BK, nt * BN);
+          if (CL > 1) {
+            // this CTA fetches 1/CL of the weight tile and multicasts it to the whole cluster
+            ptx::tma_load_2d_mc(sB + s * B_BYTES + crank * (B_BYTES / CL), tmB, &full[s], kb * BK,
+                                nt * BN + crank * (BN / CL), MC_MASK);
+          } else {
+            ptx::tma_load_2d(sB + s * B_BYTES, tmB, &full[s], kb * BK, nt * BN);
+          }
           if (++s == STAGES) s = 0, ph ^= 1;
         }
       }
@@ -276,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = cid; t < total_units; t += ncl, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
         ptx::mbar_wait(&tempty[acc], acc_ph ^ 1);
@@ -292,7 +335,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a0 + k * 32), ptx::umma_desc_sw128(b0 + k * 32),
                            IDESC, (kb | k) != 0);
           }
-          ptx::umma_commit(&empty[s]);
+          if (CL > 1) ptx::umma_commit_mc(&empty[s], MC_MASK);  // the peers' producers write into this stage too
+          else ptx::umma_commit(&empty[s]);
           if (++s == STAGES) s = 0, ph ^= 1;
         }
         ptx::umma_commit(&tfull[acc]);
@@ -305,24 +349,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int COLS_PER_GRP = (BN >= 64) ? BN / 2 : BN;
     const int row = q * 32 + lane;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = cid; t < total_units; t += ncl, ++it) {
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
-      const int nt = t % g.n_tiles, mt = t / g.n_tiles;
+      const int nt = t % g.n_tiles, mu = t / g.n_tiles;
       long long m;
       bool valid;
       int gi = 0;
       if (op.a_mode == A_CONV3X3) {
+        const int mt = mu * CL + crank;
         const int per_img = g.tiles_x * g.tiles_y;
         const int b = mt / per_img;
         const int r = mt - b * per_img;
         const int y = (r / g.tiles_x) * TILE_H + row / TILE_W;
         const int x = (r % g.tiles_x) * TILE_W + row % TILE_W;
         m = (static_cast<long long>(b) * op.H + y) * op.W + x;
-        valid = true;
+        valid = mt < g.tiles_in_group[0];
       } else {
-        gi = tile_group(g, mt);
-        const int m_local = (mt - g.mt_start[gi]) * BM + row;
+        gi = unit_group(g, mu);
+        const int m_local = ((mu - g.unit_start[gi]) * CL + crank) * BM + row;
         valid = m_local < op.grp[gi].M;
         m = op.grp[gi].o_row_off + m_local;
       }
@@ -359,8 +404,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  __syncwarp();
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // no CTA may exit while a peer can still multicast into it
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -438,19 +485,30 @@ int num_sms() {
   return n;
 }
 
-template <int BN>
+template <int BN, int CL>
 void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const WeightMaps& tmW,
             cudaStream_t stream) {
   constexpr size_t SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
   static bool configured = false;
   if (!configured) {
-    DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
-  const int tiles = g.m_tiles * g.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, SMEM, stream>>>(tmA, tmW, op, g);
-  DP_LAUNCH_CHECK();
+  const int units = g.m_units * g.n_tiles;
+  const int max_clusters = num_sms() / CL;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  DP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, tmA, tmW, op, g));
+  count_launch();
 }
 
 }  // namespace
@@ -477,12 +535,22 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   else if (op.N == 32) bn = 32;
   DP_CHECK(bn != 0, "gemm_tc: unsupported N");
   if (op.out_mode == O_DOT_RELU) DP_CHECK(op.N == 32, "O_DOT_RELU needs N == 32");
+  if (op.out_mode == O_HEAD_FUSED) DP_CHECK(op.N == 128 && op.B == 1 && op.a_mode == A_CONV3X3, "bad fused head");
   if (op.out_mode == O_CONVT2X2) DP_CHECK(op.cout % 32 == 0 && op.N == 4 * op.cout, "bad ConvT shape");
   DP_CHECK(op.ngroups >= 1 && op.ngroups <= 3, "gemm_tc: 1..3 groups");
 
   TileGeom g{};
   g.n_tiles = op.N / bn;
   g.k_blocks = op.K / BK;
+  // CTA pairs (cluster of 2 along M) share every weight tile through TMA multicast: the GEMMs are
+  // bound by L2->SM bandwidth (48 KB per 128x256x64 k-block), the pair cuts that to 32 KB per CTA.
+  int m_tiles_total = 0;
+  if (op.a_mode == A_CONV3X3) m_tiles_total = op.B * (op.W / TILE_W) * (op.H / TILE_H);
+  else
+    for (int i = 0; i < op.ngroups; ++i) m_tiles_total += (op.grp[i].M + BM - 1) / BM;
+  static const bool no_cluster = getenv("DEPTHPRO_NO_CLUSTER") != nullptr;  // debugging switch
+  const int cl = (!no_cluster && bn >= 128 && m_tiles_total * g.n_tiles >= num_sms()) ? 2 : 1;
+
   const CUtensorMap* tmA;
   if (op.a_mode == A_CONV3X3) {
     DP_CHECK(op.ngroups == 1, "conv3x3 launches are not grouped");
@@ -490,23 +558,28 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
     DP_CHECK(op.W % TILE_W == 0 && op.H % TILE_H == 0, "conv3x3: H, W must be multiples of 8, 16");
     g.tiles_x = op.W / TILE_W;
     g.tiles_y = op.H / TILE_H;
-    g.m_tiles = op.B * g.tiles_x * g.tiles_y;
-    g.mt_start[0] = 0, g.mt_start[1] = g.mt_start[2] = g.mt_start[3] = g.m_tiles;
+    g.tiles_in_group[0] = m_tiles_total;
+    g.m_units = (m_tiles_total + cl - 1) / cl;
+    g.unit_start[0] = 0, g.unit_start[1] = g.unit_start[2] = g.unit_start[3] = g.m_units;
     const uint64_t dims[4] = {(uint64_t)op.C, (uint64_t)op.W, (uint64_t)op.H, (uint64_t)op.B};
     const uint64_t str[3] = {(uint64_t)op.C * 2, (uint64_t)op.W * op.C * 2, (uint64_t)op.H * op.W * op.C * 2};
     const uint32_t box[4] = {BK, TILE_W, TILE_H, 1};
     tmA = &get_tmap(op.A, 4, dims, str, box);
   } else {
-    int mt = 0;
+    int mu = 0;
     for (int i = 0; i < 3; ++i) {
-      g.mt_start[i] = mt;
-      if (i < op.ngroups) mt += (op.grp[i].M + BM - 1) / BM;
+      g.unit_start[i] = mu;
+      g.tiles_in_group[i] = 0;
+      if (i < op.ngroups) {
+        g.tiles_in_group[i] = (op.grp[i].M + BM - 1) / BM;
+        mu += (g.tiles_in_group[i] + cl - 1) / cl;
+      }
     }
-    g.mt_start[3] = mt;
-    for (int i = op.ngroups; i < 3; ++i) g.mt_start[i] = mt;
-    g.m_tiles = mt;
+    g.unit_start[3] = mu;
+    for (int i = op.ngroups; i < 3; ++i) g.unit_start[i] = mu;
+    g.m_units = mu;
     // one map over every addressable row: a group's last tile may read rows of the next group
-    // (rows are independent; the epilogue masks them), the very last tile is zero-filled by TMA
+    // (rows are independent; the epilogue masks them), tiles past the end are zero-filled by TMA
     const uint64_t dims[2] = {(uint64_t)op.K, (uint64_t)op.a_rows};
     const uint64_t str[1] = {(uint64_t)op.lda * 2};
     const uint32_t box[2] = {BK, BM};
@@ -515,13 +588,16 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   WeightMaps tmW;
   const uint64_t wd[2] = {(uint64_t)op.K, (uint64_t)op.N};
   const uint64_t ws[1] = {(uint64_t)op.K * 2};
-  const uint32_t wb[2] = {BK, (uint32_t)bn};
+  const uint32_t wb[2] = {BK, (uint32_t)(bn / cl)};  // each CTA of a cluster loads bn / cl weight rows
   for (int i = 0; i < 3; ++i) tmW.b[i] = get_tmap(op.grp[i < op.ngroups ? i : 0].Wt, 2, wd, ws, wb);
 
-  if (bn == 256) launch<256>(op, g, *tmA, tmW, stream);
-  else if (bn == 128) launch<128>(op, g, *tmA, tmW, stream);
-  else if (bn == 64) launch<64>(op, g, *tmA, tmW, stream);
-  else launch<32>(op, g, *tmA, tmW, stream);
+  if (cl == 2) {
+    if (bn == 256) launch<256, 2>(op, g, *tmA, tmW, stream);
+    else launch<128, 2>(op, g, *tmA, tmW, stream);
+  } else if (bn == 256) launch<256, 1>(op, g, *tmA, tmW, stream);
+  else if (bn == 128) launch<128, 1>(op, g, *tmA, tmW, stream);
+  else if (bn == 64) launch<64, 1>(op, g, *tmA, tmW, stream);
+  else launch<32, 1>(op, g, *tmA, tmW, stream);
 }
 
 }  // namespace dp

@@ -567,9 +567,51 @@ __global__ void pack_hwio_kernel(const float* __restrict__ w, float* __restrict_
   out[i] = w[((static_cast<long long>(o) * I + ci) * KH + ky) * KW + kx];
 }
 
+__global__ void compose_head_w_kernel(const float* __restrict__ w1, const float* __restrict__ w2, bf16* __restrict__ wc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over [128][1152]
+  if (idx >= 128 * 1152) return;
+  const int k = idx % 1152, n = idx / 1152;
+  const int ci = k % 128, tap = k / 128, ty = tap / 3, tx = tap % 3;
+  const int c2 = n % 32, par = n / 32, py = par >> 1, px = par & 1;
+  float acc = 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int uy = py + ky + 1;  // (py + ky - 1) + 2
+    if ((uy >> 1) != ty) continue;
+    const int dy = uy & 1;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ux = px + kx + 1;
+      if ((ux >> 1) != tx) continue;
+      const int dx = ux & 1;
+      for (int c1 = 0; c1 < 128; ++c1)
+        acc = fmaf(w1[((ci * 128 + c1) * 2 + dy) * 2 + dx], w2[((c2 * 128 + c1) * 3 + ky) * 3 + kx], acc);
+    }
+  }
+  wc[idx] = __float2bfloat16_rn(acc);
+}
+__global__ void compose_head_b_kernel(const float* __restrict__ b1, const float* __restrict__ w2,
+                                      const float* __restrict__ b2, float* __restrict__ cb) {
+  const int c2 = threadIdx.x;  // 32 threads
+  float full = b2[c2];
+  for (int tap = 0; tap < 9; ++tap) {
+    float acc = 0.f;
+    for (int c1 = 0; c1 < 128; ++c1) acc = fmaf(b1[c1], w2[(c2 * 128 + c1) * 9 + tap], acc);
+    cb[tap * 32 + c2] = acc;
+    full += acc;
+  }
+  cb[9 * 32 + c2] = full;
+}
+
 }  // namespace
 
 // ============================================================================ host wrappers
+void compose_head(const float* w1, const float* b1, const float* w2, const float* b2, bf16* wc, float* cb,
+                  cudaStream_t s) {
+  compose_head_w_kernel<<<blocks_for(128 * 1152, 128), 128, 0, s>>>(w1, w2, wc);
+  DP_LAUNCH_CHECK();
+  compose_head_b_kernel<<<1, 32, 0, s>>>(b1, w2, b2, cb);
+  DP_LAUNCH_CHECK();
+}
+
 void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * 3 * IMG * IMG;
   resize_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, src_fmt, B, H, W, x);

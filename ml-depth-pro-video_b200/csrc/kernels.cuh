@@ -87,6 +87,12 @@ template <typename T>
 void pack_oihw_to_ohwi(const float* w, T* out, int O, int I, int KH, int KW, cudaStream_t s);  // conv
 template <typename T>
 void pack_convT_iohw(const float* w, T* out, int I, int O, cudaStream_t s);  // (I,O,2,2) -> ((dy,dx,o), i)
+// head.1 (ConvT 128->128 k2 s2, weight (ci,c1,2,2) + bias b1) followed by head.2 (conv3x3 128->32,
+// weight (c2,c1,3,3) + bias b2) composed in fp32 into one 3x3 conv over the coarse map:
+//   wc[(py*2+px)*32 + c2][(ty*3+tx)*128 + ci]  (bf16, [128][1152]);
+//   cb[tap][c2] = sum_c1 b1[c1]*w2[c2,c1,tap]  (9x32), cb[9][c2] = b2[c2] + sum_tap cb[tap][c2].
+void compose_head(const float* w1, const float* b1, const float* w2, const float* b2, bf16* wc, float* cb,
+                  cudaStream_t s);
 void pack_oihw_to_hwio_f32(const float* w, float* out, int O, int I, int KH, int KW, cudaStream_t s);
 
 }  // namespace dp

@@ -1,0 +1,86 @@
+"""-m gpu: the video add-on (frame stream, unprojection, colourise, frame-loop driver) through the
+drop-in API, checked against the oracle's numpy restatements of the reference scripts."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import depth_pro
+import depthpro_oracle as O
+from depth_pro import video
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def model():
+    return depth_pro.DepthPro(device=DEV, precision=torch.bfloat16).init_weights("stress", 1234).eval()
+
+
+def test_stream_matches_single_calls_and_order(model):
+    H, W, n = 270, 480, 5
+    frames = [O.synthetic_frame_u8(i, H, W) for i in range(n)]
+    stream = video.DepthStream(model, H, W, batch=2)
+    got = [(r.index, r.depth.copy(), r.focallength_px) for r in stream.run(enumerate(frames))]
+    assert [g[0] for g in got] == list(range(n))          # input order, ragged last batch included
+    for i, d, f in got:
+        one = model.infer(torch.from_numpy(frames[i]))
+        assert np.array_equal(d, one["depth"].cpu().numpy())  # batching / streaming never changes a bit
+        assert f == float(one["focallength_px"])
+    # sharded over 2 "ranks": union of the shards == the single-rank clip
+    shards = {}
+    for rank in range(2):
+        idx = video.shard_frames(n, rank, 2)
+        for r in video.DepthStream(model, H, W, batch=1).run((i, frames[i]) for i in idx):
+            shards[r.index] = r.depth.copy()
+    assert sorted(shards) == list(range(n))
+    assert all(np.array_equal(shards[i], got[i][1]) for i in range(n))
+
+
+def test_depth_to_3d_and_colours(model):
+    H, W = 270, 480
+    frame = O.synthetic_frame_u8(1, H, W)
+    pred = model.infer(torch.from_numpy(frame))
+    depth, f = pred["depth"], float(pred["focallength_px"])
+    pts, mask, cols = video.depth_to_3d(model, depth, pred["focallength_px"], W, H, rgb=torch.from_numpy(frame))
+    ref_pts, ref_mask = O.depth_to_3d(depth.cpu().numpy(), f, W, H)
+    assert np.array_equal(mask.cpu().numpy(), ref_mask) and pts.shape[0] == H * W  # clamp => every pixel valid
+    assert np.max(np.abs(pts.cpu().double().numpy() - ref_pts) / np.maximum(np.abs(ref_pts), 1e-3)) <= 1e-6
+    ref_cols = frame.reshape(-1, 3)[ref_mask.flatten()] / 255.0
+    assert np.max(np.abs(cols.cpu().double().numpy() - ref_cols)) <= 1e-7
+
+
+def test_colorize_and_u16(model):
+    depth = model.infer(torch.from_numpy(O.synthetic_frame_u8(2, 270, 480)))["depth"]
+    lut = video.colormap_lut("turbo")
+    rgb = video.colorize_depth(model, depth, "turbo").cpu().numpy()
+    norm = O.normalize_depth(depth.cpu().numpy())
+    assert np.array_equal(rgb, lut[np.minimum((norm * 256).astype(np.int64), 255)])
+    u16 = video.depth_to_uint16(model, depth).cpu().numpy().view(np.uint16)
+    assert np.array_equal(u16, O.depth_to_u16(depth.cpu().numpy()))
+
+
+def test_batch_generate_depth_maps(model, tmp_path):
+    import cv2
+
+    src, dst = tmp_path / "frames", tmp_path / "depth"
+    src.mkdir()
+    for i in range(3):
+        cv2.imwrite(str(src / f"frame_{i:04d}.png"), cv2.cvtColor(O.synthetic_frame_u8(i, 135, 240), cv2.COLOR_RGB2BGR))
+    (src / "broken.png").write_bytes(b"not a png")          # per-frame errors are swallowed, loop continues
+    n = video.batch_generate_depth_maps(str(src), str(dst), model=model)
+    assert n == 3
+    outs = sorted(os.listdir(dst))
+    assert outs == [f"frame_{i:04d}_depth.png" for i in range(3)]
+    img = cv2.imread(str(dst / outs[0]))
+    assert img.shape == (135, 240, 3)
+    # raw 16-bit export + sharding: rank 1 of 2 handles only the odd frames (sorted glob order)
+    dst2 = tmp_path / "depth_raw"
+    n1 = video.batch_generate_depth_maps(str(src), str(dst2), pattern="frame_*.png", colored=False, model=model,
+                                         rank=1, world=2)
+    assert n1 == 1 and os.listdir(dst2) == ["frame_0001_depth.png"]
+    raw = cv2.imread(str(dst2 / "frame_0001_depth.png"), cv2.IMREAD_UNCHANGED)
+    assert raw.dtype == np.uint16 and raw.shape == (135, 240) and raw.max() == 65535 and raw.min() == 0
