@@ -121,6 +121,11 @@ int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float*
 int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, int n,
                       void* stream);
 
+/* Micro-benchmark of one bf16 core on scratch buffers; mean ms per launch over `iters` launches.
+ * kind 0 GEMM+bias, 1 GEMM+bias+GELU, 2 GEMM+bias*gamma+fp32 residual (in place), 3 conv3x3 on an
+ * MxM map (Cin=K, Cout=N), 4 attention over M sequences, 5 LayerNorm over M rows. */
+int dp_kernel_bench(dp_engine* e, int kind, int M, int N, int K, int iters, float* ms_out);
+
 /* Per-launch CUDA-event profiling of the hot kernels (used by bench.py for the roofline line).
  * Classes: 0 tcgen05 GEMM, 1 tcgen05 conv3x3, 2 attention, 3 LayerNorm, 4 fp32 CUDA-core GEMM.
  * `work` is algorithmic FLOPs (classes 0,1,2,4) or bytes (class 3).  Arrays hold 5 entries.

@@ -96,6 +96,9 @@ int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float*
 int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, int n, void* stream) {
   return guard([&] { E(e)->attention_test(backend, qkv, out, n, S(stream)); });
 }
+int dp_kernel_bench(dp_engine* e, int kind, int M, int N, int K, int iters, float* ms_out) {
+  return guard([&] { *ms_out = E(e)->kernel_bench(kind, M, N, K, iters); });
+}
 int dp_profile_enable(dp_engine* e, int on) {
   (void)e;
   return guard([&] { dp::prof_enable(on != 0); });

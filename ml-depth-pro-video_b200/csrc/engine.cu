@@ -9,6 +9,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 
 #include "attention.cuh"
 #include "gemm.cuh"
@@ -845,4 +846,66 @@ void Engine::attention_test(int backend, const float* qkv, float* out, int n, cu
   }
 }
 
+}  // namespace dp
+
+namespace dp {
+// Micro-benchmark of the bf16 cores on scratch buffers (values are irrelevant, zeros):
+//  kind 0: GEMM + bias -> bf16          (qkv)      kind 1: GEMM + bias + GELU -> bf16 (fc1)
+//  kind 2: GEMM + bias, *gamma, + fp32 residual in place (proj / fc2)
+//  kind 3: conv3x3 on an MxM map, Cin = K, Cout = N, + bias + ReLU -> bf16
+//  kind 4: attention over M sequences       kind 5: LayerNorm over M rows
+// Returns the mean milliseconds per launch over `iters` launches (CUDA events).
+float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
+  DP_CUDA(cudaSetDevice(device_));
+  cudaStream_t s = nullptr;
+  auto dalloc = [&](size_t bytes) {
+    void* p = nullptr;
+    DP_CUDA(cudaMalloc(&p, bytes));
+    DP_CUDA(cudaMemset(p, 0, bytes));
+    return p;
+  };
+  std::vector<void*> bufs;
+  auto B = [&](size_t bytes) { void* p = dalloc(bytes); bufs.push_back(p); return p; };
+  GemmOp op;
+  std::function<void()> run;
+  if (kind <= 2) {
+    op.M = M, op.N = N, op.K = K, op.lda = K;
+    op.A = B((size_t)M * K * 2), op.Wt = B((size_t)N * K * 2), op.bias = (float*)B((size_t)N * 4);
+    if (kind == 2) {
+      float* r = (float*)B((size_t)M * N * 4);
+      op.gamma = (float*)B((size_t)N * 4), op.res = r, op.res_f32 = 1, op.ldres = N, op.out = r, op.out_f32 = 1, op.ldo = N;
+    } else {
+      op.out = B((size_t)M * N * 2), op.ldo = N, op.act = kind == 1 ? ACT_GELU : ACT_NONE;
+    }
+    run = [&] { gemm_tc(op, s); };
+  } else if (kind == 3) {
+    op.M = M * M, op.N = N, op.K = 9 * K, op.a_mode = A_CONV3X3, op.B = 1, op.H = M, op.W = M, op.C = K;
+    op.A = B((size_t)M * M * K * 2), op.Wt = B((size_t)N * 9 * K * 2), op.bias = (float*)B((size_t)N * 4);
+    op.act = ACT_RELU, op.out = B((size_t)M * M * N * 2), op.ldo = N;
+    run = [&] { gemm_tc(op, s); };
+  } else if (kind == 4) {
+    bf16* q = (bf16*)B((size_t)M * SEQ * 3 * EMB * 2);
+    bf16* o = (bf16*)B((size_t)M * SEQ * EMB * 2);
+    run = [&, q, o] { attention_bf16_tc(q, o, M, s); };
+  } else {
+    float* x = (float*)B((size_t)M * EMB * 4);
+    bf16* y = (bf16*)B((size_t)M * EMB * 2);
+    float* w = (float*)B(EMB * 4);
+    run = [&, x, y, w] { layernorm_rows<bf16>(x, y, w, w, M, RowMap(), 1, s); };
+  }
+  for (int i = 0; i < 3; ++i) run();
+  cudaEvent_t a, b;
+  DP_CUDA(cudaEventCreate(&a));
+  DP_CUDA(cudaEventCreate(&b));
+  DP_CUDA(cudaEventRecord(a, s));
+  for (int i = 0; i < iters; ++i) run();
+  DP_CUDA(cudaEventRecord(b, s));
+  DP_CUDA(cudaEventSynchronize(b));
+  float ms = 0.f;
+  DP_CUDA(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a), cudaEventDestroy(b);
+  for (void* p : bufs) cudaFree(p);
+  tmap_cache_clear();
+  return ms / iters;
+}
 }  // namespace dp

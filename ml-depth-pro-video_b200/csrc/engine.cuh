@@ -52,6 +52,7 @@ class Engine {
   void conv3x3_test(int backend, const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
                     int Cout, cudaStream_t s);
   void attention_test(int backend, const float* qkv, float* out, int n, cudaStream_t s);
+  float kernel_bench(int kind, int M, int N, int K, int iters);
 
   int device() const { return device_; }
   int prec() const { return prec_; }

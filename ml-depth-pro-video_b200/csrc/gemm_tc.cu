@@ -30,7 +30,13 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+// smem: 4 x 48 KB ring for the 128x256 tile + 33 KB epilogue staging = 226 KB of the 227 KB limit
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = 4;
+};
+constexpr int STG_PITCH = 33;                                // floats per staged row (conflict-free both ways)
+constexpr int STG_WARP_BYTES = 32 * STG_PITCH * 4;           // one 32x32 fp32 chunk per epilogue warp
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;
@@ -215,10 +221,87 @@ __device__ __forceinline__ void load_res(const GemmOp& op, long long m, int n0, 
   else load32<bf16>(reinterpret_cast<const bf16*>(op.res) + roff, r);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Column-per-lane epilogue for row-major outputs.  A warp's 32x32 fp32 accumulator chunk (thread =
+// row, straight from tcgen05.ld) is transposed through a per-warp shared-memory buffer; afterwards
+// lane l owns column n0+l, so every global access of the warp is ONE contiguous 64/128-byte row
+// segment (1 LSU wavefront) instead of 32 scattered 16-byte pieces, and bias / gamma are one
+// register each.  Kept deliberately small (rolled loops, no per-row mode switches): the first,
+// fully general version of this path was instruction-fetch bound.
+struct ColSlab {
+  int nv;          // valid rows of the 32-row slab
+  int wp;          // row -> pixel step: 16 for matrix rows (offset = rr), W for 8x16 conv tiles
+  long long row0;  // first output row / pixel of the slab
+};
+__device__ __forceinline__ long long slab_off(const ColSlab& cs, int rr) {
+  return cs.row0 + (rr >> 4) * cs.wp + (rr & 15);
+}
+
+// proj / fc2: out = res + gamma * (acc + bias), fp32 in place.  The 32 residual values of this
+// lane's column were prefetched into registers before the accumulator was ready.
+__device__ __forceinline__ void prefetch_res32(const float* __restrict__ res, long long ld, const ColSlab& cs, int n,
+                                               float (&rv)[32]) {
+  const float* p = res + cs.row0 * ld + n;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) rv[rr] = rr < cs.nv ? p[rr * ld] : 0.f;
+}
+__device__ __forceinline__ void epi_cols_resid32(float* __restrict__ out, long long ld, const ColSlab& cs, int n,
+                                                 uint32_t stg, int lane, float bias_v, float gamma_v,
+                                                 const float (&rv)[32]) {
+  float* p = out + cs.row0 * ld + n;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr)
+    if (rr < cs.nv) p[rr * ld] = fmaf(ptx::lds_f32(stg + (rr * STG_PITCH + lane) * 4) + bias_v, gamma_v, rv[rr]);
+}
+
+// bf16 row-major outputs: bias, activation, optional bf16 residual(s), optional ReLU'd copy.
+// Sub-word (2-byte per lane) global stores crawl, so a lane owns TWO adjacent columns and half a
+// warp covers a row: lanes 0-15 take row 2i, lanes 16-31 row 2i+1, every access is 4 bytes per lane.
+template <int ACT>
+__device__ __forceinline__ void epi_cols_store_bf16(const GemmOp& op, const GemmGroup& gp, const ColSlab& cs, int n0,
+                                                    uint32_t stg, int lane) {
+  const int cp = (lane & 15) * 2, rsel = lane >> 4;
+  const int n = n0 + cp;
+  float b0 = 0.f, b1 = 0.f, g0 = 1.f, g1 = 1.f;
+  if (gp.bias) {
+    const int bi = op.bias_mod ? n % op.bias_mod : n;
+    b0 = gp.bias[bi], b1 = gp.bias[bi + 1];
+  }
+  if (gp.gamma) g0 = gp.gamma[n], g1 = gp.gamma[n + 1];
+  const __nv_bfloat162* res = reinterpret_cast<const __nv_bfloat162*>(op.res);
+  const __nv_bfloat162* res2 = reinterpret_cast<const __nv_bfloat162*>(op.res2);
+  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(op.out);
+  __nv_bfloat162* orl = reinterpret_cast<__nv_bfloat162*>(op.out_relu);
+  const long long ldo = op.ldo, ldr = op.ldres;
+  const long long co = op.col_off + n;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int rr = 2 * i + rsel;
+    if (rr >= cs.nv) continue;
+    const long long row = slab_off(cs, rr);
+    float v0 = ptx::lds_f32(stg + (rr * STG_PITCH + cp) * 4) + b0;
+    float v1 = ptx::lds_f32(stg + (rr * STG_PITCH + cp + 1) * 4) + b1;
+    if (ACT == ACT_RELU) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
+    if (ACT == ACT_GELU) v0 = gelu_erf(v0), v1 = gelu_erf(v1);
+    v0 *= g0, v1 *= g1;
+    if (res) {
+      const float2 r = __bfloat1622float2(res[(row * ldr + n) >> 1]);
+      v0 += r.x, v1 += r.y;
+    }
+    if (res2) {
+      const float2 r = __bfloat1622float2(res2[(row * ldr + n) >> 1]);
+      v0 += r.x, v1 += r.y;
+    }
+    if (ob) ob[(row * ldo + co) >> 1] = __floats2bfloat162_rn(v0, v1);
+    if (orl) orl[(row * ldo + co) >> 1] = __floats2bfloat162_rn(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
+  }
+}
+
 template <int BN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ WeightMaps tmW,
                const GemmOp op, const TileGeom g) {
+  constexpr int STAGES = Cfg<BN>::STAGES;
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -235,6 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const uint32_t stg_all = ptx::smem_u32(smem + STAGES * STAGE_BYTES + 256);  // epilogue staging, 8 warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -271,7 +355,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow: coordinates and descriptors stay in
+    // uniform registers); one elected lane arms the barrier and issues the copies.
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int t = cid; t < total_units; t += ncl) {
@@ -291,31 +377,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           a_row = static_cast<int>(op.grp[gi].a_row_off) + lmt * BM;
           tmB = &tmW.b[gi];
         }
+        int tap = 0, c0 = 0;  // conv: running (filter tap, channel offset) of the k-block
         for (int kb = 0; kb < g.k_blocks; ++kb) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
-          ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
-          if (op.a_mode == A_CONV3X3) {
-            const int k = kb * BK;
-            const int tap = k / op.C, c0 = k - tap * op.C;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            ptx::tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b);
-          } else {
-            ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, a_row);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
+            if (op.a_mode == A_CONV3X3) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              ptx::tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b);
+            } else {
+              ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, a_row);
+            }
+            if (CL > 1) {
+              // this CTA fetches 1/CL of the weight tile and multicasts it to the whole cluster
+              ptx::tma_load_2d_mc(sB + s * B_BYTES + crank * (B_BYTES / CL), tmB, &full[s], kb * BK,
+                                  nt * BN + crank * (BN / CL), MC_MASK);
+            } else {
+              ptx::tma_load_2d(sB + s * B_BYTES, tmB, &full[s], kb * BK, nt * BN);
+            }
           }
-          if (CL > 1) {
-            // this CTA fetches 1/CL of the weight tile and multicasts it to the whole cluster
-            ptx::tma_load_2d_mc(sB + s * B_BYTES + crank * (B_BYTES / CL), tmB, &full[s], kb * BK,
-                                nt * BN + crank * (BN / CL), MC_MASK);
-          } else {
-            ptx::tma_load_2d(sB + s * B_BYTES, tmB, &full[s], kb * BK, nt * BN);
-          }
+          __syncwarp();
+          c0 += BK;
+          if (c0 == op.C) c0 = 0, ++tap;
           if (++s == STAGES) s = 0, ph ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // Warp-converged loop, one elected lane issues.  With the loop under `if (lane == 0)` every
+    // tcgen05.mma was wrapped in an elect / vote / R2UR sequence and the descriptor arithmetic ran on
+    // the (slow, serial) uniform datapath: ~90 dependent instructions per k-block, as long as the
+    // 512 tensor-core cycles they were supposed to hide behind.  Descriptors are now base + 2*k.
+    {
+      // 64-bit smem descriptor: lo = (addr >> 4) | LBO(1) << 16, hi = SBO(64) | version(1) << 14 | SW128(2) << 29
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((ptx::smem_u32(sA) & 0x3FFFF) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((ptx::smem_u32(sB) & 0x3FFFF) >> 4) | (1u << 16);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -328,18 +426,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < g.k_blocks; ++kb) {
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(sA + s * A_BYTES);
-          const uint32_t b0 = ptx::smem_u32(sB + s * B_BYTES);
+          const uint32_t a_lo = a_lo0 + s * (A_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + s * (B_BYTES >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a0 + k * 32), ptx::umma_desc_sw128(b0 + k * 32),
-                           IDESC, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + 2 * k);  // +32 B per K=16 step
+              const uint64_t db = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + 2 * k);
+              ptx::umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0);
+            }
+            if (CL > 1) ptx::umma_commit_mc(&empty[s], MC_MASK);  // the peers' producers write into this stage too
+            else ptx::umma_commit(&empty[s]);
+            if (kb == g.k_blocks - 1) ptx::umma_commit(&tfull[acc]);
           }
-          if (CL > 1) ptx::umma_commit_mc(&empty[s], MC_MASK);  // the peers' producers write into this stage too
-          else ptx::umma_commit(&empty[s]);
+          __syncwarp();
           if (++s == STAGES) s = 0, ph ^= 1;
         }
-        ptx::umma_commit(&tfull[acc]);
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -373,10 +475,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const GemmGroup& gp = op.grp[gi];
       const bool active = (BN >= 64 || grp == 0);
-      const bool has_res = op.res != nullptr && valid && active;
       const int col0 = nt * BN + grp * COLS_PER_GRP;
+      // ---- which epilogue form (warp-uniform, fixed per launch)
+      const bool resid32 = op.out_mode == O_ROWMAJOR && op.res != nullptr && op.res_f32 && op.out_f32 && op.res2 == nullptr &&
+                           op.out_relu == nullptr && op.act == ACT_NONE && op.a_mode == A_ROWMAJOR &&
+                           op.res == op.out && op.ldres == op.ldo && op.col_off == 0;
+      // (the column-domain bf16 store path below measured ~2x slower than row-per-thread 16-byte stores,
+      //  so only the fp32 residual form takes the transposed route for now)
+      const bool colwise = resid32;
+      ColSlab cs;
+      if (op.a_mode == A_CONV3X3) {
+        const int mt = mu * CL + crank;
+        const int per_img = g.tiles_x * g.tiles_y;
+        const int b = mt / per_img;
+        const int r = mt - b * per_img;
+        cs.row0 = (static_cast<long long>(b) * op.H + (r / g.tiles_x) * TILE_H + 2 * q) * op.W + (r % g.tiles_x) * TILE_W;
+        cs.wp = op.W;
+        cs.nv = mt < g.tiles_in_group[0] ? 32 : 0;
+      } else {
+        const int ml0 = ((mu - g.unit_start[gi]) * CL + crank) * BM + q * 32;
+        const int left = op.grp[gi].M - ml0;
+        cs.nv = left >= 32 ? 32 : (left > 0 ? left : 0);
+        cs.row0 = op.grp[gi].o_row_off + ml0;
+        cs.wp = 16;
+      }
+      const uint32_t stg = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;
       float resv[32];
+      const bool has_res = !colwise && op.res != nullptr && valid && active;   // row-per-thread forms
       if (has_res) load_res(op, m, col0, resv);  // in flight while the MMA of this tile finishes
+      if (resid32 && active) prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + lane, resv);
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       if (active) {
@@ -384,23 +511,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < COLS_PER_GRP; c += 32) {
           uint32_t r[32];
           ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + grp * COLS_PER_GRP + c, r);
+          const bool more = c + 32 < COLS_PER_GRP;
           float resn[32];
-          if (has_res && c + 32 < COLS_PER_GRP) load_res(op, m, col0 + c + 32, resn);
+          if (has_res && more) load_res(op, m, col0 + c + 32, resn);
+          if (resid32 && more) prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + c + 32 + lane, resn);
           ptx::tmem_ld_wait();
-          if (valid) {
+          if (!more) {
+            // the accumulator has left tensor memory: hand the buffer back to the MMA warp now, the
+            // global stores below overlap the next tile's mainloop
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty[acc]);
+          }
+          if (colwise) {
+            const int n = col0 + c + lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ptx::sts_f32(stg + (lane * STG_PITCH + j) * 4, __uint_as_float(r[j]));
+            __syncwarp();
+            if (resid32) {
+              const float bias_v = gp.bias ? gp.bias[n] : 0.f;
+              const float gamma_v = gp.gamma ? gp.gamma[n] : 1.f;
+              epi_cols_resid32(reinterpret_cast<float*>(op.out), op.ldo, cs, n, stg, lane, bias_v, gamma_v, resv);
+            } else if (op.act == ACT_GELU) {
+              epi_cols_store_bf16<ACT_GELU>(op, gp, cs, col0 + c, stg, lane);
+            } else if (op.act == ACT_RELU) {
+              epi_cols_store_bf16<ACT_RELU>(op, gp, cs, col0 + c, stg, lane);
+            } else {
+              epi_cols_store_bf16<ACT_NONE>(op, gp, cs, col0 + c, stg, lane);
+            }
+            __syncwarp();
+          } else if (valid) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             epilogue_chunk(op, gp, m, col0 + c, v, resv);
           }
-          if (has_res && c + 32 < COLS_PER_GRP) {
+          if ((has_res || resid32) && more) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) resv[j] = resn[j];
           }
         }
+      } else {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tempty[acc]);
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty[acc]);
     }
   }
 
@@ -488,7 +641,8 @@ int num_sms() {
 template <int BN, int CL>
 void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const WeightMaps& tmW,
             cudaStream_t stream) {
-  constexpr size_t SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr int STAGES = Cfg<BN>::STAGES;
+  constexpr size_t SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + 8 * STG_WARP_BYTES;
   static bool configured = false;
   if (!configured) {
     DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
