@@ -4,20 +4,25 @@
 // F.scaled_dot_product_attention, wired at src/depth_pro/network/vit_factory.py:97-110).
 // qkv is (nseq*577, 3072) bf16 with columns [q | k | v], each 16 heads x 64; out is (nseq*577, 1024).
 //
-// One persistent CTA per SM loops over work items (sequence, head, 128-row query tile); keys are
-// processed in 5 blocks of 128 (640 >= 577, the tail is masked).  Warp roles:
-//   warp 0     TMA producer : Q tile (once per item) and K/V blocks (3-deep ring), 128B swizzle.
-//   warp 1     MMA issuer   : S = Q K^T   (tcgen05.mma M128 N128 K16 x4, A/B K-major from smem),
-//                             O_j = P V   (M128 N64 K16 x8, A = P K-major from smem, B = V MN-major
-//                             straight from the TMA tile) into double-buffered TMEM.
-//   warp 2     TMEM allocator
-//   warps 4-7  softmax      : one thread per query row: tcgen05.ld the 128 scores, online softmax in
-//                             fp32 (exp2, log2e folded into the scale), write P as bf16 into the
-//                             swizzled smem tile the next MMA reads, accumulate O_j from TMEM into
-//                             registers with the running-max correction, final 1/l and bf16 store.
-// S and P are double buffered so Q K^T of block j+1 runs on the tensor pipe while the softmax warps
-// work on block j; the per-block P V products are NOT accumulated in TMEM (no read-modify-write of O
-// in tensor memory): each lands in its own TMEM buffer and is folded into registers one block later.
+// One persistent CTA per SM loops over work items (sequence, head, PAIR of 128-row query tiles); the
+// two query tiles of an item are two independent streams A / B that share every K / V block.  Keys
+// are processed in 5 blocks of 128 (640 >= 577, the tail is masked).  Warp roles:
+//   warp 0      TMA producer : Q tiles (once per item) and K/V blocks (3-deep ring), 128B swizzle.
+//   warp 1      MMA issuer   : per stream S = Q K^T (tcgen05.mma M128 N128 K16 x4, A/B K-major) and
+//                              O_j = P V (M128 N64 K16 x8, A = P K-major from smem, B = V MN-major
+//                              straight from the TMA tile); S_A, S_B, O_A[2], O_B[2] fill the 512 TMEM
+//                              columns.
+//   warp 2      TMEM allocator
+//   warps 4-7   softmax of stream A, warps 8-11 softmax of stream B: one thread per query row:
+//                              tcgen05.ld the 128 scores, online softmax in fp32 (exp2, log2e folded into
+//                              the scale), P as bf16 into the swizzled smem tile the next MMA reads, O_j
+//                              folded from TMEM into registers with the running-max correction, final
+//                              1/l and bf16 store.  The two groups are NOT synchronised with each other,
+//                              so on every SM sub-partition one warp's TMEM loads overlap the other's
+//                              MUFU exp2 work (a single group serialises LDTM -> MUFU -> STS per block
+//                              and leaves the tensor pipe idle 80% of the time).
+// Register budget: 384 threads x 168 would not hold 128 scores + 64 outputs per softmax thread, so
+// the control warps drop to 40 registers and the softmax warps grow to 232 (setmaxnreg).
 #include "attention.cuh"
 #include "ptx.cuh"
 
@@ -25,37 +30,30 @@ namespace dp {
 namespace {
 
 constexpr int SEQ = 577, HD = 64, NH = 16, LDQ = 3 * NH * HD, LDO = NH * HD;
-constexpr int QT = 128;                         // query rows per item
+constexpr int QT = 128;                         // query rows per stream
 constexpr int KB = 128;                         // keys per block
 constexpr int NB = (SEQ + KB - 1) / KB;         // 5 key blocks
 constexpr int NQT = (SEQ + QT - 1) / QT;        // 5 query tiles
+constexpr int NPAIR = (NQT + 1) / 2;            // 3 items per (sequence, head): tiles (0,1) (2,3) (4,-)
 constexpr int KV_STAGES = 3;
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;
 constexpr uint32_t TILE_BYTES = 128 * 128;      // 128 rows x 64 bf16 = 16 KB
-constexpr uint32_t SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES + 4) + 1024 + 256;
+constexpr uint32_t SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES + 4) + 1024 + 256;
 
 // idesc: D=f32, A=B=bf16, A K-major; B K-major (QK^T) or MN-major (PV: bit 16)
 constexpr uint32_t IDESC_QK = ptx::umma_idesc_bf16(128, 128);
 constexpr uint32_t IDESC_PV = ptx::umma_idesc_bf16(128, 64) | (1u << 16);
+// smem descriptor high word: SBO = 1024 B, version 1, SWIZZLE_128B (same for K-major and MN-major tiles)
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 
-// MN-major operand stored as rows of 64 bf16 (128 B, the MN dimension is contiguous) with the 128B
-// swizzle: 8-row (K) groups are 1024 B apart (SBO); one 64-element MN atom, so LBO is unused.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
+__device__ __forceinline__ uint64_t desc(uint32_t lo) { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
 
 __device__ __forceinline__ float ex2(float x) {  // MUFU ex2.approx: 2 ulp, -inf -> 0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -65,23 +63,23 @@ __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int nseq) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;                    // KV_STAGES tiles
+  uint8_t* sQ = smem;                               // 2 tiles (stream A, B)
+  uint8_t* sK = sQ + 2 * TILE_BYTES;                // KV_STAGES tiles
   uint8_t* sV = sK + KV_STAGES * TILE_BYTES;        // KV_STAGES tiles
-  uint8_t* sP = sV + KV_STAGES * TILE_BYTES;        // 2 buffers x 2 k-chunks
+  uint8_t* sP = sV + KV_STAGES * TILE_BYTES;        // 2 streams x 2 k-chunk tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * TILE_BYTES);
   uint64_t* q_full = bars;                          // 1
   uint64_t* q_empty = bars + 1;                     // 1
   uint64_t* kv_full = bars + 2;                     // KV_STAGES
   uint64_t* kv_empty = kv_full + KV_STAGES;         // KV_STAGES
-  uint64_t* s_full = kv_empty + KV_STAGES;          // 2
-  uint64_t* s_empty = s_full + 2;                   // 2
-  uint64_t* p_full = s_empty + 2;                   // 2
-  uint64_t* pv_done = p_full + 2;                   // 2
+  uint64_t* s_full = kv_empty + KV_STAGES;          // per stream
+  uint64_t* s_empty = s_full + 2;                   // per stream, 128 arrivals
+  uint64_t* p_full = s_empty + 2;                   // per stream, 128 arrivals
+  uint64_t* pv_done = p_full + 2;                   // per stream
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = nseq * NH * NQT;
+  const int n_items = nseq * NH * NPAIR;
 
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmQKV);
   if (warp == 1 && lane == 0) {
@@ -105,90 +103,118 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 256;
+  // TMEM columns: S_A [0,128), S_B [128,256), O_A[2] [256,384), O_B[2] [384,512)
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int qt = item % NQT, h = (item / NQT) % NH, seq = item / (NQT * NH);
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
+        const int pr = item % NPAIR, h = (item / NPAIR) % NH, seq = item / (NPAIR * NH);
+        const bool hasB = 2 * pr + 1 < NQT;
         const int row0 = seq * SEQ;
         ptx::mbar_wait(q_empty, (it & 1) ^ 1);
-        ptx::mbar_expect_tx(q_full, TILE_BYTES);
-        ptx::tma_load_2d(sQ, &tmQKV, q_full, h * HD, row0 + qt * QT);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(q_full, hasB ? 2 * TILE_BYTES : TILE_BYTES);
+          ptx::tma_load_2d(sQ, &tmQKV, q_full, h * HD, row0 + 2 * pr * QT);
+          if (hasB) ptx::tma_load_2d(sQ + TILE_BYTES, &tmQKV, q_full, h * HD, row0 + (2 * pr + 1) * QT);
+        }
+        __syncwarp();
         for (int j = 0; j < NB; ++j) {
           const int gb = it * NB + j, st = gb % KV_STAGES;
           ptx::mbar_wait(&kv_empty[st], ((gb / KV_STAGES) & 1) ^ 1);
-          ptx::mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-          ptx::tma_load_2d(sK + st * TILE_BYTES, &tmQKV, &kv_full[st], NH * HD + h * HD, row0 + j * KB);
-          ptx::tma_load_2d(sV + st * TILE_BYTES, &tmQKV, &kv_full[st], 2 * NH * HD + h * HD, row0 + j * KB);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+            ptx::tma_load_2d(sK + st * TILE_BYTES, &tmQKV, &kv_full[st], NH * HD + h * HD, row0 + j * KB);
+            ptx::tma_load_2d(sV + st * TILE_BYTES, &tmQKV, &kv_full[st], 2 * NH * HD + h * HD, row0 + j * KB);
+          }
+          __syncwarp();
         }
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int it = 0;
-      auto issue_pv = [&](int gb) {
-        const int b = gb & 1, st = gb % KV_STAGES;
-        ptx::mbar_wait(&p_full[b], (gb >> 1) & 1);
-        ptx::tc_fence_after();
-        const uint32_t p0 = ptx::smem_u32(sP + b * 2 * TILE_BYTES);
-        const uint32_t v0 = ptx::smem_u32(sV + st * TILE_BYTES);
-#pragma unroll
-        for (int ks = 0; ks < KB / 16; ++ks) {
-          const uint64_t da = ptx::umma_desc_sw128(p0 + (ks >> 2) * TILE_BYTES + (ks & 3) * 32);
-          const uint64_t db = umma_desc_mn_sw128(v0 + ks * 2048);
-          ptx::umma_bf16(tO + b * 64, da, db, IDESC_PV, ks != 0);
-        }
-        ptx::umma_commit(&pv_done[b]);
-        ptx::umma_commit(&kv_empty[st]);
-      };
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t q_lo = desc_lo(ptx::smem_u32(sQ)), k_lo = desc_lo(ptx::smem_u32(sK));
+      const uint32_t v_lo = desc_lo(ptx::smem_u32(sV)), p_lo = desc_lo(ptx::smem_u32(sP));
+      int nB = 0;  // items so far in which stream B was active (its barrier phases advance only then)
+      for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
+        const bool hasB = 2 * (item % NPAIR) + 1 < NQT;
         ptx::mbar_wait(q_full, it & 1);
-        for (int j = 0; j < NB; ++j) {
-          const int gb = it * NB + j, b = gb & 1, st = gb % KV_STAGES;
-          ptx::mbar_wait(&kv_full[st], (gb / KV_STAGES) & 1);
-          ptx::mbar_wait(&s_empty[b], ((gb >> 1) & 1) ^ 1);
-          ptx::tc_fence_after();
-          const uint32_t q0 = ptx::smem_u32(sQ), k0 = ptx::smem_u32(sK + st * TILE_BYTES);
+        // P V of key block jj for both streams, then release that K/V stage
+        auto issue_pv = [&](int jj) {
+          const int st = (it * NB + jj) % KV_STAGES;
+          for (int sidx = 0; sidx < (hasB ? 2 : 1); ++sidx) {
+            const int gbs = (sidx == 0 ? it : nB) * NB + jj;
+            ptx::mbar_wait(&p_full[sidx], gbs & 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint32_t d = tmem_base + 256 + sidx * 128 + (jj & 1) * 64;
 #pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks)
-            ptx::umma_bf16(tS + b * 128, ptx::umma_desc_sw128(q0 + ks * 32), ptx::umma_desc_sw128(k0 + ks * 32),
-                           IDESC_QK, ks != 0);
-          ptx::umma_commit(&s_full[b]);
-          if (j == NB - 1) ptx::umma_commit(q_empty);  // Q no longer needed once the last QK^T retires
-          if (j > 0) issue_pv(gb - 1);
+              for (int ks = 0; ks < KB / 16; ++ks) {
+                // A = P: k-chunk tile (ks >> 2), +32 B per K=16 step; B = V (MN-major): +16 keys = 2048 B
+                const uint64_t da = desc(p_lo + sidx * (2 * TILE_BYTES >> 4) + (ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2);
+                const uint64_t db = desc(v_lo + st * (TILE_BYTES >> 4) + ks * (2048 >> 4));
+                ptx::umma_bf16(d, da, db, IDESC_PV, ks != 0);
+              }
+              ptx::umma_commit(&pv_done[sidx]);
+            }
+            __syncwarp();
+          }
+          if (ptx::elect_one()) ptx::umma_commit(&kv_empty[st]);
+          __syncwarp();
+        };
+        for (int j = 0; j < NB; ++j) {
+          const int st = (it * NB + j) % KV_STAGES;
+          ptx::mbar_wait(&kv_full[st], ((it * NB + j) / KV_STAGES) & 1);
+          for (int sidx = 0; sidx < (hasB ? 2 : 1); ++sidx) {
+            const int gbs = (sidx == 0 ? it : nB) * NB + j;
+            ptx::mbar_wait(&s_empty[sidx], (gbs & 1) ^ 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < HD / 16; ++ks)
+                ptx::umma_bf16(tmem_base + sidx * 128, desc(q_lo + sidx * (TILE_BYTES >> 4) + ks * 2),
+                               desc(k_lo + st * (TILE_BYTES >> 4) + ks * 2), IDESC_QK, ks != 0);
+              ptx::umma_commit(&s_full[sidx]);
+            }
+            __syncwarp();
+          }
+          if (j == NB - 1) {
+            if (ptx::elect_one()) ptx::umma_commit(q_empty);  // Q tiles are free once the last QK^T retires
+            __syncwarp();
+          }
+          if (j > 0) issue_pv(j - 1);
         }
-        issue_pv(it * NB + NB - 1);
+        issue_pv(NB - 1);
+        if (hasB) ++nB;
       }
     }
-  } else if (warp >= 4) {
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // ------------------------------------------------------------------ softmax / accumulate
-    const int q = warp & 3;
+    const int q = warp & 3;             // TMEM lane quadrant
+    const int sidx = (warp - 4) >> 2;   // stream: 0 = A, 1 = B
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tS = tmem_base + sidx * 128, tO = tmem_base + 256 + sidx * 128;
+    uint8_t* prow = sP + sidx * 2 * TILE_BYTES + row * 128;
     const float c = 0.125f * 1.4426950408889634f;  // softmax scale * log2(e)
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int qt = item % NQT, h = (item / NQT) % NH, seq = item / (NQT * NH);
+    int ns = 0;                          // items this stream has processed (barrier phase counter)
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int pr = item % NPAIR, h = (item / NPAIR) % NH, seq = item / (NPAIR * NH);
+      const int qt = 2 * pr + sidx;
+      if (qt >= NQT) continue;           // stream B idles on the odd last tile
       const int q_row = qt * QT + row;
       float o[HD];
 #pragma unroll
       for (int d = 0; d < HD; ++d) o[d] = 0.f;
       float m_run = -INFINITY, m_acc = -INFINITY, l = 0.f;
-      float m_hist[2] = {-INFINITY, -INFINITY};
 
-      auto acc_o = [&](int gb) {
-        const int b = gb & 1;
-        ptx::mbar_wait(&pv_done[b], (gb >> 1) & 1);
-        ptx::tc_fence_after();
+      // fold O_jj (computed with P relative to max `mj`) into the register accumulator
+      auto acc_o = [&](int jj, float mj) {
         uint32_t r0[32], r1[32];
-        ptx::tmem_ld32(tO + b * 64 + lane_addr, r0);
-        ptx::tmem_ld32(tO + b * 64 + 32 + lane_addr, r1);
+        ptx::tmem_ld32(tO + (jj & 1) * 64 + lane_addr, r0);
+        ptx::tmem_ld32(tO + (jj & 1) * 64 + 32 + lane_addr, r1);
         ptx::tmem_ld_wait();
-        const float mj = m_hist[b];
         const float alpha = ex2((m_acc - mj) * c);
         m_acc = mj;
 #pragma unroll
@@ -199,18 +225,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       };
 
       for (int j = 0; j < NB; ++j) {
-        const int gb = it * NB + j, b = gb & 1;
-        if (j >= 2) acc_o(gb - 2);
-        // ---- scores of this block
-        ptx::mbar_wait(&s_full[b], (gb >> 1) & 1);
+        const int gbs = ns * NB + j;
+        ptx::mbar_wait(&s_full[sidx], gbs & 1);
         ptx::tc_fence_after();
         uint32_t sr[4][32];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld32(tS + b * 128 + ch * 32 + lane_addr, sr[ch]);
+        for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld32(tS + ch * 32 + lane_addr, sr[ch]);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&s_empty[b]);  // S[b] is in registers: the tensor pipe may overwrite it
+        ptx::mbar_arrive(&s_empty[sidx]);  // S is in registers: the next Q K^T may overwrite it
         const int key0 = j * KB;
+        const float m_prev = m_run;
         float mx = m_run;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch)
@@ -223,13 +248,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
           }
         const float alpha = ex2((m_run - mx) * c);
         m_run = mx;
-        m_hist[b] = mx;
         const float mc = mx * c;
+        // P is single-buffered per stream: the previous block's P V must have consumed it
+        if (j > 0) ptx::mbar_wait(&pv_done[sidx], (gbs - 1) & 1);
         float rs = 0.f;
-        uint8_t* prow = sP + b * 2 * TILE_BYTES + row * 128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          // 32 keys -> 4 x 16-byte chunks of the k-chunk tile (ch >> 1), chunk index (ch & 1) * 4 + i
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t pk[4];
@@ -248,10 +272,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         l = fmaf(l, alpha, rs);
         ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&p_full[b]);
+        ptx::mbar_arrive(&p_full[sidx]);
+        // O_{j-1} (other TMEM buffer than the P V just enabled) -> registers
+        if (j > 0) {
+          ptx::tc_fence_after();
+          acc_o(j - 1, m_prev);
+        }
       }
-      acc_o(it * NB + NB - 2);
-      acc_o(it * NB + NB - 1);
+      ptx::mbar_wait(&pv_done[sidx], (ns * NB + NB - 1) & 1);
+      ptx::tc_fence_after();
+      acc_o(NB - 1, m_run);
+      ptx::tc_fence_before();
       if (q_row < SEQ) {
         const float inv = 1.f / l;
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(seq) * SEQ + q_row) * LDO + h * HD);
@@ -265,9 +296,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
           dst[i] = t;
         }
       }
+      ++ns;
     }
   }
 
+  __syncwarp();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -292,7 +325,7 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
     configured = true;
   }
   const CUtensorMap& tm = get_tmap_2d_bf16(qkv, LDQ, static_cast<uint64_t>(nseq) * SEQ, LDQ, 64, 128);
-  const int items = nseq * NH * NQT;
+  const int items = nseq * NH * NPAIR;
   attention_tc_kernel<<<items < sms ? items : sms, THREADS, SMEM_BYTES, s>>>(tm, out, nseq);
   DP_LAUNCH_CHECK();
 }
