@@ -50,9 +50,11 @@ struct TileGeom {
   int tiles_x, tiles_y;  // conv only
   int unit_start[4];     // first unit of every group, unit_start[ngroups..3] = m_units
   int tiles_in_group[3]; // real m-tiles per group (tiles beyond are padding: loaded, not stored)
+  int tma_out;           // 1: bf16 row-major output goes smem -> TMA store (full-line writes)
 };
 struct WeightMaps {
   CUtensorMap b[3];      // one weight tensor map per group
+  CUtensorMap o[3];      // output tensor maps (TMA-store epilogue), one per group; o[0] for convs
 };
 
 __device__ __forceinline__ int unit_group(const TileGeom& g, int mu) {
@@ -69,7 +71,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float pe = p * t * exp2f(-1.4426950408889634f * z * z);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));  // MUFU, no range fix-ups
+  const float pe = p * t * e;
   return 0.5f * x * (x < 0.f ? pe : 2.0f - pe);
 }
 
@@ -119,12 +123,18 @@ __device__ __forceinline__ void store32(bf16* p, const float (&v)[32], bool relu
   }
 }
 
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // Epilogue for one output row `m` (linear row / NHWC pixel index) and 32 columns starting at n0.
 // `m_local` is the row inside its group (patch-embed token placement), `resv` the residual values
 // for these 32 columns, already loaded (and converted) by the caller so that the HBM round trip
 // overlaps the accumulator wait.
 __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup& gp, long long m, int n0,
-                                               float (&v)[32], const float (&resv)[32]) {
+                                               float (&v)[32], const float (&resv)[32], uint32_t slab_row = 0,
+                                               int half = 0, int swz = 0) {
   float t[32];
   if (gp.bias) {
     load32<float>(gp.bias + (op.bias_mod ? n0 % op.bias_mod : n0), t);
@@ -206,6 +216,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += t[j];
   }
+  if (slab_row) {
+    // TMA-store epilogue: this thread's 32 columns as bf16 into its 128-byte row of the warp's
+    // 32x64 slab (128B swizzle, as the output tensor map expects); one thread stores the slab later
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t a = pack2(v[8 * i], v[8 * i + 1]), b = pack2(v[8 * i + 2], v[8 * i + 3]);
+      const uint32_t c = pack2(v[8 * i + 4], v[8 * i + 5]), d = pack2(v[8 * i + 6], v[8 * i + 7]);
+      ptx::sts_u4(slab_row + (((half * 4 + i) ^ swz) << 4), a, b, c, d);
+    }
+    return;
+  }
   if (op.out) {
     if (op.out_f32)
       store32(reinterpret_cast<float*>(op.out) + off, v);
@@ -232,10 +253,8 @@ struct ColSlab {
   int nv;          // valid rows of the 32-row slab
   int wp;          // row -> pixel step: 16 for matrix rows (offset = rr), W for 8x16 conv tiles
   long long row0;  // first output row / pixel of the slab
+  int b, y, x;     // conv: image, first row, first column of the slab
 };
-__device__ __forceinline__ long long slab_off(const ColSlab& cs, int rr) {
-  return cs.row0 + (rr >> 4) * cs.wp + (rr & 15);
-}
 
 // proj / fc2: out = res + gamma * (acc + bias), fp32 in place.  The 32 residual values of this
 // lane's column were prefetched into registers before the accumulator was ready.
@@ -254,49 +273,6 @@ __device__ __forceinline__ void epi_cols_resid32(float* __restrict__ out, long l
     if (rr < cs.nv) p[rr * ld] = fmaf(ptx::lds_f32(stg + (rr * STG_PITCH + lane) * 4) + bias_v, gamma_v, rv[rr]);
 }
 
-// bf16 row-major outputs: bias, activation, optional bf16 residual(s), optional ReLU'd copy.
-// Sub-word (2-byte per lane) global stores crawl, so a lane owns TWO adjacent columns and half a
-// warp covers a row: lanes 0-15 take row 2i, lanes 16-31 row 2i+1, every access is 4 bytes per lane.
-template <int ACT>
-__device__ __forceinline__ void epi_cols_store_bf16(const GemmOp& op, const GemmGroup& gp, const ColSlab& cs, int n0,
-                                                    uint32_t stg, int lane) {
-  const int cp = (lane & 15) * 2, rsel = lane >> 4;
-  const int n = n0 + cp;
-  float b0 = 0.f, b1 = 0.f, g0 = 1.f, g1 = 1.f;
-  if (gp.bias) {
-    const int bi = op.bias_mod ? n % op.bias_mod : n;
-    b0 = gp.bias[bi], b1 = gp.bias[bi + 1];
-  }
-  if (gp.gamma) g0 = gp.gamma[n], g1 = gp.gamma[n + 1];
-  const __nv_bfloat162* res = reinterpret_cast<const __nv_bfloat162*>(op.res);
-  const __nv_bfloat162* res2 = reinterpret_cast<const __nv_bfloat162*>(op.res2);
-  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(op.out);
-  __nv_bfloat162* orl = reinterpret_cast<__nv_bfloat162*>(op.out_relu);
-  const long long ldo = op.ldo, ldr = op.ldres;
-  const long long co = op.col_off + n;
-#pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
-    const int rr = 2 * i + rsel;
-    if (rr >= cs.nv) continue;
-    const long long row = slab_off(cs, rr);
-    float v0 = ptx::lds_f32(stg + (rr * STG_PITCH + cp) * 4) + b0;
-    float v1 = ptx::lds_f32(stg + (rr * STG_PITCH + cp + 1) * 4) + b1;
-    if (ACT == ACT_RELU) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f);
-    if (ACT == ACT_GELU) v0 = gelu_erf(v0), v1 = gelu_erf(v1);
-    v0 *= g0, v1 *= g1;
-    if (res) {
-      const float2 r = __bfloat1622float2(res[(row * ldr + n) >> 1]);
-      v0 += r.x, v1 += r.y;
-    }
-    if (res2) {
-      const float2 r = __bfloat1622float2(res2[(row * ldr + n) >> 1]);
-      v0 += r.x, v1 += r.y;
-    }
-    if (ob) ob[(row * ldo + co) >> 1] = __floats2bfloat162_rn(v0, v1);
-    if (orl) orl[(row * ldo + co) >> 1] = __floats2bfloat162_rn(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
-  }
-}
-
 template <int BN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ WeightMaps tmW,
@@ -313,12 +289,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 8 * STG_WARP_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  const uint32_t stg_all = ptx::smem_u32(smem + STAGES * STAGE_BYTES + 256);  // epilogue staging, 8 warps
+  const uint32_t stg_all = ptx::smem_u32(smem + STAGES * STAGE_BYTES);  // epilogue staging, 8 warps, 1024-B aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -480,8 +456,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool resid32 = op.out_mode == O_ROWMAJOR && op.res != nullptr && op.res_f32 && op.out_f32 && op.res2 == nullptr &&
                            op.out_relu == nullptr && op.act == ACT_NONE && op.a_mode == A_ROWMAJOR &&
                            op.res == op.out && op.ldres == op.ldo && op.col_off == 0;
-      // (the column-domain bf16 store path below measured ~2x slower than row-per-thread 16-byte stores,
-      //  so only the fp32 residual form takes the transposed route for now)
+      // (a column-domain bf16 store path measured ~2x slower than row-per-thread 16-byte stores; bf16
+      //  outputs take the TMA-store route instead, only the fp32 residual form is transposed)
       const bool colwise = resid32;
       ColSlab cs;
       if (op.a_mode == A_CONV3X3) {
@@ -492,12 +468,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         cs.row0 = (static_cast<long long>(b) * op.H + (r / g.tiles_x) * TILE_H + 2 * q) * op.W + (r % g.tiles_x) * TILE_W;
         cs.wp = op.W;
         cs.nv = mt < g.tiles_in_group[0] ? 32 : 0;
+        cs.b = b, cs.y = (r / g.tiles_x) * TILE_H + 2 * q, cs.x = (r % g.tiles_x) * TILE_W;
       } else {
         const int ml0 = ((mu - g.unit_start[gi]) * CL + crank) * BM + q * 32;
         const int left = op.grp[gi].M - ml0;
         cs.nv = left >= 32 ? 32 : (left > 0 ? left : 0);
         cs.row0 = op.grp[gi].o_row_off + ml0;
         cs.wp = 16;
+        cs.b = cs.y = cs.x = 0;
       }
       const uint32_t stg = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;
       float resv[32];
@@ -527,18 +505,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) ptx::sts_f32(stg + (lane * STG_PITCH + j) * 4, __uint_as_float(r[j]));
             __syncwarp();
-            if (resid32) {
-              const float bias_v = gp.bias ? gp.bias[n] : 0.f;
-              const float gamma_v = gp.gamma ? gp.gamma[n] : 1.f;
-              epi_cols_resid32(reinterpret_cast<float*>(op.out), op.ldo, cs, n, stg, lane, bias_v, gamma_v, resv);
-            } else if (op.act == ACT_GELU) {
-              epi_cols_store_bf16<ACT_GELU>(op, gp, cs, col0 + c, stg, lane);
-            } else if (op.act == ACT_RELU) {
-              epi_cols_store_bf16<ACT_RELU>(op, gp, cs, col0 + c, stg, lane);
-            } else {
-              epi_cols_store_bf16<ACT_NONE>(op, gp, cs, col0 + c, stg, lane);
-            }
+            const float bias_v = gp.bias ? gp.bias[n] : 0.f;
+            const float gamma_v = gp.gamma ? gp.gamma[n] : 1.f;
+            epi_cols_resid32(reinterpret_cast<float*>(op.out), op.ldo, cs, n, stg, lane, bias_v, gamma_v, resv);
             __syncwarp();
+          } else if (g.tma_out) {
+            const int half = (c >> 5) & 1;
+            const uint32_t slab = stg_all + (warp - EPI_WARP0) * 4096;
+            if (half == 0) {
+              if (lane == 0) ptx::tma_store_wait_read();  // the previous slab store has drained the buffer
+              __syncwarp();
+            }
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            epilogue_chunk(op, gp, m, col0 + c, v, resv, slab + lane * 128, half, lane & 7);
+            if (half == 1) {
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && cs.nv > 0) {
+                const int ccol = op.col_off + col0 + c - 32;
+                if (op.a_mode == A_CONV3X3) ptx::tma_store_4d(&tmW.o[0], slab, ccol, cs.x, cs.y, cs.b);
+                else ptx::tma_store_2d(&tmW.o[gi], slab, ccol, static_cast<int>(cs.row0));
+                ptx::tma_store_commit();
+              }
+            }
           } else if (valid) {
             float v[32];
 #pragma unroll
@@ -557,6 +548,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (warp >= EPI_WARP0 && lane == 0) ptx::tma_store_wait_read();  // smem must outlive the bulk stores
   __syncwarp();
   ptx::tc_fence_before();
   if (CL > 1) ptx::cluster_sync_all();  // no CTA may exit while a peer can still multicast into it
@@ -744,6 +736,30 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   const uint64_t ws[1] = {(uint64_t)op.K * 2};
   const uint32_t wb[2] = {BK, (uint32_t)(bn / cl)};  // each CTA of a cluster loads bn / cl weight rows
   for (int i = 0; i < 3; ++i) tmW.b[i] = get_tmap(op.grp[i < op.ngroups ? i : 0].Wt, 2, wd, ws, wb);
+  // TMA-store epilogue for plain bf16 row-major outputs (no ReLU'd twin): rows leave the SM as full
+  // 128-byte lines instead of 32 scattered 16-byte pieces per store instruction
+  static const bool no_tma_out = getenv("DEPTHPRO_NO_TMA_STORE") != nullptr;  // debugging switch
+  g.tma_out = (!no_tma_out && op.out_mode == O_ROWMAJOR && !op.out_f32 && op.out != nullptr && op.out_relu == nullptr &&
+               bn >= 128 && op.ldo % 8 == 0 && (op.col_off % 64) == 0)
+                  ? 1
+                  : 0;
+  for (int i = 0; i < 3; ++i) tmW.o[i] = tmW.b[0];
+  if (g.tma_out) {
+    if (op.a_mode == A_CONV3X3) {
+      const uint64_t od[4] = {(uint64_t)op.ldo, (uint64_t)op.W, (uint64_t)op.H, (uint64_t)op.B};
+      const uint64_t os[3] = {(uint64_t)op.ldo * 2, (uint64_t)op.W * op.ldo * 2, (uint64_t)op.H * op.W * op.ldo * 2};
+      const uint32_t ob[4] = {64, TILE_W, 2, 1};
+      tmW.o[0] = get_tmap(op.out, 4, od, os, ob);
+    } else {
+      for (int i = 0; i < op.ngroups; ++i) {
+        // rows past a group's end are out of bounds for ITS map, so a tail tile never touches the next group
+        const uint64_t od[2] = {(uint64_t)op.ldo, (uint64_t)(op.grp[i].o_row_off + op.grp[i].M)};
+        const uint64_t os[1] = {(uint64_t)op.ldo * 2};
+        const uint32_t ob[2] = {64, 32};
+        tmW.o[i] = get_tmap(op.out, 2, od, os, ob);
+      }
+    }
+  }
 
   if (cl == 2) {
     if (bn == 256) launch<256, 2>(op, g, *tmA, tmW, stream);
