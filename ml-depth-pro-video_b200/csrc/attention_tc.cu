@@ -43,6 +43,10 @@ constexpr uint32_t SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES + 4) + 1024 + 25
 // idesc: D=f32, A=B=bf16, A K-major; B K-major (QK^T) or MN-major (PV: bit 16)
 constexpr uint32_t IDESC_QK = ptx::umma_idesc_bf16(128, 128);
 constexpr uint32_t IDESC_PV = ptx::umma_idesc_bf16(128, 64) | (1u << 16);
+// the last key block holds 577 - 512 = 65 keys: its Q K^T runs at N = 80 and its P V at K = 80
+constexpr int LAST_KEYS = SEQ - (NB - 1) * KB;                 // 65
+constexpr int LAST_N = (LAST_KEYS + 15) / 16 * 16;            // 80
+constexpr uint32_t IDESC_QK_LAST = ptx::umma_idesc_bf16(128, LAST_N);
 // smem descriptor high word: SBO = 1024 B, version 1, SWIZZLE_128B (same for K-major and MN-major tiles)
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 
@@ -133,8 +137,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       }
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer
-      const uint32_t q_lo = desc_lo(ptx::smem_u32(sQ)), k_lo = desc_lo(ptx::smem_u32(sK));
-      const uint32_t v_lo = desc_lo(ptx::smem_u32(sV)), p_lo = desc_lo(ptx::smem_u32(sP));
+      // all tiles sit at compile-time offsets from the (1024-B aligned) smem base: one live register
+      const uint32_t q_lo = desc_lo(ptx::smem_u32(sQ));
+      const uint32_t k_lo = q_lo + (2 * TILE_BYTES >> 4);
+      const uint32_t v_lo = k_lo + (KV_STAGES * TILE_BYTES >> 4);
+      const uint32_t p_lo = v_lo + (KV_STAGES * TILE_BYTES >> 4);
       int nB = 0;  // items so far in which stream B was active (its barrier phases advance only then)
       for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
         const bool hasB = 2 * (item % NPAIR) + 1 < NQT;
@@ -148,8 +155,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               const uint32_t d = tmem_base + 256 + sidx * 128 + (jj & 1) * 64;
+              const int nks = jj == NB - 1 ? LAST_N / 16 : KB / 16;
 #pragma unroll
               for (int ks = 0; ks < KB / 16; ++ks) {
+                if (ks >= nks) break;
                 // A = P: k-chunk tile (ks >> 2), +32 B per K=16 step; B = V (MN-major): +16 keys = 2048 B
                 const uint64_t da = desc(p_lo + sidx * (2 * TILE_BYTES >> 4) + (ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2);
                 const uint64_t db = desc(v_lo + st * (TILE_BYTES >> 4) + ks * (2048 >> 4));
@@ -173,7 +182,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 #pragma unroll
               for (int ks = 0; ks < HD / 16; ++ks)
                 ptx::umma_bf16(tmem_base + sidx * 128, desc(q_lo + sidx * (TILE_BYTES >> 4) + ks * 2),
-                               desc(k_lo + st * (TILE_BYTES >> 4) + ks * 2), IDESC_QK, ks != 0);
+                               desc(k_lo + st * (TILE_BYTES >> 4) + ks * 2), j == NB - 1 ? IDESC_QK_LAST : IDESC_QK,
+                               ks != 0);
               ptx::umma_commit(&s_full[sidx]);
             }
             __syncwarp();
@@ -229,8 +239,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         ptx::mbar_wait(&s_full[sidx], gbs & 1);
         ptx::tc_fence_after();
         uint32_t sr[4][32];
+        const bool last = j == NB - 1;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) ptx::tmem_ld32(tS + ch * 32 + lane_addr, sr[ch]);
+        for (int ch = 0; ch < 4; ++ch)
+          if (!(last && ch * 32 >= LAST_N)) ptx::tmem_ld32(tS + ch * 32 + lane_addr, sr[ch]);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&s_empty[sidx]);  // S is in registers: the next Q K^T may overwrite it
@@ -242,7 +254,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             float v = __uint_as_float(sr[ch][e]);
-            if (j == NB - 1 && key0 + ch * 32 + e >= SEQ) v = -INFINITY;
+            if (last && key0 + ch * 32 + e >= SEQ) v = -INFINITY;  // also covers the columns that were not loaded
             sr[ch][e] = __float_as_uint(v);
             mx = fmaxf(mx, v);
           }
@@ -256,13 +268,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         for (int ch = 0; ch < 4; ++ch) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            uint32_t pk[4];
+            const int k8 = (ch * 4 + i) * 8;            // first key of this 8-key group inside the block
+            if (last && k8 >= LAST_N) continue;          // beyond the K = 80 the last P V reads
+            uint32_t pk[4] = {0u, 0u, 0u, 0u};
+            if (!(last && k8 >= LAST_KEYS)) {            // fully masked groups are zeros without MUFU work
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const float p0 = ex2(fmaf(__uint_as_float(sr[ch][i * 8 + 2 * w]), c, -mc));
-              const float p1 = ex2(fmaf(__uint_as_float(sr[ch][i * 8 + 2 * w + 1]), c, -mc));
-              rs += p0 + p1;
-              pk[w] = pack_bf16(p0, p1);
+              for (int w = 0; w < 4; ++w) {
+                const float p0 = ex2(fmaf(__uint_as_float(sr[ch][i * 8 + 2 * w]), c, -mc));
+                const float p1 = ex2(fmaf(__uint_as_float(sr[ch][i * 8 + 2 * w + 1]), c, -mc));
+                rs += p0 + p1;
+                pk[w] = pack_bf16(p0, p1);
+              }
             }
             const int chunk = (ch & 1) * 4 + i;
             uint4* dst = reinterpret_cast<uint4*>(prow + (ch >> 1) * TILE_BYTES + ((chunk ^ (row & 7)) << 4));

@@ -231,7 +231,10 @@ void Engine::set_weight(const std::string& name, const void* data, const int64_t
     src = stage_;
   }
   const bool bf = prec_ == BF16;
-  if (bf && (name == "head.1.weight" || name == "head.1.bias" || name == "head.2.weight" || name == "head.2.bias")) {
+  const bool fusion_tail = starts_with(name, "decoder.fusions.") && name[16] != '0' &&
+                           (ends_with(name, ".deconv.weight") || ends_with(name, ".out_conv.weight"));
+  if (bf && (name == "head.1.weight" || name == "head.1.bias" || name == "head.2.weight" || name == "head.2.bias" ||
+             fusion_tail)) {
     Packed& rw = raw_[name];
     if (rw.bytes != n * 4) {
       if (rw.ptr) DP_CUDA(cudaFree(rw.ptr));
@@ -325,6 +328,16 @@ void Engine::finalize() {
     auto R = [&](const char* k) { return reinterpret_cast<const float*>(raw_.at(k).ptr); };
     compose_head(R("head.1.weight"), R("head.1.bias"), R("head.2.weight"), R("head.2.bias"), (bf16*)head_wc_, head_cb_,
                  nullptr);
+    // exact-linear fusion deconv (no bias) o out_conv (1x1 + bias) of fusion blocks 1-4 (decoder.py:176-178)
+    for (int i = 1; i <= 4; ++i) {
+      const std::string p = "decoder.fusions." + std::to_string(i) + ".";
+      Packed& pk = packed_[p + "deconv_out.weight"];
+      if (!pk.ptr) {
+        DP_CUDA(cudaMalloc(&pk.ptr, 4 * 256 * 256 * 2));
+        pk.bytes = 4 * 256 * 256 * 2;
+      }
+      compose_deconv_1x1(R((p + "deconv.weight").c_str()), R((p + "out_conv.weight").c_str()), (bf16*)pk.ptr, 256, nullptr);
+    }
     DP_CUDA(cudaStreamSynchronize(nullptr));
   }
   if (finalized_) return;  // workspace already allocated; weights re-bound above
@@ -625,7 +638,11 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
             nullptr, t_, nullptr);
     conv3x3(t_, S, 256, p + "resnet2.residual.3.weight", 256, F(p + "resnet2.residual.3.bias"), ACT_NONE, xin, nullptr,
             x2_, nullptr);
-    if (i != 0) {
+    if (i != 0 && prec_ == BF16) {
+      // deconv o out_conv pre-composed into one ConvT (+bias): one GEMM and one full-resolution
+      // round trip less per level
+      convT(x2_, S, 256, p + "deconv_out.weight", 256, feat_[i], 256, 0, F(p + "out_conv.bias"), nullptr);
+    } else if (i != 0) {
       convT(x2_, S, 256, p + "deconv.weight", 256, y_, 256, 0, nullptr, nullptr);
       conv1x1(y_, 2 * S, 256, p + "out_conv.weight", 256, feat_[i], F(p + "out_conv.bias"));
     } else {

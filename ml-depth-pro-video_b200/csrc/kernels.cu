@@ -601,9 +601,24 @@ __global__ void compose_head_b_kernel(const float* __restrict__ b1, const float*
   cb[9 * 32 + c2] = full;
 }
 
+__global__ void compose_deconv_kernel(const float* __restrict__ wd, const float* __restrict__ wo, bf16* __restrict__ wc,
+                                      int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over [4*C][C]
+  if (idx >= 4 * C * C) return;
+  const int ci = idx % C, n = idx / C, cop = n % C, q = n / C, dy = q >> 1, dx = q & 1;
+  float acc = 0.f;
+  for (int co = 0; co < C; ++co) acc = fmaf(wo[cop * C + co], wd[((ci * C + co) * 2 + dy) * 2 + dx], acc);
+  wc[idx] = __float2bfloat16_rn(acc);
+}
+
 }  // namespace
 
 // ============================================================================ host wrappers
+void compose_deconv_1x1(const float* wd, const float* wo, bf16* wc, int C, cudaStream_t s) {
+  compose_deconv_kernel<<<blocks_for(4LL * C * C, 256), 256, 0, s>>>(wd, wo, wc, C);
+  DP_LAUNCH_CHECK();
+}
+
 void compose_head(const float* w1, const float* b1, const float* w2, const float* b2, bf16* wc, float* cb,
                   cudaStream_t s) {
   compose_head_w_kernel<<<blocks_for(128 * 1152, 128), 128, 0, s>>>(w1, w2, wc);

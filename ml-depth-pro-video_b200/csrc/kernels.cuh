@@ -93,6 +93,10 @@ void pack_convT_iohw(const float* w, T* out, int I, int O, cudaStream_t s);  // 
 //   cb[tap][c2] = sum_c1 b1[c1]*w2[c2,c1,tap]  (9x32), cb[9][c2] = b2[c2] + sum_tap cb[tap][c2].
 void compose_head(const float* w1, const float* b1, const float* w2, const float* b2, bf16* wc, float* cb,
                   cudaStream_t s);
+// FeatureFusionBlock2d tail (decoder.py:176-178): ConvTranspose2d k2 s2 (no bias, weight (ci,co,2,2))
+// followed by a 1x1 conv (weight (co',co)) composed in fp32 into one ConvT in the GEMM layout
+//   wc[(dy*2+dx)*C + co'][ci] = sum_co wo[co'][co] * wd[ci][co][dy][dx]      (C x C channels)
+void compose_deconv_1x1(const float* wd, const float* wo, bf16* wc, int C, cudaStream_t s);
 void pack_oihw_to_hwio_f32(const float* w, float* out, int O, int I, int KH, int KW, cudaStream_t s);
 
 }  // namespace dp

@@ -61,8 +61,9 @@ def test_oracle_matches_golden(oracle_run, golden_dir):
     _, out, taps = oracle_run
     gold = np.load(os.path.join(golden_dir, "reference_outputs.npz"))
     g = torch.from_numpy(gold["depth_1536"])
-    assert float(_pix_rel(out["depth"][::16, ::16], g).max()) <= 2e-5
-    assert abs(float(out["focallength_px"]) - float(gold["f_px_1536"])) / float(gold["f_px_1536"]) <= 2e-5
+    # two fp32 CPU runs on different hosts (other core count / oneDNN blocking) differ by a few 1e-5
+    assert float(_pix_rel(out["depth"][::16, ::16], g).max()) <= 1e-4
+    assert abs(float(out["focallength_px"]) - float(gold["f_px_1536"])) / float(gold["f_px_1536"]) <= 1e-4
 
 
 def test_fp32_vs_oracle(model_fp32, oracle_run, golden_dir):
