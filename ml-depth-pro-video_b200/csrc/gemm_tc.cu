@@ -63,18 +63,61 @@ __device__ __forceinline__ int unit_group(const TileGeom& g, int mu) {
 
 // GELU (exact-erf form) for the bf16 path: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far
 // below bf16 output rounding) on the MUFU rcp / ex2 units instead of the ~30-instruction erff().
-// 1 + erf(x/sqrt2) is formed without cancellation: p*e for x < 0, 2 - p*e for x >= 0.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));  // MUFU, no range fix-ups
-  const float pe = p * t * e;
-  return 0.5f * x * (x < 0.f ? pe : 2.0f - pe);
+// The fc1 epilogue is instruction-issue bound (ncu: 87 M warp instructions vs 23 M for the same GEMM
+// without GELU), so two elements are processed per instruction with the packed fp32x2 FMA pipe.
+struct F2 {
+  unsigned long long u;
+};
+__device__ __forceinline__ F2 pack_f2(float a, float b) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(F2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v.u)); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.u) : "l"(a.u), "l"(b.u), "l"(c.u));
+  return r;
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u));
+  return r;
+}
+__device__ __forceinline__ F2 splat2(float a) { return pack_f2(a, a); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)),  erf(z) = sign(z) (1 - (a1 t + ... + a5 t^5) exp(-z^2)),  t = 1/(1 + p z)
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const F2 x = pack_f2(x0, x1);
+  F2 z;
+  z.u = x.u & 0x7fffffff7fffffffull;                       // |x|
+  z = mul2(z, splat2(0.70710678118654752440f));
+  const F2 d = fma2(z, splat2(0.3275911f), splat2(1.0f));
+  float d0, d1;
+  unpack_f2(d, d0, d1);
+  const F2 t = pack_f2(rcp_approx(d0), rcp_approx(d1));
+  F2 p = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
+  p = fma2(p, t, splat2(1.421413741f));
+  p = fma2(p, t, splat2(-0.284496736f));
+  p = fma2(p, t, splat2(0.254829592f));
+  p = mul2(p, t);
+  const F2 w = mul2(mul2(z, splat2(-1.4426950408889634f)), z);  // -log2(e) z^2
+  float w0, w1;
+  unpack_f2(w, w0, w1);
+  const F2 e = pack_f2(ex2_approx(w0), ex2_approx(w1));
+  F2 u = fma2(p, mul2(e, splat2(-1.0f)), splat2(1.0f));          // 1 - p e  = |erf|
+  u.u |= x.u & 0x8000000080000000ull;                            // copysign(|erf|, x)
+  const F2 g = mul2(mul2(x, splat2(0.5f)), fma2(u, splat2(1.0f), splat2(1.0f)));
+  unpack_f2(g, x0, x1);
 }
 
 template <typename T>
@@ -146,7 +189,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (op.act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
   }
   if (gp.gamma) {
     load32<float>(gp.gamma + n0, t);
@@ -329,6 +372,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // register split: the four control warps need few registers, the epilogue warps hold a whole
+  // tile's residual values in flight (384 x 168 = 128 x 40 + 256 x 232)
+  if (warp < EPI_WARP0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     // The whole warp walks the loop (warp-uniform control flow: coordinates and descriptors stay in
@@ -420,7 +467,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // ------------------------------------------------------------ epilogue
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int grp = (warp - EPI_WARP0) >> 2;  // column half
@@ -458,7 +507,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                            op.res == op.out && op.ldres == op.ldo && op.col_off == 0;
       // (a column-domain bf16 store path measured ~2x slower than row-per-thread 16-byte stores; bf16
       //  outputs take the TMA-store route instead, only the fp32 residual form is transposed)
-      const bool colwise = resid32;
       ColSlab cs;
       if (op.a_mode == A_CONV3X3) {
         const int mt = mu * CL + crank;
@@ -478,10 +526,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         cs.b = cs.y = cs.x = 0;
       }
       const uint32_t stg = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;
+      const bool colwise = resid32;
       float resv[32];
       const bool has_res = !colwise && op.res != nullptr && valid && active;   // row-per-thread forms
       if (has_res) load_res(op, m, col0, resv);  // in flight while the MMA of this tile finishes
-      if (resid32 && active) prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + lane, resv);
+      // fp32 residual form: the residual values of TWO chunks are in flight ahead of the one being
+      // processed (the first two are requested before the accumulator is even ready)
+      float resn[32];
+      if (resid32 && active) {
+        prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + lane, resv);
+        if (COLS_PER_GRP > 32) prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + 32 + lane, resn);
+      }
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       if (active) {
@@ -490,9 +545,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t r[32];
           ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + grp * COLS_PER_GRP + c, r);
           const bool more = c + 32 < COLS_PER_GRP;
-          float resn[32];
+          float resn2[32];
           if (has_res && more) load_res(op, m, col0 + c + 32, resn);
-          if (resid32 && more) prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + c + 32 + lane, resn);
+          if (resid32 && c + 64 < COLS_PER_GRP)
+            prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + c + 64 + lane, resn2);
           ptx::tmem_ld_wait();
           if (!more) {
             // the accumulator has left tensor memory: hand the buffer back to the MMA warp now, the
@@ -536,7 +592,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             epilogue_chunk(op, gp, m, col0 + c, v, resv);
           }
-          if ((has_res || resid32) && more) {
+          if (resid32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) resv[j] = resn[j], resn[j] = resn2[j];
+          } else if (has_res && more) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) resv[j] = resn[j];
           }
