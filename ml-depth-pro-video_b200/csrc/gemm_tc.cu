@@ -54,7 +54,8 @@ struct TileGeom {
 };
 struct WeightMaps {
   CUtensorMap b[3];      // one weight tensor map per group
-  CUtensorMap o[3];      // output tensor maps (TMA-store epilogue), one per group; o[0] for convs
+  CUtensorMap o[3];      // output tensor maps (TMA-store epilogue), one per group; o[0] for convs / ConvT
+  CUtensorMap orelu;     // same geometry as o[0] over the ReLU'd twin (dual-store convs)
 };
 
 __device__ __forceinline__ int unit_group(const TileGeom& g, int mu) {
@@ -177,7 +178,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // overlaps the accumulator wait.
 __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup& gp, long long m, int n0,
                                                float (&v)[32], const float (&resv)[32], uint32_t slab_row = 0,
-                                               int half = 0, int swz = 0) {
+                                               int half = 0, int swz = 0, uint32_t* keep = nullptr) {
   float t[32];
   if (gp.bias) {
     load32<float>(gp.bias + (op.bias_mod ? n0 % op.bias_mod : n0), t);
@@ -201,6 +202,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup
   if (op.out_mode == O_ROWMAJOR) {
     off = m * op.ldo + op.col_off + n0;
   } else if (op.out_mode == O_CONVT2X2) {
+    off = 0;
+    if (!slab_row) {
     const int q = n0 / op.cout, co = n0 - q * op.cout;
     const int x = static_cast<int>(m % op.W);
     const long long by = m / op.W;  // b*H + y
@@ -208,6 +211,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup
     const long long b = by / op.H;
     const long long orow = (b * 2 * op.H + 2 * y + (q >> 1)) * (2LL * op.W) + 2 * x + (q & 1);
     off = orow * op.ldo + op.col_off + co;
+    }
   } else if (op.out_mode == O_PATCH_EMBED) {
     const long long seq = m / 576;
     const int p = static_cast<int>(m - seq * 576);
@@ -267,6 +271,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup
       const uint32_t a = pack2(v[8 * i], v[8 * i + 1]), b = pack2(v[8 * i + 2], v[8 * i + 3]);
       const uint32_t c = pack2(v[8 * i + 4], v[8 * i + 5]), d = pack2(v[8 * i + 6], v[8 * i + 7]);
       ptx::sts_u4(slab_row + (((half * 4 + i) ^ swz) << 4), a, b, c, d);
+      if (keep) keep[4 * i] = a, keep[4 * i + 1] = b, keep[4 * i + 2] = c, keep[4 * i + 3] = d;
     }
     return;
   }
@@ -316,7 +321,15 @@ __device__ __forceinline__ void epi_cols_resid32(float* __restrict__ out, long l
     if (rr < cs.nv) p[rr * ld] = fmaf(ptx::lds_f32(stg + (rr * STG_PITCH + lane) * 4) + bias_v, gamma_v, rv[rr]);
 }
 
-template <int BN, int CL>
+// EPI selects the epilogue form at compile time so that each instantiation carries only its own
+// code and registers (one monolithic epilogue made every added feature slow the hot GEMMs down):
+//   EPI_TMA   bf16 row-major output, single store: row-per-thread math -> smem slab -> TMA store
+//   EPI_RES32 fp32 residual update in place (proj / fc2): smem transpose, column-per-lane, deep prefetch
+//   EPI_MISC  everything else: ConvT scatter and dual (x, relu(x)) stores via TMA, direct stores for
+//             patch-embed placement, fused dots, small / odd shapes
+enum { EPI_TMA = 0, EPI_RES32 = 1, EPI_MISC = 2 };
+
+template <int BN, int CL, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ WeightMaps tmW,
                const GemmOp op, const TileGeom g) {
@@ -501,12 +514,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const GemmGroup& gp = op.grp[gi];
       const bool active = (BN >= 64 || grp == 0);
       const int col0 = nt * BN + grp * COLS_PER_GRP;
-      // ---- which epilogue form (warp-uniform, fixed per launch)
-      const bool resid32 = op.out_mode == O_ROWMAJOR && op.res != nullptr && op.res_f32 && op.out_f32 && op.res2 == nullptr &&
-                           op.out_relu == nullptr && op.act == ACT_NONE && op.a_mode == A_ROWMAJOR &&
-                           op.res == op.out && op.ldres == op.ldo && op.col_off == 0;
-      // (a column-domain bf16 store path measured ~2x slower than row-per-thread 16-byte stores; bf16
-      //  outputs take the TMA-store route instead, only the fp32 residual form is transposed)
       ColSlab cs;
       if (op.a_mode == A_CONV3X3) {
         const int mt = mu * CL + crank;
@@ -526,83 +533,141 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         cs.b = cs.y = cs.x = 0;
       }
       const uint32_t stg = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;
-      const bool colwise = resid32;
-      float resv[32];
-      const bool has_res = !colwise && op.res != nullptr && valid && active;   // row-per-thread forms
-      if (has_res) load_res(op, m, col0, resv);  // in flight while the MMA of this tile finishes
-      // fp32 residual form: the residual values of TWO chunks are in flight ahead of the one being
-      // processed (the first two are requested before the accumulator is even ready)
-      float resn[32];
-      if (resid32 && active) {
-        prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + lane, resv);
-        if (COLS_PER_GRP > 32) prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + 32 + lane, resn);
+      const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + grp * COLS_PER_GRP;
+      if (!active) {
+        ptx::mbar_wait(&tfull[acc], acc_ph);
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tempty[acc]);
+        continue;
       }
-      ptx::mbar_wait(&tfull[acc], acc_ph);
-      ptx::tc_fence_after();
-      if (active) {
+      if constexpr (EPI == EPI_RES32) {
+        // ---- proj / fc2: out = res + gamma * (acc + bias), fp32 in place, column-per-lane through smem.
+        // The residual values of TWO chunks are in flight ahead of the one being processed; the first
+        // two are requested before the accumulator is even ready.
+        const float* resp = reinterpret_cast<const float*>(op.res);
+        float resv[32], resn[32];
+        prefetch_res32(resp, op.ldres, cs, col0 + lane, resv);
+        if (COLS_PER_GRP > 32) prefetch_res32(resp, op.ldres, cs, col0 + 32 + lane, resn);
+        ptx::mbar_wait(&tfull[acc], acc_ph);
+        ptx::tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < COLS_PER_GRP; c += 32) {
           uint32_t r[32];
-          ptx::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + grp * COLS_PER_GRP + c, r);
-          const bool more = c + 32 < COLS_PER_GRP;
+          ptx::tmem_ld32(t_acc + c, r);
           float resn2[32];
-          if (has_res && more) load_res(op, m, col0 + c + 32, resn);
-          if (resid32 && c + 64 < COLS_PER_GRP)
-            prefetch_res32(reinterpret_cast<const float*>(op.res), op.ldres, cs, col0 + c + 64 + lane, resn2);
+          if (c + 64 < COLS_PER_GRP) prefetch_res32(resp, op.ldres, cs, col0 + c + 64 + lane, resn2);
           ptx::tmem_ld_wait();
-          if (!more) {
-            // the accumulator has left tensor memory: hand the buffer back to the MMA warp now, the
-            // global stores below overlap the next tile's mainloop
+          if (c + 32 >= COLS_PER_GRP) {  // accumulator is out of TMEM: release it, stores overlap the next tile
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[acc]);
           }
-          if (colwise) {
-            const int n = col0 + c + lane;
+          const int n = col0 + c + lane;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) ptx::sts_f32(stg + (lane * STG_PITCH + j) * 4, __uint_as_float(r[j]));
-            __syncwarp();
-            const float bias_v = gp.bias ? gp.bias[n] : 0.f;
-            const float gamma_v = gp.gamma ? gp.gamma[n] : 1.f;
-            epi_cols_resid32(reinterpret_cast<float*>(op.out), op.ldo, cs, n, stg, lane, bias_v, gamma_v, resv);
-            __syncwarp();
-          } else if (g.tma_out) {
+          for (int j = 0; j < 32; ++j) ptx::sts_f32(stg + (lane * STG_PITCH + j) * 4, __uint_as_float(r[j]));
+          __syncwarp();
+          const float bias_v = gp.bias ? gp.bias[n] : 0.f;
+          const float gamma_v = gp.gamma ? gp.gamma[n] : 1.f;
+          epi_cols_resid32(reinterpret_cast<float*>(op.out), op.ldo, cs, n, stg, lane, bias_v, gamma_v, resv);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) resv[j] = resn[j], resn[j] = resn2[j];
+        }
+      } else {
+        // ---- row-per-thread math; output through a swizzled smem slab + TMA store (g.tma_out) or direct
+        const uint32_t slab = stg_all + (warp - EPI_WARP0) * 4096;
+        const bool has_res = op.res != nullptr && valid;
+        float resv[32];
+        if (has_res) load_res(op, m, col0, resv);  // in flight while the MMA of this tile finishes
+        uint32_t keep0[16], keep1[16];             // EPI_MISC dual stores: packed words of both slab halves
+        ptx::mbar_wait(&tfull[acc], acc_ph);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < COLS_PER_GRP; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(t_acc + c, r);
+          const bool more = c + 32 < COLS_PER_GRP;
+          float resn[32];
+          if (has_res && more) load_res(op, m, col0 + c + 32, resn);
+          ptx::tmem_ld_wait();
+          if (!more) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty[acc]);
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (EPI == EPI_TMA || g.tma_out) {
             const int half = (c >> 5) & 1;
-            const uint32_t slab = stg_all + (warp - EPI_WARP0) * 4096;
             if (half == 0) {
               if (lane == 0) ptx::tma_store_wait_read();  // the previous slab store has drained the buffer
               __syncwarp();
             }
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            epilogue_chunk(op, gp, m, col0 + c, v, resv, slab + lane * 128, half, lane & 7);
+            if constexpr (EPI == EPI_TMA) {
+              epilogue_chunk(op, gp, m, col0 + c, v, resv, slab + lane * 128, half, lane & 7);
+            } else {
+              epilogue_chunk(op, gp, m, col0 + c, v, resv, slab + lane * 128, half, lane & 7,
+                             op.out_relu ? (half ? keep1 : keep0) : nullptr);
+            }
             if (half == 1) {
               ptx::fence_proxy_async();
               __syncwarp();
-              if (lane == 0 && cs.nv > 0) {
-                const int ccol = op.col_off + col0 + c - 32;
-                if (op.a_mode == A_CONV3X3) ptx::tma_store_4d(&tmW.o[0], slab, ccol, cs.x, cs.y, cs.b);
-                else ptx::tma_store_2d(&tmW.o[gi], slab, ccol, static_cast<int>(cs.row0));
-                ptx::tma_store_commit();
+              const int ccol = op.col_off + col0 + c - 32;
+              if constexpr (EPI == EPI_TMA) {
+                if (lane == 0 && cs.nv > 0) {
+                  if (op.a_mode == A_CONV3X3) ptx::tma_store_4d(&tmW.o[0], slab, ccol, cs.x, cs.y, cs.b);
+                  else ptx::tma_store_2d(&tmW.o[gi], slab, ccol, static_cast<int>(cs.row0));
+                  ptx::tma_store_commit();
+                }
+              } else {
+                // ConvT: n-chunk -> (parity, channel); the slab is 32 consecutive input pixels of one row
+                int cq = 0, cx = 0, cby = 0, cco = ccol;
+                if (op.out_mode == O_CONVT2X2) {
+                  const int nn = col0 + c - 32;
+                  cq = nn / op.cout;
+                  cco = op.col_off + nn - cq * op.cout;
+                  cx = static_cast<int>(cs.row0 % op.W);
+                  cby = static_cast<int>(cs.row0 / op.W);
+                }
+                auto issue = [&](const CUtensorMap* tm) {
+                  if (op.out_mode == O_CONVT2X2) ptx::tma_store_5d(tm, slab, cco, cq & 1, cx, cq >> 1, cby);
+                  else if (op.a_mode == A_CONV3X3) ptx::tma_store_4d(tm, slab, ccol, cs.x, cs.y, cs.b);
+                  else ptx::tma_store_2d(tm, slab, ccol, static_cast<int>(cs.row0));
+                  ptx::tma_store_commit();
+                };
+                if (lane == 0 && cs.nv > 0) issue(&tmW.o[0]);
+                if (op.out_relu) {
+                  if (lane == 0) ptx::tma_store_wait_read();
+                  __syncwarp();
+                  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+                  for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t* kp = hh ? keep1 : keep0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      uint32_t w[4];
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&kp[4 * i + e]);
+                        x = __hmax2(x, zero);
+                        w[e] = *reinterpret_cast<uint32_t*>(&x);
+                      }
+                      ptx::sts_u4(slab + lane * 128 + (((hh * 4 + i) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
+                    }
+                  }
+                  ptx::fence_proxy_async();
+                  __syncwarp();
+                  if (lane == 0 && cs.nv > 0) issue(&tmW.orelu);
+                }
               }
             }
           } else if (valid) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             epilogue_chunk(op, gp, m, col0 + c, v, resv);
           }
-          if (resid32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) resv[j] = resn[j], resn[j] = resn2[j];
-          } else if (has_res && more) {
+          if (has_res && more) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) resv[j] = resn[j];
           }
         }
-      } else {
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tempty[acc]);
       }
     }
   }
@@ -638,17 +703,18 @@ EncodeTiledFn encode_fn() {
 
 struct TmapKey {
   const void* ptr;
-  uint64_t d0, d1, d2, d3, s1, s2, s3;
-  uint32_t b0, b1, b2, b3;
+  uint64_t d0, d1, d2, d3, d4, s1, s2, s3, s4;
+  uint32_t b0, b1, b2, b3, b4;
   bool operator==(const TmapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && s1 == o.s1 &&
-           s2 == o.s2 && s3 == o.s3 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && b3 == o.b3;
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && d4 == o.d4 && s1 == o.s1 &&
+           s2 == o.s2 && s3 == o.s3 && s4 == o.s4 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && b3 == o.b3 && b4 == o.b4;
   }
 };
 struct TmapHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
-    for (uint64_t v : {k.d0, k.d1, k.d2, k.d3, k.s1, k.s2, k.s3, (uint64_t)k.b0, (uint64_t)k.b1, (uint64_t)k.b2})
+    for (uint64_t v : {k.d0, k.d1, k.d2, k.d3, k.d4, k.s1, k.s2, k.s3, k.s4, (uint64_t)k.b0, (uint64_t)k.b1, (uint64_t)k.b2,
+                       (uint64_t)k.b3})
       h = h * 1000003u ^ v;
     return h;
   }
@@ -660,15 +726,16 @@ std::unordered_map<TmapKey, CUtensorMap, TmapHash>& tmap_cache() {
 
 const CUtensorMap& get_tmap(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                             const uint32_t* box) {
-  TmapKey key{ptr, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, strides_bytes[0],
-              rank > 2 ? strides_bytes[1] : 0, rank > 3 ? strides_bytes[2] : 0, box[0], box[1],
-              rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0};
+  TmapKey key{ptr, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, rank > 4 ? dims[4] : 0,
+              strides_bytes[0], rank > 2 ? strides_bytes[1] : 0, rank > 3 ? strides_bytes[2] : 0,
+              rank > 4 ? strides_bytes[3] : 0, box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+              rank > 4 ? box[4] : 0};
   auto& cache = tmap_cache();
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   CUtensorMap tm;
-  cuuint64_t gd[4], gs[3];
-  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) gd[i] = dims[i], bx[i] = box[i];
   for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
   DP_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16-byte aligned");
@@ -689,14 +756,14 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int CL>
+template <int BN, int CL, int EPI>
 void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const WeightMaps& tmW,
             cudaStream_t stream) {
   constexpr int STAGES = Cfg<BN>::STAGES;
   constexpr size_t SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + 8 * STG_WARP_BYTES;
   static bool configured = false;
   if (!configured) {
-    DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
   const int units = g.m_units * g.n_tiles;
@@ -712,7 +779,7 @@ void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const W
   attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  DP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, tmA, tmW, op, g));
+  DP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL, EPI>, tmA, tmW, op, g));
   count_launch();
 }
 
@@ -798,35 +865,59 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   // TMA-store epilogue for plain bf16 row-major outputs (no ReLU'd twin): rows leave the SM as full
   // 128-byte lines instead of 32 scattered 16-byte pieces per store instruction
   static const bool no_tma_out = getenv("DEPTHPRO_NO_TMA_STORE") != nullptr;  // debugging switch
-  g.tma_out = (!no_tma_out && op.out_mode == O_ROWMAJOR && !op.out_f32 && op.out != nullptr && op.out_relu == nullptr &&
-               bn >= 128 && op.ldo % 8 == 0 && (op.col_off % 64) == 0)
-                  ? 1
-                  : 0;
+  const bool rowmajor_ok = op.out_mode == O_ROWMAJOR && !op.out_f32 && op.out != nullptr;
+  // ConvT: a 32-row slab must be 32 consecutive input pixels of ONE image row, a 64-column chunk must
+  // stay inside one (dy, dx) parity
+  const bool convt_ok = op.out_mode == O_CONVT2X2 && op.out != nullptr && op.W % 32 == 0 && op.cout % 64 == 0 &&
+                        op.a_mode == A_ROWMAJOR && op.ngroups == 1 && op.M % 32 == 0;
+  g.tma_out = (!no_tma_out && (rowmajor_ok || convt_ok) && bn >= 128 && op.ldo % 8 == 0 && (op.col_off % 64) == 0) ? 1 : 0;
   for (int i = 0; i < 3; ++i) tmW.o[i] = tmW.b[0];
+  tmW.orelu = tmW.b[0];
   if (g.tma_out) {
-    if (op.a_mode == A_CONV3X3) {
-      const uint64_t od[4] = {(uint64_t)op.ldo, (uint64_t)op.W, (uint64_t)op.H, (uint64_t)op.B};
-      const uint64_t os[3] = {(uint64_t)op.ldo * 2, (uint64_t)op.W * op.ldo * 2, (uint64_t)op.H * op.W * op.ldo * 2};
-      const uint32_t ob[4] = {64, TILE_W, 2, 1};
-      tmW.o[0] = get_tmap(op.out, 4, od, os, ob);
-    } else {
-      for (int i = 0; i < op.ngroups; ++i) {
-        // rows past a group's end are out of bounds for ITS map, so a tail tile never touches the next group
-        const uint64_t od[2] = {(uint64_t)op.ldo, (uint64_t)(op.grp[i].o_row_off + op.grp[i].M)};
-        const uint64_t os[1] = {(uint64_t)op.ldo * 2};
-        const uint32_t ob[2] = {64, 32};
-        tmW.o[i] = get_tmap(op.out, 2, od, os, ob);
+    auto make = [&](const void* base, int group) -> const CUtensorMap& {
+      if (op.out_mode == O_CONVT2X2) {
+        // output (b, 2y+dy, 2x+dx, c) viewed as [c][dx][x][dy][b*H+y]
+        const uint64_t ld = (uint64_t)op.ldo * 2;
+        const uint64_t od[5] = {(uint64_t)op.ldo, 2, (uint64_t)op.W, 2, (uint64_t)op.B * op.H};
+        const uint64_t os[4] = {ld, 2 * ld, 2 * (uint64_t)op.W * ld, 4 * (uint64_t)op.W * ld};
+        const uint32_t ob[5] = {64, 1, 32, 1, 1};
+        return get_tmap(base, 5, od, os, ob);
       }
-    }
+      if (op.a_mode == A_CONV3X3) {
+        const uint64_t od[4] = {(uint64_t)op.ldo, (uint64_t)op.W, (uint64_t)op.H, (uint64_t)op.B};
+        const uint64_t os[3] = {(uint64_t)op.ldo * 2, (uint64_t)op.W * op.ldo * 2, (uint64_t)op.H * op.W * op.ldo * 2};
+        const uint32_t ob[4] = {64, TILE_W, 2, 1};
+        return get_tmap(base, 4, od, os, ob);
+      }
+      // rows past a group's end are out of bounds for ITS map, so a tail tile never touches the next group
+      const uint64_t od[2] = {(uint64_t)op.ldo, (uint64_t)(op.grp[group].o_row_off + op.grp[group].M)};
+      const uint64_t os[1] = {(uint64_t)op.ldo * 2};
+      const uint32_t ob[2] = {64, 32};
+      return get_tmap(base, 2, od, os, ob);
+    };
+    for (int i = 0; i < op.ngroups; ++i) tmW.o[i] = make(op.out, i);
+    if (op.out_relu) tmW.orelu = make(op.out_relu, 0);
   }
 
+  const bool resid32 = op.out_mode == O_ROWMAJOR && op.res != nullptr && op.res_f32 && op.out_f32 && op.res2 == nullptr &&
+                       op.out_relu == nullptr && op.act == ACT_NONE && op.a_mode == A_ROWMAJOR && op.res == op.out &&
+                       op.ldres == op.ldo && op.col_off == 0 && bn >= 128;
+  const bool plain_tma = g.tma_out && op.out_mode == O_ROWMAJOR && op.out_relu == nullptr;
+  const int epi = resid32 ? EPI_RES32 : (plain_tma ? EPI_TMA : EPI_MISC);
+#define DP_LAUNCH(BN_, CL_)                                                          \
+  do {                                                                               \
+    if (epi == EPI_RES32) launch<BN_, CL_, EPI_RES32>(op, g, *tmA, tmW, stream);     \
+    else if (epi == EPI_TMA) launch<BN_, CL_, EPI_TMA>(op, g, *tmA, tmW, stream);    \
+    else launch<BN_, CL_, EPI_MISC>(op, g, *tmA, tmW, stream);                       \
+  } while (0)
   if (cl == 2) {
-    if (bn == 256) launch<256, 2>(op, g, *tmA, tmW, stream);
-    else launch<128, 2>(op, g, *tmA, tmW, stream);
-  } else if (bn == 256) launch<256, 1>(op, g, *tmA, tmW, stream);
-  else if (bn == 128) launch<128, 1>(op, g, *tmA, tmW, stream);
-  else if (bn == 64) launch<64, 1>(op, g, *tmA, tmW, stream);
-  else launch<32, 1>(op, g, *tmA, tmW, stream);
+    if (bn == 256) DP_LAUNCH(256, 2);
+    else DP_LAUNCH(128, 2);
+  } else if (bn == 256) DP_LAUNCH(256, 1);
+  else if (bn == 128) DP_LAUNCH(128, 1);
+  else if (bn == 64) launch<64, 1, EPI_MISC>(op, g, *tmA, tmW, stream);
+  else launch<32, 1, EPI_MISC>(op, g, *tmA, tmW, stream);
+#undef DP_LAUNCH
 }
 
 }  // namespace dp
