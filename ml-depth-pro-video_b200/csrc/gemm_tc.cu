@@ -35,8 +35,7 @@ template <int BN>
 struct Cfg {
   static constexpr int STAGES = 4;
 };
-constexpr int STG_PITCH = 33;                                // floats per staged row (conflict-free both ways)
-constexpr int STG_WARP_BYTES = 32 * STG_PITCH * 4;           // one 32x32 fp32 chunk per epilogue warp
+constexpr int STG_WARP_BYTES = 4096;                         // one swizzled 32x32 fp32 chunk / TMA slab per epilogue warp
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;
@@ -306,19 +305,34 @@ struct ColSlab {
 
 // proj / fc2: out = res + gamma * (acc + bias), fp32 in place.  The 32 residual values of this
 // lane's column were prefetched into registers before the accumulator was ready.
-__device__ __forceinline__ void prefetch_res32(const float* __restrict__ res, long long ld, const ColSlab& cs, int n,
-                                               float (&rv)[32]) {
-  const float* p = res + cs.row0 * ld + n;
+// fp32 residual epilogue, 128-bit form.  The warp's 32x32 accumulator chunk is staged row-per-thread
+// into a 4 KB smem tile (16-byte chunks XOR-swizzled by row, conflict-free both ways); afterwards lane
+// (rg = lane >> 3, cq = lane & 7) owns columns [4cq, 4cq+4) of rows rg, rg+4, ..., rg+28, so every
+// global access is a 128-byte row segment moved by LDG.128 / STG.128: 4x fewer LSU instructions than
+// the 32-bit column-per-lane form (the epilogue of proj / fc2 was LSU-issue bound).
+__device__ __forceinline__ void prefetch_res4(const float* __restrict__ res, long long ld, const ColSlab& cs, int n0,
+                                              int lane, float4 (&rv)[8]) {
+  const float* p = res + (cs.row0 + (lane >> 3)) * ld + n0 + (lane & 7) * 4;
 #pragma unroll
-  for (int rr = 0; rr < 32; ++rr) rv[rr] = rr < cs.nv ? p[rr * ld] : 0.f;
+  for (int i = 0; i < 8; ++i)
+    rv[i] = (4 * i + (lane >> 3)) < cs.nv ? *reinterpret_cast<const float4*>(p + 4 * i * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
-__device__ __forceinline__ void epi_cols_resid32(float* __restrict__ out, long long ld, const ColSlab& cs, int n,
-                                                 uint32_t stg, int lane, float bias_v, float gamma_v,
-                                                 const float (&rv)[32]) {
-  float* p = out + cs.row0 * ld + n;
+__device__ __forceinline__ void epi_rows4_resid32(float* __restrict__ out, long long ld, const ColSlab& cs, int n0,
+                                                  uint32_t stg, int lane, const float4 b4, const float4 g4,
+                                                  const float4 (&rv)[8]) {
+  const int rg = lane >> 3, cq = lane & 7;
+  float* p = out + (cs.row0 + rg) * ld + n0 + cq * 4;
 #pragma unroll
-  for (int rr = 0; rr < 32; ++rr)
-    if (rr < cs.nv) p[rr * ld] = fmaf(ptx::lds_f32(stg + (rr * STG_PITCH + lane) * 4) + bias_v, gamma_v, rv[rr]);
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * i + rg;
+    const float4 a = ptx::lds_v4(stg + row * 128 + ((cq ^ (row & 7)) << 4));
+    float4 o;
+    o.x = fmaf(a.x + b4.x, g4.x, rv[i].x);
+    o.y = fmaf(a.y + b4.y, g4.y, rv[i].y);
+    o.z = fmaf(a.z + b4.z, g4.z, rv[i].z);
+    o.w = fmaf(a.w + b4.w, g4.w, rv[i].w);
+    if (row < cs.nv) *reinterpret_cast<float4*>(p + 4 * i * ld) = o;
+  }
 }
 
 // EPI selects the epilogue form at compile time so that each instantiation carries only its own
@@ -532,7 +546,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         cs.wp = 16;
         cs.b = cs.y = cs.x = 0;
       }
-      const uint32_t stg = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + grp * COLS_PER_GRP;
       if (!active) {
         ptx::mbar_wait(&tfull[acc], acc_ph);
@@ -545,32 +558,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // The residual values of TWO chunks are in flight ahead of the one being processed; the first
         // two are requested before the accumulator is even ready.
         const float* resp = reinterpret_cast<const float*>(op.res);
-        float resv[32], resn[32];
-        prefetch_res32(resp, op.ldres, cs, col0 + lane, resv);
-        if (COLS_PER_GRP > 32) prefetch_res32(resp, op.ldres, cs, col0 + 32 + lane, resn);
+        const uint32_t tile = stg_all + (warp - EPI_WARP0) * 4096;
+        float4 resv[8], resn[8];
+        prefetch_res4(resp, op.ldres, cs, col0, lane, resv);
+        if (COLS_PER_GRP > 32) prefetch_res4(resp, op.ldres, cs, col0 + 32, lane, resn);
         ptx::mbar_wait(&tfull[acc], acc_ph);
         ptx::tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < COLS_PER_GRP; c += 32) {
           uint32_t r[32];
           ptx::tmem_ld32(t_acc + c, r);
-          float resn2[32];
-          if (c + 64 < COLS_PER_GRP) prefetch_res32(resp, op.ldres, cs, col0 + c + 64 + lane, resn2);
+          float4 resn2[8];
+          if (c + 64 < COLS_PER_GRP) prefetch_res4(resp, op.ldres, cs, col0 + c + 64, lane, resn2);
           ptx::tmem_ld_wait();
           if (c + 32 >= COLS_PER_GRP) {  // accumulator is out of TMEM: release it, stores overlap the next tile
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[acc]);
           }
-          const int n = col0 + c + lane;
+          const int nq = col0 + c + (lane & 7) * 4;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) ptx::sts_f32(stg + (lane * STG_PITCH + j) * 4, __uint_as_float(r[j]));
+          for (int j = 0; j < 8; ++j)
+            ptx::sts_v4(tile + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           __syncwarp();
-          const float bias_v = gp.bias ? gp.bias[n] : 0.f;
-          const float gamma_v = gp.gamma ? gp.gamma[n] : 1.f;
-          epi_cols_resid32(reinterpret_cast<float*>(op.out), op.ldo, cs, n, stg, lane, bias_v, gamma_v, resv);
+          const float4 b4 = gp.bias ? *reinterpret_cast<const float4*>(gp.bias + nq) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 g4 = gp.gamma ? *reinterpret_cast<const float4*>(gp.gamma + nq) : make_float4(1.f, 1.f, 1.f, 1.f);
+          epi_rows4_resid32(reinterpret_cast<float*>(op.out), op.ldo, cs, col0 + c, tile, lane, b4, g4, resv);
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) resv[j] = resn[j], resn[j] = resn2[j];
+          for (int j = 0; j < 8; ++j) resv[j] = resn[j], resn[j] = resn2[j];
         }
       } else {
         // ---- row-per-thread math; output through a swizzled smem slab + TMA store (g.tma_out) or direct
