@@ -30,19 +30,24 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-// smem: 4 x 48 KB ring for the 128x256 tile + 33 KB epilogue staging = 226 KB of the 227 KB limit
-template <int BN>
+// smem ring: as many k-block stages as fit beside the 32 KB epilogue staging (at most 8).  A CTA pair
+// (CL = 2, tcgen05 cta_group::2) keeps only HALF of the weight tile per CTA: 32 KB stages, 6 deep at
+// BN = 256 instead of 4 x 48 KB -- the ring covers 2560 tensor-core cycles of load latency, not 1536.
+template <int BN, int CL>
 struct Cfg {
-  static constexpr int STAGES = 4;
+  static constexpr int B_ROWS = BN / CL;                      // weight rows held by one CTA
+  static constexpr int STAGE = 128 * 64 * 2 + B_ROWS * 64 * 2;
+  static constexpr int FIT = (232448 - 1024 - 256 - 8 * 4096) / STAGE;
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
 };
 constexpr int STG_WARP_BYTES = 4096;                         // one swizzled 32x32 fp32 chunk / TMA slab per epilogue warp
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 256;
 constexpr int TILE_W = 16, TILE_H = 8;  // conv: 128 rows = 8 x 16 output pixels
 
-// m-tiles are scheduled in UNITS of CL tiles (CL = cluster size: the CTAs of a cluster run CL
-// adjacent m-tiles of the same n-tile in lockstep and share the weight tile by TMA multicast).
+// m-tiles are scheduled in UNITS of CL tiles.  CL = 2 is a CTA pair on one TPC: the two CTAs hold two
+// adjacent m-tiles and one half of the weight tile each, and the leader CTA issues ONE
+// tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs' shared memory and writes both CTAs' TMEM.
 // A unit never straddles a group: every group is padded to a whole number of units.
 struct TileGeom {
   int m_units, n_tiles, k_blocks;
@@ -347,12 +352,13 @@ template <int BN, int CL, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ WeightMaps tmW,
                const GemmOp op, const TileGeom g) {
-  constexpr int STAGES = Cfg<BN>::STAGES;
+  constexpr int STAGES = Cfg<BN, CL>::STAGES;
+  constexpr bool PAIR = CL == 2;
   constexpr uint32_t A_BYTES = BM * BK * 2;
-  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t B_BYTES = (BN / CL) * BK * 2;  // per CTA
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM, BN);
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM * CL, BN);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
@@ -371,7 +377,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int total_units = g.m_units * g.n_tiles;
   const int crank = CL > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;  // cluster index / number of clusters
-  constexpr uint16_t MC_MASK = (1u << CL) - 1;
+  // pair mode: the smem-full and accumulator-empty barriers that gate the MMA live in the leader CTA
+  const uint32_t tempty_leader = PAIR ? ptx::mapa_u32(&tempty[0], 0) : ptx::smem_u32(&tempty[0]);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -380,18 +387,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], CL);  // every CTA of the cluster must release a stage
+      ptx::mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], EPI_THREADS);
+      ptx::mbar_init(&tempty[a], 8 * CL);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   if (CL > 1) ptx::cluster_sync_all();  // peers' barriers must be initialised before any remote arrive
@@ -431,18 +443,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < g.k_blocks; ++kb) {
           ptx::mbar_wait(&empty[s], ph ^ 1);
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
-            if (op.a_mode == A_CONV3X3) {
-              const int ky = tap / 3, kx = tap - ky * 3;
-              ptx::tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b);
+            if constexpr (PAIR) {
+              // both CTAs' bytes complete on the leader's barrier; the leader arms it for the pair
+              const uint32_t fbar = ptx::mapa_u32(&full[s], 0);
+              if (crank == 0) ptx::mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+              if (op.a_mode == A_CONV3X3) {
+                const int ky = tap / 3, kx = tap - ky * 3;
+                ptx::tma_load_4d_pair(sA + s * A_BYTES, &tmA, fbar, c0, x0 + kx - 1, y0 + ky - 1, b);
+              } else {
+                ptx::tma_load_2d_pair(sA + s * A_BYTES, &tmA, fbar, kb * BK, a_row);
+              }
+              ptx::tma_load_2d_pair(sB + s * B_BYTES, tmB, fbar, kb * BK, nt * BN + crank * (BN / 2));
             } else {
-              ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, a_row);
-            }
-            if (CL > 1) {
-              // this CTA fetches 1/CL of the weight tile and multicasts it to the whole cluster
-              ptx::tma_load_2d_mc(sB + s * B_BYTES + crank * (B_BYTES / CL), tmB, &full[s], kb * BK,
-                                  nt * BN + crank * (BN / CL), MC_MASK);
-            } else {
+              ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
+              if (op.a_mode == A_CONV3X3) {
+                const int ky = tap / 3, kx = tap - ky * 3;
+                ptx::tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b);
+              } else {
+                ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, a_row);
+              }
               ptx::tma_load_2d(sB + s * B_BYTES, tmB, &full[s], kb * BK, nt * BN);
             }
           }
@@ -453,8 +472,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && crank == 0) {
+    // ------------------------------------------------------------ MMA issuer (pair: the leader CTA only)
     // Warp-converged loop, one elected lane issues.  With the loop under `if (lane == 0)` every
     // tcgen05.mma was wrapped in an elect / vote / R2UR sequence and the descriptor arithmetic ran on
     // the (slow, serial) uniform datapath: ~90 dependent instructions per k-block, as long as the
@@ -483,11 +502,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t da = (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + 2 * k);  // +32 B per K=16 step
               const uint64_t db = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + 2 * k);
-              ptx::umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0);
+              if (PAIR) ptx::umma_bf16_pair(d_tmem, da, db, IDESC, (kb | k) != 0);
+              else ptx::umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0);
             }
-            if (CL > 1) ptx::umma_commit_mc(&empty[s], MC_MASK);  // the peers' producers write into this stage too
-            else ptx::umma_commit(&empty[s]);
-            if (kb == g.k_blocks - 1) ptx::umma_commit(&tfull[acc]);
+            if (PAIR) {  // release the stage / publish the accumulator in both CTAs
+              ptx::umma_commit_pair(&empty[s]);
+              if (kb == g.k_blocks - 1) ptx::umma_commit_pair(&tfull[acc]);
+            } else {
+              ptx::umma_commit(&empty[s]);
+              if (kb == g.k_blocks - 1) ptx::umma_commit(&tfull[acc]);
+            }
           }
           __syncwarp();
           if (++s == STAGES) s = 0, ph ^= 1;
@@ -550,7 +574,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!active) {
         ptx::mbar_wait(&tfull[acc], acc_ph);
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&tempty[acc]);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
         continue;
       }
       if constexpr (EPI == EPI_RES32) {
@@ -573,7 +598,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tmem_ld_wait();
           if (c + 32 >= COLS_PER_GRP) {  // accumulator is out of TMEM: release it, stores overlap the next tile
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&tempty[acc]);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
           }
           const int nq = col0 + c + (lane & 7) * 4;
 #pragma unroll
@@ -607,7 +633,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tmem_ld_wait();
           if (!more) {
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&tempty[acc]);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
           }
           float v[32];
 #pragma unroll
@@ -691,11 +718,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp >= EPI_WARP0 && lane == 0) ptx::tma_store_wait_read();  // smem must outlive the bulk stores
   __syncwarp();
   ptx::tc_fence_before();
-  if (CL > 1) ptx::cluster_sync_all();  // no CTA may exit while a peer can still multicast into it
+  if (CL > 1) ptx::cluster_sync_all();  // no CTA may exit while the pair's MMA can still read its smem / write its TMEM
   else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -775,8 +803,8 @@ int num_sms() {
 template <int BN, int CL, int EPI>
 void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const WeightMaps& tmW,
             cudaStream_t stream) {
-  constexpr int STAGES = Cfg<BN>::STAGES;
-  constexpr size_t SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + 8 * STG_WARP_BYTES;
+  constexpr int STAGES = Cfg<BN, CL>::STAGES;
+  constexpr size_t SMEM = STAGES * Cfg<BN, CL>::STAGE + 1024 /*align*/ + 256 /*barriers*/ + 8 * STG_WARP_BYTES;
   static bool configured = false;
   if (!configured) {
     DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
