@@ -294,6 +294,46 @@ __device__ __forceinline__ void load_res(const GemmOp& op, long long m, int n0, 
   else load32<bf16>(reinterpret_cast<const bf16*>(op.res) + roff, r);
 }
 
+// EPI_TMA chunk: 32 columns of this thread's row (bias already added) -> activation / LayerScale /
+// residuals -> bf16 into the warp's swizzled slab.  The bf16 residual was requested one chunk ahead.
+__device__ __forceinline__ void epi_tma_chunk(const GemmOp& op, const GemmGroup& gp, long long m, int n0, float (&v)[32],
+                                              const uint4 (&resraw)[4], bool has_res, uint32_t slab_row, int half,
+                                              int swz) {
+  if (op.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (op.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
+  }
+  float t[32];
+  if (gp.gamma) {
+    load32<float>(gp.gamma + n0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= t[j];
+  }
+  if (has_res) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resraw[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        v[8 * i + 2 * j] += f.x, v[8 * i + 2 * j + 1] += f.y;
+      }
+    }
+  }
+  if (op.res2) {
+    load32<bf16>(reinterpret_cast<const bf16*>(op.res2) + m * op.ldres + n0, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += t[j];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    ptx::sts_u4(slab_row + (((half * 4 + i) ^ swz) << 4), pack2(v[8 * i], v[8 * i + 1]), pack2(v[8 * i + 2], v[8 * i + 3]),
+                pack2(v[8 * i + 4], v[8 * i + 5]), pack2(v[8 * i + 6], v[8 * i + 7]));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Column-per-lane epilogue for row-major outputs.  A warp's 32x32 fp32 accumulator chunk (thread =
 // row, straight from tcgen05.ld) is transposed through a per-warp shared-memory buffer; afterwards
@@ -614,8 +654,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) resv[j] = resn[j], resn[j] = resn2[j];
         }
+      } else if constexpr (EPI == EPI_TMA) {
+        // ---- row-per-thread math, bf16 output through a swizzled smem slab + TMA store.  Software
+        // pipelined: as soon as chunk c has been copied out of the TMEM-load registers (bias add), the
+        // TMEM load, bias and residual of chunk c+1 are issued and fly during the math of chunk c.
+        static_assert(COLS_PER_GRP % 64 == 0, "EPI_TMA works on 64-column slabs");
+        const uint32_t slab = stg_all + (warp - EPI_WARP0) * 4096;
+        const bool has_res = op.res != nullptr && valid;
+        const bf16* resp = reinterpret_cast<const bf16*>(op.res) + m * op.ldres + col0;
+        uint32_t r[32];
+        float bias[32];
+        uint4 resc[4], resn[4];
+        auto prefetch = [&](int c) {  // bias + residual of the chunk at column offset c
+          if (gp.bias) load32<float>(gp.bias + (op.bias_mod ? (col0 + c) % op.bias_mod : col0 + c), bias);
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) resn[i] = reinterpret_cast<const uint4*>(resp + c)[i];
+          }
+        };
+        prefetch(0);  // in flight while the MMA of this tile finishes
+        ptx::mbar_wait(&tfull[acc], acc_ph);
+        ptx::tc_fence_after();
+        ptx::tmem_ld32(t_acc, r);
+#pragma unroll 1
+        for (int c = 0; c < COLS_PER_GRP; c += 64) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int cc = c + half * 32;
+            const bool more = cc + 32 < COLS_PER_GRP;
+            float v[32];
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (gp.bias ? bias[j] : 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) resc[i] = resn[i];
+            if (more) {
+              ptx::tmem_ld32(t_acc + cc + 32, r);
+              prefetch(cc + 32);
+            } else {  // accumulator is out of TMEM: release it, the rest overlaps the next tile's MMA
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
+            }
+            if (half == 0) {
+              if (lane == 0) ptx::tma_store_wait_read();  // the previous slab store has drained the buffer
+              __syncwarp();
+            }
+            epi_tma_chunk(op, gp, m, col0 + cc, v, resc, has_res, slab + lane * 128, half, lane & 7);
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && cs.nv > 0) {
+            const int ccol = op.col_off + col0 + c;
+            if (op.a_mode == A_CONV3X3) ptx::tma_store_4d(&tmW.o[0], slab, ccol, cs.x, cs.y, cs.b);
+            else ptx::tma_store_2d(&tmW.o[gi], slab, ccol, static_cast<int>(cs.row0));
+            ptx::tma_store_commit();
+          }
+        }
       } else {
-        // ---- row-per-thread math; output through a swizzled smem slab + TMA store (g.tma_out) or direct
+        // ---- EPI_MISC: row-per-thread math; output through a swizzled smem slab + TMA store (g.tma_out) or direct
         const uint32_t slab = stg_all + (warp - EPI_WARP0) * 4096;
         const bool has_res = op.res != nullptr && valid;
         float resv[32];
@@ -639,29 +736,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (EPI == EPI_TMA || g.tma_out) {
+          if (g.tma_out) {
             const int half = (c >> 5) & 1;
             if (half == 0) {
               if (lane == 0) ptx::tma_store_wait_read();  // the previous slab store has drained the buffer
               __syncwarp();
             }
-            if constexpr (EPI == EPI_TMA) {
-              epilogue_chunk(op, gp, m, col0 + c, v, resv, slab + lane * 128, half, lane & 7);
-            } else {
-              epilogue_chunk(op, gp, m, col0 + c, v, resv, slab + lane * 128, half, lane & 7,
-                             op.out_relu ? (half ? keep1 : keep0) : nullptr);
-            }
+            epilogue_chunk(op, gp, m, col0 + c, v, resv, slab + lane * 128, half, lane & 7,
+                           op.out_relu ? (half ? keep1 : keep0) : nullptr);
             if (half == 1) {
               ptx::fence_proxy_async();
               __syncwarp();
               const int ccol = op.col_off + col0 + c - 32;
-              if constexpr (EPI == EPI_TMA) {
-                if (lane == 0 && cs.nv > 0) {
-                  if (op.a_mode == A_CONV3X3) ptx::tma_store_4d(&tmW.o[0], slab, ccol, cs.x, cs.y, cs.b);
-                  else ptx::tma_store_2d(&tmW.o[gi], slab, ccol, static_cast<int>(cs.row0));
-                  ptx::tma_store_commit();
-                }
-              } else {
+              {
                 // ConvT: n-chunk -> (parity, channel); the slab is 32 consecutive input pixels of one row
                 int cq = 0, cx = 0, cby = 0, cco = ccol;
                 if (op.out_mode == O_CONVT2X2) {
@@ -946,7 +1033,7 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   const bool resid32 = op.out_mode == O_ROWMAJOR && op.res != nullptr && op.res_f32 && op.out_f32 && op.res2 == nullptr &&
                        op.out_relu == nullptr && op.act == ACT_NONE && op.a_mode == A_ROWMAJOR && op.res == op.out &&
                        op.ldres == op.ldo && op.col_off == 0 && bn >= 128;
-  const bool plain_tma = g.tma_out && op.out_mode == O_ROWMAJOR && op.out_relu == nullptr;
+  const bool plain_tma = g.tma_out && op.out_mode == O_ROWMAJOR && op.out_relu == nullptr && !(op.res && op.res_f32);
   const int epi = resid32 ? EPI_RES32 : (plain_tma ? EPI_TMA : EPI_MISC);
 #define DP_LAUNCH(BN_, CL_)                                                          \
   do {                                                                               \
