@@ -627,32 +627,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float4 resv[8], resn[8];
         prefetch_res4(resp, op.ldres, cs, col0, lane, resv);
         if (COLS_PER_GRP > 32) prefetch_res4(resp, op.ldres, cs, col0 + 32, lane, resn);
+        auto ld_bg = [&](int c, float4& b4, float4& g4) {
+          const int nq = col0 + c + (lane & 7) * 4;
+          b4 = gp.bias ? *reinterpret_cast<const float4*>(gp.bias + nq) : make_float4(0.f, 0.f, 0.f, 0.f);
+          g4 = gp.gamma ? *reinterpret_cast<const float4*>(gp.gamma + nq) : make_float4(1.f, 1.f, 1.f, 1.f);
+        };
+        float4 b4, g4, b4n, g4n;
+        ld_bg(0, b4, g4);
         ptx::mbar_wait(&tfull[acc], acc_ph);
         ptx::tc_fence_after();
+        uint32_t r[32];
+        ptx::tmem_ld32(t_acc, r);
 #pragma unroll 1
         for (int c = 0; c < COLS_PER_GRP; c += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld32(t_acc + c, r);
           float4 resn2[8];
           if (c + 64 < COLS_PER_GRP) prefetch_res4(resp, op.ldres, cs, col0 + c + 64, lane, resn2);
+          if (c + 32 < COLS_PER_GRP) ld_bg(c + 32, b4n, g4n);
           ptx::tmem_ld_wait();
-          if (c + 32 >= COLS_PER_GRP) {  // accumulator is out of TMEM: release it, stores overlap the next tile
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
-          }
-          const int nq = col0 + c + (lane & 7) * 4;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             ptx::sts_v4(tile + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          if (c + 32 < COLS_PER_GRP) {
+            ptx::tmem_ld32(t_acc + c + 32, r);  // next chunk flies during this chunk's read-modify-write
+          } else {  // accumulator is out of TMEM: release it, stores overlap the next tile
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
+          }
           __syncwarp();
-          const float4 b4 = gp.bias ? *reinterpret_cast<const float4*>(gp.bias + nq) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 g4 = gp.gamma ? *reinterpret_cast<const float4*>(gp.gamma + nq) : make_float4(1.f, 1.f, 1.f, 1.f);
           epi_rows4_resid32(reinterpret_cast<float*>(op.out), op.ldo, cs, col0 + c, tile, lane, b4, g4, resv);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j) resv[j] = resn[j], resn[j] = resn2[j];
+          b4 = b4n, g4 = g4n;
         }
       } else if constexpr (EPI == EPI_TMA) {
         // ---- row-per-thread math, bf16 output through a swizzled smem slab + TMA store.  Software

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 300 python scripts/kernel_bench.py "attention 37 seq" proj+res > gpurun_out/plain_kb.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc_kernel -s 3 -c 1 -o gpurun_out/prof_attn python scripts/kernel_bench.py "attention 37 seq" > gpurun_out/ncu_kb.log 2>&1; echo "ncu exit $?"
+cat gpurun_out/plain_kb.log | head -3
+tail -3 gpurun_out/ncu_kb.log
