@@ -4,25 +4,27 @@
 // F.scaled_dot_product_attention, wired at src/depth_pro/network/vit_factory.py:97-110).
 // qkv is (nseq*577, 3072) bf16 with columns [q | k | v], each 16 heads x 64; out is (nseq*577, 1024).
 //
-// One persistent CTA per SM loops over work items (sequence, head, PAIR of 128-row query tiles); the
-// two query tiles of an item are two independent streams A / B that share every K / V block.  Keys
-// are processed in 5 blocks of 128 (640 >= 577, the tail is masked).  Warp roles:
-//   warp 0      TMA producer : Q tiles (once per item) and K/V blocks (3-deep ring), 128B swizzle.
-//   warp 1      MMA issuer   : per stream S = Q K^T (tcgen05.mma M128 N128 K16 x4, A/B K-major) and
-//                              O_j = P V (M128 N64 K16 x8, A = P K-major from smem, B = V MN-major
-//                              straight from the TMA tile); S_A, S_B, O_A[2], O_B[2] fill the 512 TMEM
-//                              columns.
-//   warp 2      TMEM allocator
-//   warps 4-7   softmax of stream A, warps 8-11 softmax of stream B: one thread per query row:
-//                              tcgen05.ld the 128 scores, online softmax in fp32 (exp2, log2e folded into
-//                              the scale), P as bf16 into the swizzled smem tile the next MMA reads, O_j
-//                              folded from TMEM into registers with the running-max correction, final
-//                              1/l and bf16 store.  The two groups are NOT synchronised with each other,
-//                              so on every SM sub-partition one warp's TMEM loads overlap the other's
-//                              MUFU exp2 work (a single group serialises LDTM -> MUFU -> STS per block
-//                              and leaves the tensor pipe idle 80% of the time).
-// Register budget: 384 threads x 168 would not hold 128 scores + 64 outputs per softmax thread, so
-// the control warps drop to 40 registers and the softmax warps grow to 232 (setmaxnreg).
+// One persistent CTA per SM runs TWO INDEPENDENT STREAMS.  A stream owns whole (sequence, head) units
+// -- 5 query tiles of 128 rows x 5 key blocks of 128 (the 65-key tail runs at N = K = 80 and is masked)
+// -- and has its own warps, shared-memory rings, TMEM columns and mbarriers, so the streams drift out of
+// phase and one stream's MUFU exp2 work overlaps the other's TMEM loads, maxima and barrier waits:
+//   warp 0 / 2     TMA producer : Q tile, K ring (2 deep) and V ring (2 deep), 128B swizzle.  K and V
+//                                 have separate barriers: a K stage is recycled as soon as its Q K^T has
+//                                 retired, two key blocks before it is needed again.
+//   warp 1 / 3     MMA issuer   : S = Q K^T (tcgen05.mma M128 N128 K16 x4) and O += P V (M128 N64 K16 x8,
+//                                 A = P K-major from smem, B = V MN-major straight from the TMA tile).  O
+//                                 ACCUMULATES IN TMEM over the 5 key blocks of a query tile.
+//   warps 4-7 / 8-11  softmax   : one thread per query row: tcgen05.ld the 128 scores, row maximum, exp2
+//                                 (log2e folded into the scale), P as bf16 into the swizzled smem tile the
+//                                 P V MMA reads.  The running maximum is LAZY: O (in TMEM) and l are only
+//                                 rescaled when some row's maximum grew by more than 2^8 -- otherwise the
+//                                 old reference maximum stays in use (P <= 256, exact after the final 1/l);
+//                                 a rescale is a TMEM load / multiply / store of the warp's 32 x 64 slice.
+//                                 After the last block: O from TMEM, 1/l, bf16 store.
+// 296 stream slots x 2 units = 592 = 37 sequences x 16 heads: a frame's attention is perfectly balanced.
+// Register budget: the control warps drop to 40 registers, the softmax warps grow to 232 (setmaxnreg).
+#include <type_traits>
+
 #include "attention.cuh"
 #include "ptx.cuh"
 
@@ -30,15 +32,16 @@ namespace dp {
 namespace {
 
 constexpr int SEQ = 577, HD = 64, NH = 16, LDQ = 3 * NH * HD, LDO = NH * HD;
-constexpr int QT = 128;                         // query rows per stream
+constexpr int QT = 128;                         // query rows per tile
 constexpr int KB = 128;                         // keys per block
 constexpr int NB = (SEQ + KB - 1) / KB;         // 5 key blocks
 constexpr int NQT = (SEQ + QT - 1) / QT;        // 5 query tiles
-constexpr int NPAIR = (NQT + 1) / 2;            // 3 items per (sequence, head): tiles (0,1) (2,3) (4,-)
-constexpr int KV_STAGES = 3;
+constexpr int RING = 2;                         // K ring depth = V ring depth
 constexpr int THREADS = 384;
 constexpr uint32_t TILE_BYTES = 128 * 128;      // 128 rows x 64 bf16 = 16 KB
-constexpr uint32_t SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES + 4) + 1024 + 256;
+constexpr int STREAM_TILES = 1 + 2 * RING + 2;  // Q, K ring, V ring, P (two 64-key halves)
+constexpr uint32_t SMEM_BYTES = 2 * STREAM_TILES * TILE_BYTES + 1024 + 256;
+constexpr int NBAR = 7 + 4 * RING;              // mbarriers per stream
 
 // idesc: D=f32, A=B=bf16, A K-major; B K-major (QK^T) or MN-major (PV: bit 16)
 constexpr uint32_t IDESC_QK = ptx::umma_idesc_bf16(128, 128);
@@ -49,6 +52,7 @@ constexpr int LAST_N = (LAST_KEYS + 15) / 16 * 16;            // 80
 constexpr uint32_t IDESC_QK_LAST = ptx::umma_idesc_bf16(128, LAST_N);
 // smem descriptor high word: SBO = 1024 B, version 1, SWIZZLE_128B (same for K-major and MN-major tiles)
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr float RESCALE_LOG2 = 8.0f;            // lazy maximum: tolerate P up to 2^8
 
 __device__ __forceinline__ uint64_t desc(uint32_t lo) { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
@@ -67,34 +71,43 @@ __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int nseq) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                               // 2 tiles (stream A, B)
-  uint8_t* sK = sQ + 2 * TILE_BYTES;                // KV_STAGES tiles
-  uint8_t* sV = sK + KV_STAGES * TILE_BYTES;        // KV_STAGES tiles
-  uint8_t* sP = sV + KV_STAGES * TILE_BYTES;        // 2 streams x 2 k-chunk tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * TILE_BYTES);
-  uint64_t* q_full = bars;                          // 1
-  uint64_t* q_empty = bars + 1;                     // 1
-  uint64_t* kv_full = bars + 2;                     // KV_STAGES
-  uint64_t* kv_empty = kv_full + KV_STAGES;         // KV_STAGES
-  uint64_t* s_full = kv_empty + KV_STAGES;          // per stream
-  uint64_t* s_empty = s_full + 2;                   // per stream, 128 arrivals
-  uint64_t* p_full = s_empty + 2;                   // per stream, 128 arrivals
-  uint64_t* pv_done = p_full + 2;                   // per stream
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = nseq * NH * NPAIR;
+  const int sidx = warp < 4 ? (warp >> 1) : ((warp - 4) >> 2);  // stream of this warp
+  // per-stream shared memory: [Q | K ring | V ring | P lo, P hi]
+  uint8_t* sQ = smem + sidx * STREAM_TILES * TILE_BYTES;
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + RING * TILE_BYTES;
+  uint8_t* sP = sV + RING * TILE_BYTES;
+  uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem + 2 * STREAM_TILES * TILE_BYTES);
+  uint64_t* bars = bars_all + sidx * NBAR;
+  uint64_t* q_full = bars;                  // 1 (TMA tx)
+  uint64_t* q_empty = bars + 1;             // 1 (commit after the tile's last Q K^T)
+  uint64_t* s_full = bars + 2;              // 1 (commit)
+  uint64_t* s_empty = bars + 3;             // 128 softmax threads
+  uint64_t* p_full = bars + 4;              // 128 softmax threads
+  uint64_t* pv_done = bars + 5;             // 1 (commit)
+  uint64_t* o_empty = bars + 6;             // 128 softmax threads: the tile's O has been read out of TMEM
+  uint64_t* k_full = bars + 7;              // RING
+  uint64_t* k_empty = k_full + RING;        // RING
+  uint64_t* v_full = k_empty + RING;        // RING
+  uint64_t* v_empty = v_full + RING;        // RING
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_all + 2 * NBAR);
+
+  const int n_units = nseq * NH;
+  const int slot = blockIdx.x + sidx * gridDim.x, n_slots = 2 * gridDim.x;
 
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmQKV);
-  if (warp == 1 && lane == 0) {
+  if ((warp == 1 || warp == 3) && lane == 0) {
     ptx::mbar_init(q_full, 1);
     ptx::mbar_init(q_empty, 1);
-    for (int i = 0; i < KV_STAGES; ++i) ptx::mbar_init(&kv_full[i], 1), ptx::mbar_init(&kv_empty[i], 1);
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&s_empty[i], 128);
-      ptx::mbar_init(&p_full[i], 128);
-      ptx::mbar_init(&pv_done[i], 1);
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(s_empty, 128);
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(pv_done, 1);
+    ptx::mbar_init(o_empty, 128);
+    for (int i = 0; i < RING; ++i) {
+      ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1), ptx::mbar_init(&v_empty[i], 1);
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -106,213 +119,211 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S_A [0,128), S_B [128,256), O_A[2] [256,384), O_B[2] [384,512)
+  // TMEM columns of stream s: S at [256 s, 256 s + 128), O at [256 s + 128, 256 s + 192)
+  const uint32_t tmem_base = *tmem_slot + sidx * 256;
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0) {
+    if ((warp & 1) == 0) {
       // ---------------------------------------------------------------- TMA producer
-      for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
-        const int pr = item % NPAIR, h = (item / NPAIR) % NH, seq = item / (NPAIR * NH);
-        const bool hasB = 2 * pr + 1 < NQT;
-        const int row0 = seq * SEQ;
-        ptx::mbar_wait(q_empty, (it & 1) ^ 1);
-        if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(q_full, hasB ? 2 * TILE_BYTES : TILE_BYTES);
-          ptx::tma_load_2d(sQ, &tmQKV, q_full, h * HD, row0 + 2 * pr * QT);
-          if (hasB) ptx::tma_load_2d(sQ + TILE_BYTES, &tmQKV, q_full, h * HD, row0 + (2 * pr + 1) * QT);
-        }
-        __syncwarp();
-        for (int j = 0; j < NB; ++j) {
-          const int gb = it * NB + j, st = gb % KV_STAGES;
-          ptx::mbar_wait(&kv_empty[st], ((gb / KV_STAGES) & 1) ^ 1);
+      int T = 0;  // query tiles this stream has started
+      for (int u = slot; u < n_units; u += n_slots) {
+        const int h = u % NH, row0 = (u / NH) * SEQ;
+        for (int qt = 0; qt < NQT; ++qt, ++T) {
+          ptx::mbar_wait(q_empty, (T & 1) ^ 1);
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-            ptx::tma_load_2d(sK + st * TILE_BYTES, &tmQKV, &kv_full[st], NH * HD + h * HD, row0 + j * KB);
-            ptx::tma_load_2d(sV + st * TILE_BYTES, &tmQKV, &kv_full[st], 2 * NH * HD + h * HD, row0 + j * KB);
+            ptx::mbar_expect_tx(q_full, TILE_BYTES);
+            ptx::tma_load_2d(sQ, &tmQKV, q_full, h * HD, row0 + qt * QT);
           }
           __syncwarp();
+          for (int j = 0; j < NB; ++j) {
+            const int G = T * NB + j, st = G % RING;
+            const uint32_t ph = ((G / RING) & 1) ^ 1;
+            ptx::mbar_wait(&k_empty[st], ph);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
+              ptx::tma_load_2d(sK + st * TILE_BYTES, &tmQKV, &k_full[st], NH * HD + h * HD, row0 + j * KB);
+            }
+            __syncwarp();
+            ptx::mbar_wait(&v_empty[st], ph);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
+              ptx::tma_load_2d(sV + st * TILE_BYTES, &tmQKV, &v_full[st], 2 * NH * HD + h * HD, row0 + j * KB);
+            }
+            __syncwarp();
+          }
         }
       }
-    } else if (warp == 1) {
+    } else {
       // ---------------------------------------------------------------- MMA issuer
-      // all tiles sit at compile-time offsets from the (1024-B aligned) smem base: one live register
       const uint32_t q_lo = desc_lo(ptx::smem_u32(sQ));
-      const uint32_t k_lo = q_lo + (2 * TILE_BYTES >> 4);
-      const uint32_t v_lo = k_lo + (KV_STAGES * TILE_BYTES >> 4);
-      const uint32_t p_lo = v_lo + (KV_STAGES * TILE_BYTES >> 4);
-      int nB = 0;  // items so far in which stream B was active (its barrier phases advance only then)
-      for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
-        const bool hasB = 2 * (item % NPAIR) + 1 < NQT;
-        ptx::mbar_wait(q_full, it & 1);
-        // P V of key block jj for both streams, then release that K/V stage
-        auto issue_pv = [&](int jj) {
-          const int st = (it * NB + jj) % KV_STAGES;
-          for (int sidx = 0; sidx < (hasB ? 2 : 1); ++sidx) {
-            const int gbs = (sidx == 0 ? it : nB) * NB + jj;
-            ptx::mbar_wait(&p_full[sidx], gbs & 1);
+      const uint32_t k_lo = q_lo + (TILE_BYTES >> 4);
+      const uint32_t v_lo = k_lo + (RING * TILE_BYTES >> 4);
+      const uint32_t p_lo = v_lo + (RING * TILE_BYTES >> 4);
+      const uint32_t tS = tmem_base, tO = tmem_base + 128;
+      int T = 0;
+      for (int u = slot; u < n_units; u += n_slots) {
+        for (int qt = 0; qt < NQT; ++qt, ++T) {
+          // O += P V of key block jj, then release that V stage
+          auto issue_pv = [&](int jj) {
+            const int G = T * NB + jj, st = G % RING;
+            ptx::mbar_wait(&v_full[st], (G / RING) & 1);
+            if (jj == 0) ptx::mbar_wait(o_empty, (T & 1) ^ 1);  // the previous tile's O has been read out
+            ptx::mbar_wait(p_full, G & 1);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-              const uint32_t d = tmem_base + 256 + sidx * 128 + (jj & 1) * 64;
               const int nks = jj == NB - 1 ? LAST_N / 16 : KB / 16;
 #pragma unroll
               for (int ks = 0; ks < KB / 16; ++ks) {
                 if (ks >= nks) break;
-                // A = P: k-chunk tile (ks >> 2), +32 B per K=16 step; B = V (MN-major): +16 keys = 2048 B
-                const uint64_t da = desc(p_lo + sidx * (2 * TILE_BYTES >> 4) + (ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2);
+                // A = P: 64-key half (ks >> 2), +32 B per K=16 step; B = V (MN-major): +16 keys = 2048 B
+                const uint64_t da = desc(p_lo + (ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2);
                 const uint64_t db = desc(v_lo + st * (TILE_BYTES >> 4) + ks * (2048 >> 4));
-                ptx::umma_bf16(d, da, db, IDESC_PV, ks != 0);
+                ptx::umma_bf16(tO, da, db, IDESC_PV, (jj | ks) != 0);
               }
-              ptx::umma_commit(&pv_done[sidx]);
+              ptx::umma_commit(pv_done);
+              ptx::umma_commit(&v_empty[st]);
             }
             __syncwarp();
-          }
-          if (ptx::elect_one()) ptx::umma_commit(&kv_empty[st]);
-          __syncwarp();
-        };
-        for (int j = 0; j < NB; ++j) {
-          const int st = (it * NB + j) % KV_STAGES;
-          ptx::mbar_wait(&kv_full[st], ((it * NB + j) / KV_STAGES) & 1);
-          for (int sidx = 0; sidx < (hasB ? 2 : 1); ++sidx) {
-            const int gbs = (sidx == 0 ? it : nB) * NB + j;
-            ptx::mbar_wait(&s_empty[sidx], (gbs & 1) ^ 1);
+          };
+          ptx::mbar_wait(q_full, T & 1);
+          for (int j = 0; j < NB; ++j) {
+            const int G = T * NB + j, st = G % RING;
+            ptx::mbar_wait(&k_full[st], (G / RING) & 1);
+            ptx::mbar_wait(s_empty, (G & 1) ^ 1);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < HD / 16; ++ks)
-                ptx::umma_bf16(tmem_base + sidx * 128, desc(q_lo + sidx * (TILE_BYTES >> 4) + ks * 2),
-                               desc(k_lo + st * (TILE_BYTES >> 4) + ks * 2), j == NB - 1 ? IDESC_QK_LAST : IDESC_QK,
-                               ks != 0);
-              ptx::umma_commit(&s_full[sidx]);
+                ptx::umma_bf16(tS, desc(q_lo + ks * 2), desc(k_lo + st * (TILE_BYTES >> 4) + ks * 2),
+                               j == NB - 1 ? IDESC_QK_LAST : IDESC_QK, ks != 0);
+              ptx::umma_commit(s_full);
+              ptx::umma_commit(&k_empty[st]);
+              if (j == NB - 1) ptx::umma_commit(q_empty);  // the Q tile is free once its last Q K^T retires
             }
             __syncwarp();
+            if (j > 0) issue_pv(j - 1);
           }
-          if (j == NB - 1) {
-            if (ptx::elect_one()) ptx::umma_commit(q_empty);  // Q tiles are free once the last QK^T retires
-            __syncwarp();
-          }
-          if (j > 0) issue_pv(j - 1);
+          issue_pv(NB - 1);
         }
-        issue_pv(NB - 1);
-        if (hasB) ++nB;
       }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ------------------------------------------------------------------ softmax / accumulate
+    // ------------------------------------------------------------------ softmax
     const int q = warp & 3;             // TMEM lane quadrant
-    const int sidx = (warp - 4) >> 2;   // stream: 0 = A, 1 = B
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tS = tmem_base + sidx * 128, tO = tmem_base + 256 + sidx * 128;
-    uint8_t* prow = sP + sidx * 2 * TILE_BYTES + row * 128;
+    const uint32_t tS = tmem_base + lane_addr, tO = tmem_base + 128 + lane_addr;
+    const uint32_t prow = ptx::smem_u32(sP) + row * 128;
     const float c = 0.125f * 1.4426950408889634f;  // softmax scale * log2(e)
-    int ns = 0;                          // items this stream has processed (barrier phase counter)
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int pr = item % NPAIR, h = (item / NPAIR) % NH, seq = item / (NPAIR * NH);
-      const int qt = 2 * pr + sidx;
-      if (qt >= NQT) continue;           // stream B idles on the odd last tile
-      const int q_row = qt * QT + row;
-      float o[HD];
-#pragma unroll
-      for (int d = 0; d < HD; ++d) o[d] = 0.f;
-      float m_run = -INFINITY, m_acc = -INFINITY, l = 0.f;
+    int T = 0;
+    for (int u = slot; u < n_units; u += n_slots) {
+      const int h = u % NH, seq = u / NH;
+      for (int qt = 0; qt < NQT; ++qt, ++T) {
+        float m_ref = -INFINITY;  // reference maximum the exponentials (and O, l) are relative to
+        float l = 0.f;
 
-      // fold O_jj (computed with P relative to max `mj`) into the register accumulator
-      auto acc_o = [&](int jj, float mj) {
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld32(tO + (jj & 1) * 64 + lane_addr, r0);
-        ptx::tmem_ld32(tO + (jj & 1) * 64 + 32 + lane_addr, r1);
-        ptx::tmem_ld_wait();
-        const float alpha = ex2((m_acc - mj) * c);
-        m_acc = mj;
+        auto block = [&](int j, auto last_tag) {
+          constexpr bool LAST = decltype(last_tag)::value;
+          constexpr int NCH = LAST ? (LAST_N + 31) / 32 : 4;  // 32-column chunks to load
+          constexpr int NKEY = LAST ? LAST_KEYS : KB;         // valid keys in this block
+          constexpr int NG = (LAST ? LAST_N : KB) / 8;        // 8-key groups the P V MMA reads
+          const int G = T * NB + j;
+          ptx::mbar_wait(s_full, G & 1);
+          ptx::tc_fence_after();
+          uint32_t sr[NCH][32];
 #pragma unroll
-        for (int d = 0; d < 32; ++d) {
-          o[d] = fmaf(o[d], alpha, __uint_as_float(r0[d]));
-          o[32 + d] = fmaf(o[32 + d], alpha, __uint_as_float(r1[d]));
-        }
-      };
+          for (int ch = 0; ch < NCH; ++ch) ptx::tmem_ld32(tS + ch * 32, sr[ch]);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(s_empty);  // S is in registers: the next Q K^T may overwrite it
+          // row maximum over the valid keys, four independent chains
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int k = 0; k < NKEY; ++k) mx4[k & 3] = fmaxf(mx4[k & 3], __uint_as_float(sr[k >> 5][k & 31]));
+          const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          // P and O are single-buffered: the previous block's P V must have retired
+          if (j > 0) {
+            ptx::mbar_wait(pv_done, (G - 1) & 1);
+            ptx::tc_fence_after();
+          }
+          if (j == 0) {
+            m_ref = mx;
+          } else if (__any_sync(0xffffffffu, (mx - m_ref) * c > RESCALE_LOG2)) {
+            const float m_new = fmaxf(m_ref, mx);
+            const float alpha = ex2((m_ref - m_new) * c);
+            m_ref = m_new;
+            l *= alpha;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t o[32];
+              ptx::tmem_ld32(tO + hh * 32, o);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int d = 0; d < 32; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+              ptx::tmem_st32(tO + hh * 32, o);
+            }
+            ptx::tmem_st_wait();
+          }
+          const float mc = m_ref * c;
+          float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int g8 = 0; g8 < NG; ++g8) {
+            uint32_t pk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const int k0 = g8 * 8 + 2 * w;
+              float p0 = 0.f, p1 = 0.f;
+              if (k0 < NKEY) p0 = ex2(fmaf(__uint_as_float(sr[k0 >> 5][k0 & 31]), c, -mc));
+              if (k0 + 1 < NKEY) p1 = ex2(fmaf(__uint_as_float(sr[(k0 + 1) >> 5][(k0 + 1) & 31]), c, -mc));
+              if (k0 < NKEY) rs4[w] += p0 + p1;
+              pk[w] = pack_bf16(p0, p1);
+            }
+            // 64-key half (g8 >> 3), 16-byte chunk (g8 & 7) of this row, 128B swizzle
+            ptx::sts_u4(prow + (g8 >> 3) * TILE_BYTES + (((g8 & 7) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+          l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+          ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(p_full);
+        };
+        for (int j = 0; j < NB - 1; ++j) block(j, std::false_type{});
+        block(NB - 1, std::true_type{});
 
-      for (int j = 0; j < NB; ++j) {
-        const int gbs = ns * NB + j;
-        ptx::mbar_wait(&s_full[sidx], gbs & 1);
+        // the tile's O: TMEM -> registers -> 1/l -> bf16
+        ptx::mbar_wait(pv_done, (T * NB + NB - 1) & 1);
         ptx::tc_fence_after();
-        uint32_t sr[4][32];
-        const bool last = j == NB - 1;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-          if (!(last && ch * 32 >= LAST_N)) ptx::tmem_ld32(tS + ch * 32 + lane_addr, sr[ch]);
+        uint32_t o0[32], o1[32];
+        ptx::tmem_ld32(tO, o0);
+        ptx::tmem_ld32(tO + 32, o1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&s_empty[sidx]);  // S is in registers: the next Q K^T may overwrite it
-        const int key0 = j * KB;
-        const float m_prev = m_run;
-        float mx = m_run;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float v = __uint_as_float(sr[ch][e]);
-            if (last && key0 + ch * 32 + e >= SEQ) v = -INFINITY;  // also covers the columns that were not loaded
-            sr[ch][e] = __float_as_uint(v);
-            mx = fmaxf(mx, v);
-          }
-        const float alpha = ex2((m_run - mx) * c);
-        m_run = mx;
-        const float mc = mx * c;
-        // P is single-buffered per stream: the previous block's P V must have consumed it
-        if (j > 0) ptx::mbar_wait(&pv_done[sidx], (gbs - 1) & 1);
-        float rs = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        ptx::mbar_arrive(o_empty);
+        const int q_row = qt * QT + row;
+        if (q_row < SEQ) {
+          const float inv = 1.f / l;
+          uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(seq) * SEQ + q_row) * LDO + h * HD);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int k8 = (ch * 4 + i) * 8;            // first key of this 8-key group inside the block
-            if (last && k8 >= LAST_N) continue;          // beyond the K = 80 the last P V reads
-            uint32_t pk[4] = {0u, 0u, 0u, 0u};
-            if (!(last && k8 >= LAST_KEYS)) {            // fully masked groups are zeros without MUFU work
+            uint4 t;
+            t.x = pack_bf16(__uint_as_float(o0[8 * i]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
+            t.y = pack_bf16(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
+            t.z = pack_bf16(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
+            t.w = pack_bf16(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
+            dst[i] = t;
+          }
 #pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                const float p0 = ex2(fmaf(__uint_as_float(sr[ch][i * 8 + 2 * w]), c, -mc));
-                const float p1 = ex2(fmaf(__uint_as_float(sr[ch][i * 8 + 2 * w + 1]), c, -mc));
-                rs += p0 + p1;
-                pk[w] = pack_bf16(p0, p1);
-              }
-            }
-            const int chunk = (ch & 1) * 4 + i;
-            uint4* dst = reinterpret_cast<uint4*>(prow + (ch >> 1) * TILE_BYTES + ((chunk ^ (row & 7)) << 4));
-            *dst = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int i = 0; i < 4; ++i) {
+            uint4 t;
+            t.x = pack_bf16(__uint_as_float(o1[8 * i]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
+            t.y = pack_bf16(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
+            t.z = pack_bf16(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
+            t.w = pack_bf16(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
+            dst[4 + i] = t;
           }
         }
-        l = fmaf(l, alpha, rs);
-        ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&p_full[sidx]);
-        // O_{j-1} (other TMEM buffer than the P V just enabled) -> registers
-        if (j > 0) {
-          ptx::tc_fence_after();
-          acc_o(j - 1, m_prev);
-        }
       }
-      ptx::mbar_wait(&pv_done[sidx], (ns * NB + NB - 1) & 1);
-      ptx::tc_fence_after();
-      acc_o(NB - 1, m_run);
-      ptx::tc_fence_before();
-      if (q_row < SEQ) {
-        const float inv = 1.f / l;
-        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(seq) * SEQ + q_row) * LDO + h * HD);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4 t;
-          t.x = pack_bf16(o[8 * i] * inv, o[8 * i + 1] * inv);
-          t.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-          t.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-          t.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-          dst[i] = t;
-        }
-      }
-      ++ns;
     }
   }
 
@@ -321,7 +332,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc(*tmem_slot, 512);
   }
 }
 
@@ -341,8 +352,8 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
     configured = true;
   }
   const CUtensorMap& tm = get_tmap_2d_bf16(qkv, LDQ, static_cast<uint64_t>(nseq) * SEQ, LDQ, 64, 128);
-  const int items = nseq * NH * NPAIR;
-  attention_tc_kernel<<<items < sms ? items : sms, THREADS, SMEM_BYTES, s>>>(tm, out, nseq);
+  const int ctas = (nseq * NH + 1) / 2;  // two streams per CTA, one (sequence, head) unit at a time each
+  attention_tc_kernel<<<ctas < sms ? ctas : sms, THREADS, SMEM_BYTES, s>>>(tm, out, nseq);
   DP_LAUNCH_CHECK();
 }
 
