@@ -217,6 +217,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
     const uint32_t tS = tmem_base + lane_addr, tO = tmem_base + 128 + lane_addr;
     const uint32_t prow = ptx::smem_u32(sP) + row * 128;
     const float c = 0.125f * 1.4426950408889634f;  // softmax scale * log2(e)
+    // MUFU ping-pong.  The softmax warps of quadrant q of both streams sit on the same SM sub-partition
+    // and share its MUFU unit.  Left alone the two streams phase-LOCK: when their exp2 phases collide
+    // both slow down, finish together and then also do their TMEM loads / maxima / barrier waits
+    // together, leaving the MUFU idle half of the time (ncu: XU pipe 46 %).  A pair of named barriers
+    // per quadrant makes the exp2 phases alternate strictly, so one stream's exponentials always run
+    // under the other's non-MUFU work.  Only the first min(blocks A, blocks B) blocks take part.
+    auto units_of = [&](int sl) { return sl < n_units ? (n_units - sl + n_slots - 1) / n_slots : 0; };
+    const int u_a = units_of(blockIdx.x), u_b = units_of(blockIdx.x + gridDim.x);
+    const int n_pp = (u_a < u_b ? u_a : u_b) * NQT * NB;   // blocks that ping-pong
+    const int bar_mine = 1 + q + 4 * sidx, bar_peer = 1 + q + 4 * (sidx ^ 1);
     int T = 0;
     for (int u = slot; u < n_units; u += n_slots) {
       const int h = u % NH, seq = u / NH;
@@ -266,6 +276,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             }
             ptx::tmem_st_wait();
           }
+          // my turn on the MUFU: stream A leads, B follows A's block G, A's block G follows B's block G-1
+          if (G < n_pp && (sidx == 1 || G > 0)) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");
           const float mc = m_ref * c;
           float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -284,6 +296,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             ptx::sts_u4(prow + (g8 >> 3) * TILE_BYTES + (((g8 & 7) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
           l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+          if (G < n_pp && (sidx == 0 || G < n_pp - 1)) asm volatile("bar.arrive %0, 64;" ::"r"(bar_peer) : "memory");
           ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
           ptx::tc_fence_before();
           ptx::mbar_arrive(p_full);
