@@ -68,6 +68,11 @@ def build(force: bool = False, verbose: bool = True) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        # an unresolved symbol would only show up as a dlopen failure on the GPU box: check here
+        chk = subprocess.run([sys.executable, "-c", f"import ctypes; ctypes.CDLL({OUT!r})"], capture_output=True, text=True)
+        if chk.returncode != 0:
+            os.remove(OUT)
+            raise RuntimeError(f"{OUT} does not load:\n{chk.stderr[-2000:]}")
         if verbose:
             print(f"[build] linked {OUT}", flush=True)
     return OUT

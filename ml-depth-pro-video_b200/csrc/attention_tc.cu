@@ -68,7 +68,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int nseq) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, int nseq) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -278,6 +278,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
           }
           // my turn on the MUFU: stream A leads, B follows A's block G, A's block G follows B's block G-1
           if (G < n_pp && (sidx == 1 || G > 0)) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");
+          if (j == 0) {  // the previous tile's output store must have drained this warp's P rows
+            if (lane == 0) ptx::tma_store_wait_read();
+            __syncwarp();
+          }
           const float mc = m_ref * c;
           float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -313,33 +317,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(o_empty);
-        const int q_row = qt * QT + row;
-        if (q_row < SEQ) {
-          const float inv = 1.f / l;
-          uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(seq) * SEQ + q_row) * LDO + h * HD);
+        // 1/l, bf16, then out through the (now idle) low P tile: 32 rows x 128 B per warp in the 128B-swizzle
+        // layout, one TMA store per warp.  tmOut is (sequence, token, channel): rows >= 577 are clipped.
+        const float inv = 1.f / l;
+        const uint32_t orow = ptx::smem_u32(sP) + row * 128;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 t;
-            t.x = pack_bf16(__uint_as_float(o0[8 * i]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
-            t.y = pack_bf16(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
-            t.z = pack_bf16(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
-            t.w = pack_bf16(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
-            dst[i] = t;
-          }
+        for (int i = 0; i < 4; ++i)
+          ptx::sts_u4(orow + ((i ^ (row & 7)) << 4),
+                      pack_bf16(__uint_as_float(o0[8 * i]) * inv, __uint_as_float(o0[8 * i + 1]) * inv),
+                      pack_bf16(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv),
+                      pack_bf16(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv),
+                      pack_bf16(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv));
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 t;
-            t.x = pack_bf16(__uint_as_float(o1[8 * i]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
-            t.y = pack_bf16(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
-            t.z = pack_bf16(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
-            t.w = pack_bf16(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
-            dst[4 + i] = t;
-          }
+        for (int i = 0; i < 4; ++i)
+          ptx::sts_u4(orow + (((4 + i) ^ (row & 7)) << 4),
+                      pack_bf16(__uint_as_float(o1[8 * i]) * inv, __uint_as_float(o1[8 * i + 1]) * inv),
+                      pack_bf16(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv),
+                      pack_bf16(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv),
+                      pack_bf16(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv));
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && qt * QT + q * 32 < SEQ) {
+          ptx::tma_store_3d(&tmOut, ptx::smem_u32(sP) + q * 4096, h * HD, qt * QT + q * 32, seq);
+          ptx::tma_store_commit();
         }
       }
     }
   }
 
+  if (warp >= 4 && lane == 0) ptx::tma_store_wait_read();  // smem must outlive the bulk stores
   __syncwarp();
   ptx::tc_fence_before();
   __syncthreads();
@@ -351,6 +357,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 
 }  // namespace
 
+const CUtensorMap& get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                 const uint32_t* box);  // gemm_tc.cu
 const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
                                     uint32_t box_rows);  // gemm_tc.cu
 
@@ -365,8 +373,12 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
     configured = true;
   }
   const CUtensorMap& tm = get_tmap_2d_bf16(qkv, LDQ, static_cast<uint64_t>(nseq) * SEQ, LDQ, 64, 128);
+  const uint64_t od[3] = {(uint64_t)LDO, (uint64_t)SEQ, (uint64_t)nseq};
+  const uint64_t os[2] = {(uint64_t)LDO * 2, (uint64_t)SEQ * LDO * 2};
+  const uint32_t ob[3] = {64, 32, 1};
+  const CUtensorMap& tmo = get_tmap_bf16(out, 3, od, os, ob);
   const int ctas = (nseq * NH + 1) / 2;  // two streams per CTA, one (sequence, head) unit at a time each
-  attention_tc_kernel<<<ctas < sms ? ctas : sms, THREADS, SMEM_BYTES, s>>>(tm, out, nseq);
+  attention_tc_kernel<<<ctas < sms ? ctas : sms, THREADS, SMEM_BYTES, s>>>(tm, tmo, nseq);
   DP_LAUNCH_CHECK();
 }
 

@@ -926,6 +926,12 @@ void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const W
 
 void tmap_cache_clear() { tmap_cache().clear(); }
 
+// cached bf16 tensor map of any rank <= 5 (128B swizzle) for the other translation units
+const CUtensorMap& get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                 const uint32_t* box) {
+  return get_tmap(ptr, rank, dims, strides_bytes, box);
+}
+
 // 2D row-major bf16 matrix (rows x cols, leading dimension ld_elems), 128B-swizzled box.
 const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
                                     uint32_t box_rows) {
