@@ -33,14 +33,14 @@ constexpr int BK = 64;
 // smem ring: as many k-block stages as fit beside the 32 KB epilogue staging (at most 8).  A CTA pair
 // (CL = 2, tcgen05 cta_group::2) keeps only HALF of the weight tile per CTA: 32 KB stages, 6 deep at
 // BN = 256 instead of 4 x 48 KB -- the ring covers 2560 tensor-core cycles of load latency, not 1536.
-template <int BN, int CL>
+template <int BN, int CL, int EPI>
 struct Cfg {
   static constexpr int B_ROWS = BN / CL;                      // weight rows held by one CTA
   static constexpr int STAGE = 128 * 64 * 2 + B_ROWS * 64 * 2;
-  static constexpr int FIT = (232448 - 1024 - 256 - 8 * 4096) / STAGE;
+  static constexpr int STG_WARP = EPI == 3 ? 8192 : 4096;     // EPI_TMA2 stages x and relu(x) side by side
+  static constexpr int FIT = (232448 - 1024 - 256 - 8 * STG_WARP) / STAGE;
   static constexpr int STAGES = FIT > 8 ? 8 : FIT;
 };
-constexpr int STG_WARP_BYTES = 4096;                         // one swizzled 32x32 fp32 chunk / TMA slab per epilogue warp
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int TILE_W = 16, TILE_H = 8;  // conv: 128 rows = 8 x 16 output pixels
@@ -66,8 +66,9 @@ __device__ __forceinline__ int unit_group(const TileGeom& g, int mu) {
   return (mu >= g.unit_start[1] ? 1 : 0) + (mu >= g.unit_start[2] ? 1 : 0);
 }
 
-// GELU (exact-erf form) for the bf16 path: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far
-// below bf16 output rounding) on the MUFU rcp / ex2 units instead of the ~30-instruction erff().
+// GELU (exact-erf form) for the bf16 path: erf by Abramowitz-Stegun 7.1.28,
+//   erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16,  |err| <= 3e-7 (far below bf16 output rounding),
+// one MUFU rcp per element instead of the ~30-instruction erff() (7.1.26 needs rcp AND ex2).
 // The fc1 epilogue is instruction-issue bound (ncu: 87 M warp instructions vs 23 M for the same GEMM
 // without GELU), so two elements are processed per instruction with the packed fp32x2 FMA pipe.
 struct F2 {
@@ -90,38 +91,34 @@ __device__ __forceinline__ F2 mul2(F2 a, F2 b) {
   return r;
 }
 __device__ __forceinline__ F2 splat2(float a) { return pack_f2(a, a); }
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)),  erf(z) = sign(z) (1 - (a1 t + ... + a5 t^5) exp(-z^2)),  t = 1/(1 + p z)
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)),  erf(z) = sign(z) (1 - s^-16),  s = 1 + a1 |z| + ... + a6 |z|^6
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   const F2 x = pack_f2(x0, x1);
   F2 z;
   z.u = x.u & 0x7fffffff7fffffffull;                       // |x|
   z = mul2(z, splat2(0.70710678118654752440f));
-  const F2 d = fma2(z, splat2(0.3275911f), splat2(1.0f));
-  float d0, d1;
-  unpack_f2(d, d0, d1);
-  const F2 t = pack_f2(rcp_approx(d0), rcp_approx(d1));
-  F2 p = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
-  p = fma2(p, t, splat2(1.421413741f));
-  p = fma2(p, t, splat2(-0.284496736f));
-  p = fma2(p, t, splat2(0.254829592f));
-  p = mul2(p, t);
-  const F2 w = mul2(mul2(z, splat2(-1.4426950408889634f)), z);  // -log2(e) z^2
-  float w0, w1;
-  unpack_f2(w, w0, w1);
-  const F2 e = pack_f2(ex2_approx(w0), ex2_approx(w1));
-  F2 u = fma2(p, mul2(e, splat2(-1.0f)), splat2(1.0f));          // 1 - p e  = |erf|
-  u.u |= x.u & 0x8000000080000000ull;                            // copysign(|erf|, x)
-  const F2 g = mul2(mul2(x, splat2(0.5f)), fma2(u, splat2(1.0f), splat2(1.0f)));
+  F2 s = fma2(z, splat2(0.0000430638f), splat2(0.0002765672f));
+  s = fma2(s, z, splat2(0.0001520143f));
+  s = fma2(s, z, splat2(0.0092705272f));
+  s = fma2(s, z, splat2(0.0422820123f));
+  s = fma2(s, z, splat2(0.0705230784f));
+  s = fma2(s, z, splat2(1.0f));
+  float s0, s1;
+  unpack_f2(s, s0, s1);
+  F2 r = pack_f2(rcp_approx(s0), rcp_approx(s1));          // s >= 1: r in (0, 1], r^16 underflows to 0 for large |x|
+  r = mul2(r, r);
+  r = mul2(r, r);
+  r = mul2(r, r);
+  r = mul2(r, r);
+  F2 u = fma2(r, splat2(-1.0f), splat2(1.0f));             // |erf|
+  u.u |= x.u & 0x8000000080000000ull;                      // copysign(|erf|, x)
+  const F2 h = mul2(x, splat2(0.5f));
+  const F2 g = fma2(h, u, h);
   unpack_f2(g, x0, x1);
 }
 
@@ -181,8 +178,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // for these 32 columns, already loaded (and converted) by the caller so that the HBM round trip
 // overlaps the accumulator wait.
 __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup& gp, long long m, int n0,
-                                               float (&v)[32], const float (&resv)[32], uint32_t slab_row = 0,
-                                               int half = 0, int swz = 0, uint32_t* keep = nullptr) {
+                                               float (&v)[32], const float (&resv)[32]) {
   float t[32];
   if (gp.bias) {
     load32<float>(gp.bias + (op.bias_mod ? n0 % op.bias_mod : n0), t);
@@ -206,8 +202,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup
   if (op.out_mode == O_ROWMAJOR) {
     off = m * op.ldo + op.col_off + n0;
   } else if (op.out_mode == O_CONVT2X2) {
-    off = 0;
-    if (!slab_row) {
     const int q = n0 / op.cout, co = n0 - q * op.cout;
     const int x = static_cast<int>(m % op.W);
     const long long by = m / op.W;  // b*H + y
@@ -215,7 +209,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup
     const long long b = by / op.H;
     const long long orow = (b * 2 * op.H + 2 * y + (q >> 1)) * (2LL * op.W) + 2 * x + (q & 1);
     off = orow * op.ldo + op.col_off + co;
-    }
   } else if (op.out_mode == O_PATCH_EMBED) {
     const long long seq = m / 576;
     const int p = static_cast<int>(m - seq * 576);
@@ -267,18 +260,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmOp& op, const GemmGroup
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += t[j];
   }
-  if (slab_row) {
-    // TMA-store epilogue: this thread's 32 columns as bf16 into its 128-byte row of the warp's
-    // 32x64 slab (128B swizzle, as the output tensor map expects); one thread stores the slab later
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t a = pack2(v[8 * i], v[8 * i + 1]), b = pack2(v[8 * i + 2], v[8 * i + 3]);
-      const uint32_t c = pack2(v[8 * i + 4], v[8 * i + 5]), d = pack2(v[8 * i + 6], v[8 * i + 7]);
-      ptx::sts_u4(slab_row + (((half * 4 + i) ^ swz) << 4), a, b, c, d);
-      if (keep) keep[4 * i] = a, keep[4 * i + 1] = b, keep[4 * i + 2] = c, keep[4 * i + 3] = d;
-    }
-    return;
-  }
   if (op.out) {
     if (op.out_f32)
       store32(reinterpret_cast<float*>(op.out) + off, v);
@@ -294,11 +275,17 @@ __device__ __forceinline__ void load_res(const GemmOp& op, long long m, int n0, 
   else load32<bf16>(reinterpret_cast<const bf16*>(op.res) + roff, r);
 }
 
+__device__ __forceinline__ uint32_t relu2(uint32_t packed) {  // max(x, 0) on a bf16 pair
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&packed);
+  x = __hmax2(x, __floats2bfloat162_rn(0.f, 0.f));
+  return *reinterpret_cast<uint32_t*>(&x);
+}
+
 // EPI_TMA chunk: 32 columns of this thread's row (bias already added) -> activation / LayerScale /
 // residuals -> bf16 into the warp's swizzled slab.  The bf16 residual was requested one chunk ahead.
 __device__ __forceinline__ void epi_tma_chunk(const GemmOp& op, const GemmGroup& gp, long long m, int n0, float (&v)[32],
                                               const uint4 (&resraw)[4], bool has_res, uint32_t slab_row, int half,
-                                              int swz) {
+                                              int swz, uint32_t relu_row = 0) {
   if (op.act == ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -329,9 +316,12 @@ __device__ __forceinline__ void epi_tma_chunk(const GemmOp& op, const GemmGroup&
     for (int j = 0; j < 32; ++j) v[j] += t[j];
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    ptx::sts_u4(slab_row + (((half * 4 + i) ^ swz) << 4), pack2(v[8 * i], v[8 * i + 1]), pack2(v[8 * i + 2], v[8 * i + 3]),
-                pack2(v[8 * i + 4], v[8 * i + 5]), pack2(v[8 * i + 6], v[8 * i + 7]));
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t w0 = pack2(v[8 * i], v[8 * i + 1]), w1 = pack2(v[8 * i + 2], v[8 * i + 3]);
+    const uint32_t w2 = pack2(v[8 * i + 4], v[8 * i + 5]), w3 = pack2(v[8 * i + 6], v[8 * i + 7]);
+    ptx::sts_u4(slab_row + (((half * 4 + i) ^ swz) << 4), w0, w1, w2, w3);
+    if (relu_row) ptx::sts_u4(relu_row + (((half * 4 + i) ^ swz) << 4), relu2(w0), relu2(w1), relu2(w2), relu2(w3));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -382,17 +372,21 @@ __device__ __forceinline__ void epi_rows4_resid32(float* __restrict__ out, long 
 
 // EPI selects the epilogue form at compile time so that each instantiation carries only its own
 // code and registers (one monolithic epilogue made every added feature slow the hot GEMMs down):
-//   EPI_TMA   bf16 row-major output, single store: row-per-thread math -> smem slab -> TMA store
+//   EPI_TMA   bf16 output (row-major, NHWC conv tile or ConvT pixel shuffle), single store:
+//             row-per-thread math -> smem slab -> TMA store, software pipelined
+//   EPI_TMA2  same with a second, ReLU'd copy of the output (x feeds the residual add, relu(x) the next
+//             conv's TMA loads): two slabs per warp, one ring stage fewer
 //   EPI_RES32 fp32 residual update in place (proj / fc2): smem transpose, column-per-lane, deep prefetch
 //   EPI_MISC  everything else: ConvT scatter and dual (x, relu(x)) stores via TMA, direct stores for
 //             patch-embed placement, fused dots, small / odd shapes
-enum { EPI_TMA = 0, EPI_RES32 = 1, EPI_MISC = 2 };
+enum { EPI_TMA = 0, EPI_RES32 = 1, EPI_MISC = 2, EPI_TMA2 = 3 };
 
 template <int BN, int CL, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ WeightMaps tmW,
                const GemmOp op, const TileGeom g) {
-  constexpr int STAGES = Cfg<BN, CL>::STAGES;
+  constexpr int STAGES = Cfg<BN, CL, EPI>::STAGES;
+  constexpr int STG_WARP_BYTES = Cfg<BN, CL, EPI>::STG_WARP;
   constexpr bool PAIR = CL == 2;
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = (BN / CL) * BK * 2;  // per CTA
@@ -623,7 +617,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // The residual values of TWO chunks are in flight ahead of the one being processed; the first
         // two are requested before the accumulator is even ready.
         const float* resp = reinterpret_cast<const float*>(op.res);
-        const uint32_t tile = stg_all + (warp - EPI_WARP0) * 4096;
+        const uint32_t tile = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;
         float4 resv[8], resn[8];
         prefetch_res4(resp, op.ldres, cs, col0, lane, resv);
         if (COLS_PER_GRP > 32) prefetch_res4(resp, op.ldres, cs, col0 + 32, lane, resn);
@@ -662,12 +656,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 8; ++j) resv[j] = resn[j], resn[j] = resn2[j];
           b4 = b4n, g4 = g4n;
         }
-      } else if constexpr (EPI == EPI_TMA) {
+      } else if constexpr (EPI == EPI_TMA || EPI == EPI_TMA2) {
         // ---- row-per-thread math, bf16 output through a swizzled smem slab + TMA store.  Software
         // pipelined: as soon as chunk c has been copied out of the TMEM-load registers (bias add), the
         // TMEM load, bias and residual of chunk c+1 are issued and fly during the math of chunk c.
         static_assert(COLS_PER_GRP % 64 == 0, "EPI_TMA works on 64-column slabs");
-        const uint32_t slab = stg_all + (warp - EPI_WARP0) * 4096;
+        const uint32_t slab = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;
+        const uint32_t slab_relu = EPI == EPI_TMA2 ? slab + 4096 : 0;
         const bool has_res = op.res != nullptr && valid;
         const bf16* resp = reinterpret_cast<const bf16*>(op.res) + m * op.ldres + col0;
         uint32_t r[32];
@@ -708,24 +703,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (lane == 0) ptx::tma_store_wait_read();  // the previous slab store has drained the buffer
               __syncwarp();
             }
-            epi_tma_chunk(op, gp, m, col0 + cc, v, resc, has_res, slab + lane * 128, half, lane & 7);
+            epi_tma_chunk(op, gp, m, col0 + cc, v, resc, has_res, slab + lane * 128, half, lane & 7,
+                          EPI == EPI_TMA2 ? slab_relu + lane * 128 : 0);
           }
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0 && cs.nv > 0) {
-            const int ccol = op.col_off + col0 + c;
-            if (op.a_mode == A_CONV3X3) ptx::tma_store_4d(&tmW.o[0], slab, ccol, cs.x, cs.y, cs.b);
-            else ptx::tma_store_2d(&tmW.o[gi], slab, ccol, static_cast<int>(cs.row0));
+            auto issue = [&](const CUtensorMap* tm, uint32_t src) {
+              const int ccol = op.col_off + col0 + c;
+              if (op.out_mode == O_CONVT2X2) {
+                // n-chunk -> (parity, channel); the slab is 32 consecutive input pixels of one image row
+                const int nn = col0 + c, cq = nn / op.cout;
+                ptx::tma_store_5d(tm, src, op.col_off + nn - cq * op.cout, cq & 1, static_cast<int>(cs.row0 % op.W),
+                                  cq >> 1, static_cast<int>(cs.row0 / op.W));
+              } else if (op.a_mode == A_CONV3X3) {
+                ptx::tma_store_4d(tm, src, ccol, cs.x, cs.y, cs.b);
+              } else {
+                ptx::tma_store_2d(tm, src, ccol, static_cast<int>(cs.row0));
+              }
+            };
+            issue(op.out_mode == O_ROWMAJOR && op.a_mode != A_CONV3X3 ? &tmW.o[gi] : &tmW.o[0], slab);
+            if (EPI == EPI_TMA2) issue(&tmW.orelu, slab_relu);
             ptx::tma_store_commit();
           }
         }
       } else {
-        // ---- EPI_MISC: row-per-thread math; output through a swizzled smem slab + TMA store (g.tma_out) or direct
-        const uint32_t slab = stg_all + (warp - EPI_WARP0) * 4096;
+        // ---- EPI_MISC: row-per-thread math, direct global stores (patch-embed token placement, fused
+        // dots, fp32 / odd-shaped outputs, outputs whose geometry the TMA-store forms do not cover)
         const bool has_res = op.res != nullptr && valid;
         float resv[32];
         if (has_res) load_res(op, m, col0, resv);  // in flight while the MMA of this tile finishes
-        uint32_t keep0[16], keep1[16];             // EPI_MISC dual stores: packed words of both slab halves
         ptx::mbar_wait(&tfull[acc], acc_ph);
         ptx::tc_fence_after();
 #pragma unroll 1
@@ -744,63 +751,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (g.tma_out) {
-            const int half = (c >> 5) & 1;
-            if (half == 0) {
-              if (lane == 0) ptx::tma_store_wait_read();  // the previous slab store has drained the buffer
-              __syncwarp();
-            }
-            epilogue_chunk(op, gp, m, col0 + c, v, resv, slab + lane * 128, half, lane & 7,
-                           op.out_relu ? (half ? keep1 : keep0) : nullptr);
-            if (half == 1) {
-              ptx::fence_proxy_async();
-              __syncwarp();
-              const int ccol = op.col_off + col0 + c - 32;
-              {
-                // ConvT: n-chunk -> (parity, channel); the slab is 32 consecutive input pixels of one row
-                int cq = 0, cx = 0, cby = 0, cco = ccol;
-                if (op.out_mode == O_CONVT2X2) {
-                  const int nn = col0 + c - 32;
-                  cq = nn / op.cout;
-                  cco = op.col_off + nn - cq * op.cout;
-                  cx = static_cast<int>(cs.row0 % op.W);
-                  cby = static_cast<int>(cs.row0 / op.W);
-                }
-                auto issue = [&](const CUtensorMap* tm) {
-                  if (op.out_mode == O_CONVT2X2) ptx::tma_store_5d(tm, slab, cco, cq & 1, cx, cq >> 1, cby);
-                  else if (op.a_mode == A_CONV3X3) ptx::tma_store_4d(tm, slab, ccol, cs.x, cs.y, cs.b);
-                  else ptx::tma_store_2d(tm, slab, ccol, static_cast<int>(cs.row0));
-                  ptx::tma_store_commit();
-                };
-                if (lane == 0 && cs.nv > 0) issue(&tmW.o[0]);
-                if (op.out_relu) {
-                  if (lane == 0) ptx::tma_store_wait_read();
-                  __syncwarp();
-                  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-                  for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t* kp = hh ? keep1 : keep0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                      uint32_t w[4];
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&kp[4 * i + e]);
-                        x = __hmax2(x, zero);
-                        w[e] = *reinterpret_cast<uint32_t*>(&x);
-                      }
-                      ptx::sts_u4(slab + lane * 128 + (((hh * 4 + i) ^ (lane & 7)) << 4), w[0], w[1], w[2], w[3]);
-                    }
-                  }
-                  ptx::fence_proxy_async();
-                  __syncwarp();
-                  if (lane == 0 && cs.nv > 0) issue(&tmW.orelu);
-                }
-              }
-            }
-          } else if (valid) {
-            epilogue_chunk(op, gp, m, col0 + c, v, resv);
-          }
+          if (valid) epilogue_chunk(op, gp, m, col0 + c, v, resv);
           if (has_res && more) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) resv[j] = resn[j];
@@ -898,8 +849,8 @@ int num_sms() {
 template <int BN, int CL, int EPI>
 void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const WeightMaps& tmW,
             cudaStream_t stream) {
-  constexpr int STAGES = Cfg<BN, CL>::STAGES;
-  constexpr size_t SMEM = STAGES * Cfg<BN, CL>::STAGE + 1024 /*align*/ + 256 /*barriers*/ + 8 * STG_WARP_BYTES;
+  using C = Cfg<BN, CL, EPI>;
+  constexpr size_t SMEM = C::STAGES * C::STAGE + 1024 /*align*/ + 256 /*barriers*/ + 8 * C::STG_WARP;
   static bool configured = false;
   if (!configured) {
     DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -1047,12 +998,15 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   const bool resid32 = op.out_mode == O_ROWMAJOR && op.res != nullptr && op.res_f32 && op.out_f32 && op.res2 == nullptr &&
                        op.out_relu == nullptr && op.act == ACT_NONE && op.a_mode == A_ROWMAJOR && op.res == op.out &&
                        op.ldres == op.ldo && op.col_off == 0 && bn >= 128;
-  const bool plain_tma = g.tma_out && op.out_mode == O_ROWMAJOR && op.out_relu == nullptr && !(op.res && op.res_f32);
-  const int epi = resid32 ? EPI_RES32 : (plain_tma ? EPI_TMA : EPI_MISC);
+  if (op.out_mode == O_CONVT2X2) DP_CHECK(op.res == nullptr && op.res2 == nullptr, "ConvT epilogue has no residual");
+  const bool tma_epi = g.tma_out && !(op.res && op.res_f32);
+  const int epi = resid32 ? EPI_RES32 : (tma_epi ? (op.out_relu ? EPI_TMA2 : EPI_TMA) : EPI_MISC);
+  g.tma_out = tma_epi ? 1 : 0;
 #define DP_LAUNCH(BN_, CL_)                                                          \
   do {                                                                               \
     if (epi == EPI_RES32) launch<BN_, CL_, EPI_RES32>(op, g, *tmA, tmW, stream);     \
     else if (epi == EPI_TMA) launch<BN_, CL_, EPI_TMA>(op, g, *tmA, tmW, stream);    \
+    else if (epi == EPI_TMA2) launch<BN_, CL_, EPI_TMA2>(op, g, *tmA, tmW, stream);  \
     else launch<BN_, CL_, EPI_MISC>(op, g, *tmA, tmW, stream);                       \
   } while (0)
   if (cl == 2) {
