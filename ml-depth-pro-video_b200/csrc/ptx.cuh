@@ -217,7 +217,9 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 }
 // arrive on an mbarrier that may live in the peer CTA (address from mapa_u32)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+  // default .release.cta semantics: the barrier only orders TMEM reads (tcgen05.wait::ld + fence) against the
+  // leader's next MMA.  `.release.cluster` compiled to MEMBAR.ALL.GPU + ERRBAR: 17 % of the epilogue warps' time.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in THIS CTA's smem, the bytes complete on `bar_cluster_addr`,
 // which is the leader CTA's barrier (the pair's MMA is issued by the leader alone)

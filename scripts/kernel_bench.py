@@ -10,7 +10,8 @@ cases = [("qkv", 0, T, 3072, 1024), ("fc1+gelu", 1, T, 4096, 1024), ("proj+res",
          ("fc2+res", 2, T, 1024, 4096), ("patch_embed~", 0, 36 * 576, 1024, 768),
          ("conv768 256->256", 3, 768, 256, 256), ("conv384 256->256", 3, 384, 256, 256),
          ("conv768 256->128", 3, 768, 128, 256), ("conv96 1024->256", 3, 96, 256, 1024),
-         ("attention 37 seq", 4, 37, 0, 0), ("layernorm", 5, T, 0, 0)]
+         ("attention 37 seq", 4, 37, 0, 0), ("layernorm", 5, T, 0, 0),
+         ("fc1 no-gelu", 0, T, 4096, 1024)]
 out = {}
 if len(sys.argv) > 1:
     cases = [c for c in cases if c[0] in sys.argv[1:]]
