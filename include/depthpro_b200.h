@@ -110,10 +110,16 @@ int dp_tap(dp_engine* e, const char* stage, float* out, int64_t capacity, int64_
 
 /* Unit-test / microbenchmark entry for the GEMM cores:  C[M,N] = A[M,K] * W[N,K]^T (+bias),
  * fp32 row-major in and out; `backend` 0 = fp32 CUDA-core, 1 = bf16 tcgen05 (inputs are
- * rounded to bf16 on the fly). */
+ * rounded to bf16 on the fly).  `act`: low byte = activation (0 none, 1 ReLU, 2 GELU); for the
+ * bf16 backend the high bits select the epilogue form under test: 0x100 bf16 output through the
+ * TMA-store epilogue (returned as fp32), 0x200 fp32 residual form  C += bias * (acc + bias)  in
+ * place (LayerScale gamma := bias), 0x400 ConvTranspose k2 s2 pixel shuffle (M = S*S pixels,
+ * N = 4*Cout; C is the (2S, 2S, Cout) map), 0x800 with 0x100 / 0x400: dual store, C = ReLU twin. */
 int dp_gemm_test(dp_engine* e, int backend, const float* A, const float* Wt, const float* bias,
                  float* C, int M, int N, int K, int act, void* stream);
-/* Same for 3x3 / pad 1 / stride 1 convolution over NHWC fp32 (B,H,W,Cin) with OIHW weights. */
+/* Same for 3x3 / pad 1 / stride 1 convolution over NHWC fp32 (B,H,W,Cin) with OIHW weights.
+ * `backend` high bits (bf16 only): 0x100 bf16 output through the TMA-store epilogue, 0x800 (with
+ * 0x100) dual store, y = ReLU twin. */
 int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float* w_oihw,
                     const float* bias, float* y_nhwc, int B, int H, int W, int Cin, int Cout,
                     void* stream);

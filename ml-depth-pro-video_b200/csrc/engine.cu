@@ -797,28 +797,57 @@ T* to_dev(const float* src, size_t n, cudaStream_t s) {
 }  // namespace
 
 void Engine::gemm_test(int backend, const float* A, const float* Wt, const float* bias, float* C, int M, int N, int K,
-                       int act, cudaStream_t s) {
+                       int act_flags, cudaStream_t s) {
   DP_CUDA(cudaSetDevice(device_));
+  // act_flags: low byte = activation; bf16 backend only: 0x100 bf16 output (TMA-store epilogue), 0x200 fp32
+  // residual form C += bias * (acc + bias) in place (gamma := bias), 0x400 ConvT k2 s2 pixel shuffle of an
+  // S x S map (M = S*S, N = 4*Cout) into a (2S, 2S, Cout) bf16 map, 0x800 with 0x100/0x400: return the ReLU twin
+  const int act = act_flags & 0xff, flags = act_flags & ~0xff;
   GemmOp op;
   op.M = M, op.N = N, op.K = K, op.lda = K, op.bias = bias, op.act = act, op.out = C, op.out_f32 = 1, op.ldo = N;
   if (backend == BF16) {
     bf16* a = to_dev<bf16>(A, (size_t)M * K, s);
     bf16* w = to_dev<bf16>(Wt, (size_t)N * K, s);
     op.A = a, op.Wt = w;
+    bf16 *ob = nullptr, *orelu = nullptr;
+    const size_t n_out = (size_t)M * N;
+    if (flags & 0x200) {
+      op.gamma = bias, op.res = C, op.res_f32 = 1, op.ldres = N;
+    } else if (flags & (0x100 | 0x400)) {
+      DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ob), n_out * 2, s));
+      op.out = ob, op.out_f32 = 0;
+      if (flags & 0x800) {
+        DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&orelu), n_out * 2, s));
+        op.out_relu = orelu;
+      }
+      if (flags & 0x400) {
+        int S = 1;
+        while (S * S < M) ++S;
+        DP_CHECK(S * S == M && N % 4 == 0, "ConvT test: M must be a square, N = 4*Cout");
+        op.B = 1, op.H = S, op.W = S, op.cout = N / 4, op.out_mode = O_CONVT2X2, op.ldo = N / 4;
+        op.bias_mod = bias ? N / 4 : 0;
+      }
+    }
     gemm_tc(op, s);
+    if (ob) convert<bf16, float>((flags & 0x800) ? orelu : ob, C, (long long)n_out, s);
     DP_CUDA(cudaFreeAsync(a, s));
     DP_CUDA(cudaFreeAsync(w, s));
+    if (ob) DP_CUDA(cudaFreeAsync(ob, s));
+    if (orelu) DP_CUDA(cudaFreeAsync(orelu, s));
     DP_CUDA(cudaStreamSynchronize(s));
     tmap_cache_clear();  // the temporaries' tensor maps must not be reused
   } else {
+    DP_CHECK(flags == 0, "gemm_test: epilogue flags need the bf16 backend");
     op.A = A, op.Wt = Wt;
     gemm_simt(op, s);
   }
 }
-
-void Engine::conv3x3_test(int backend, const float* x, const float* w, const float* bias, float* y, int B, int H, int W_,
-                          int Cin, int Cout, cudaStream_t s) {
+void Engine::conv3x3_test(int backend_flags, const float* x, const float* w, const float* bias, float* y, int B, int H,
+                          int W_, int Cin, int Cout, cudaStream_t s) {
   DP_CUDA(cudaSetDevice(device_));
+  // backend_flags: low byte = backend; bf16 only: 0x100 bf16 NHWC output through the TMA-store epilogue,
+  // 0x800 (with 0x100) dual store, y receives the ReLU twin
+  const int backend = backend_flags & 0xff, flags = backend_flags & ~0xff;
   GemmOp op;
   op.M = B * H * W_, op.N = Cout, op.K = 9 * Cin, op.a_mode = A_CONV3X3, op.B = B, op.H = H, op.W = W_, op.C = Cin;
   op.bias = bias, op.out = y, op.out_f32 = 1, op.ldo = Cout;
@@ -829,9 +858,22 @@ void Engine::conv3x3_test(int backend, const float* x, const float* w, const flo
     DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wp), nw * 2, s));
     pack_oihw_to_ohwi<bf16>(w, wp, Cout, Cin, 3, 3, s);
     op.A = a, op.Wt = wp;
+    bf16 *ob = nullptr, *orelu = nullptr;
+    const size_t n_out = (size_t)B * H * W_ * Cout;
+    if (flags & 0x100) {
+      DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ob), n_out * 2, s));
+      op.out = ob, op.out_f32 = 0;
+      if (flags & 0x800) {
+        DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&orelu), n_out * 2, s));
+        op.out_relu = orelu;
+      }
+    }
     gemm_tc(op, s);
+    if (ob) convert<bf16, float>((flags & 0x800) ? orelu : ob, y, (long long)n_out, s);
     DP_CUDA(cudaFreeAsync(a, s));
     DP_CUDA(cudaFreeAsync(wp, s));
+    if (ob) DP_CUDA(cudaFreeAsync(ob, s));
+    if (orelu) DP_CUDA(cudaFreeAsync(orelu, s));
     DP_CUDA(cudaStreamSynchronize(s));
     tmap_cache_clear();
   } else {

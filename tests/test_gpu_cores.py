@@ -57,6 +57,78 @@ def test_gemm_bf16_tcgen05(M, N, K, act):
     assert relerr(got, ref) < 2e-5
 
 
+# ---- epilogue forms of the tcgen05 GEMM (flags documented at dp_gemm_test in include/depthpro_b200.h)
+def _bf16r(t):
+    return t.bfloat16().float()
+
+
+@pytest.mark.parametrize("M,N,K,act", [(300, 256, 128, 0), (21349, 3072, 1024, 0), (21349, 4096, 1024, 2),
+                                       (1155, 128, 256, 1)])
+def test_gemm_bf16_tma_store_epilogue(M, N, K, act):
+    """bf16 row-major output through smem + TMA store (qkv / fc1+GELU path, single CTA and CTA pair)."""
+    g = torch.Generator(device=DEV).manual_seed(7 * M + N)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    got = _gemm(1, A, W, b, act | 0x100)
+    ref = _ref_gemm(_bf16r(A), _bf16r(W), b, act)
+    # output rounded to bf16: half an ulp = 2^-9 relative per element (erf-GELU approximation is 1e-6 abs)
+    err = (got - ref).abs()
+    assert (err <= ref.abs() * 2.0 ** -8 + 2e-5).all(), float(err.max())
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 128), (21349, 1024, 1024), (21349, 1024, 4096)])
+def test_gemm_bf16_fp32_residual_epilogue(M, N, K):
+    """proj / fc2 form: x += gamma * (acc + bias) on the fp32 residual stream, in place."""
+    g = torch.Generator(device=DEV).manual_seed(M + 3 * N + K)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    res = torch.randn(M, N, device=DEV, generator=g)
+    C = res.clone()
+    _capi.check(lib().dp_gemm_test(engine(), 1, A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 0x200,
+                                   stream()))
+    torch.cuda.synchronize()
+    ref = res.double() + b.double() * (_bf16r(A).double() @ _bf16r(W).double().t() + b.double())
+    assert relerr(C, ref) < 2e-5
+
+
+@pytest.mark.parametrize("S,Cout,K,dual", [(32, 64, 128, 0), (96, 256, 256, 0), (192, 256, 256, 1), (32, 128, 64, 1)])
+def test_gemm_bf16_convt_pixel_shuffle_epilogue(S, Cout, K, dual):
+    """ConvTranspose2d k2 s2 as GEMM (N = (dy, dx, o)) + pixel shuffle through a 5-D TMA store; dual = ReLU twin."""
+    g = torch.Generator(device=DEV).manual_seed(S + Cout + K)
+    M, N = S * S, 4 * Cout
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(Cout, device=DEV, generator=g)
+    C = torch.empty(2 * S, 2 * S, Cout, device=DEV)
+    flags = 0x400 | (0x800 if dual else 0)
+    _capi.check(lib().dp_gemm_test(engine(), 1, A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, flags,
+                                   stream()))
+    torch.cuda.synchronize()
+    y = (_bf16r(A) @ _bf16r(W).t()).view(S, S, 2, 2, Cout) + b          # (y, x, dy, dx, o)
+    ref = y.permute(0, 2, 1, 3, 4).reshape(2 * S, 2 * S, Cout)
+    if dual:
+        ref = ref.clamp_min(0)
+    err = (C - ref).abs()
+    assert (err <= ref.abs() * 2.0 ** -8 + 2e-5).all(), float(err.max())
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,dual", [(1, 96, 96, 256, 256, 0), (1, 192, 192, 256, 256, 1), (2, 24, 48, 128, 128, 1)])
+def test_conv3x3_bf16_tma_store_epilogue(B, H, W, Cin, Cout, dual):
+    """NHWC bf16 conv output through the 4-D TMA store (CTA pair at 192^2), optional (x, relu(x)) dual store."""
+    g = torch.Generator(device=DEV).manual_seed(H + Cin + dual)
+    x = torch.randn(B, Cin, H, W, device=DEV, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=g) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device=DEV, generator=g)
+    got = _conv(1 | 0x100 | (0x800 if dual else 0), x, w, b)
+    ref = F.conv2d(_bf16r(x), _bf16r(w), b, padding=1)
+    if dual:
+        ref = ref.clamp_min(0)
+    err = (got - ref).abs()
+    assert (err <= ref.abs() * 2.0 ** -8 + 3e-5).all(), float(err.max())
+
+
 def _conv(backend, x_nchw, w, bias):
     B, Cin, H, W_ = x_nchw.shape
     Cout = w.shape[0]
