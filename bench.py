@@ -2,6 +2,7 @@
 """bench.py — Depth Pro hot path on B200: frames/s at 1536^2 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+                    [--workload frame1536|clip1080p|stream4k]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
@@ -16,6 +17,11 @@ with no data-path collective: weak scaling).  Rank 0 prints ONE JSON line:
   roofline   dominant kernel (tcgen05 GEMM/conv `gemm_tc_kernel`): algorithmic FLOPs / its summed
              CUDA-event time over a profiled replay of the timed steps, vs MEASURED_PEAKS.json
   cpu_baseline  the oracle (CPU fp32 port of the reference) on this box's host cores, 1 frame
+
+`--workload clip1080p` (BASELINE.json configs[2]) streams uint8 1080p frames from pinned host memory
+through `video.DepthStream` (fused transform + resize -> infer -> 1080p fp32 depth back to pinned host,
+double-buffered); `--workload stream4k` (configs[3]) adds the depth -> 3-D unprojection with colours at
+3840x2160.  Both report the same metric (frames/s) with `value` device-resident and `e2e` host to host.
 
 `--impl reference` times the reference's CPU implementation (the oracle port; the reference is
 Python + timm and /root/reference does not exist on the GPU box) on the host cores.
@@ -49,6 +55,51 @@ def _peaks():
         d = json.load(open(p))
         return d, "MEASURED_PEAKS.json"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per gemm_tc_kernel launch from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by scripts/ncu_summarise.py)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p))["gemm_tc_kernel"]
+    except (KeyError, ValueError):
+        return None
+
+
+# HBM-bound kernels either side of the network: (name, dp_kernel_bench kind, H, W)
+HBM_CASES = [("resize 1080p u8 -> 1536^2 f32 (fused transform)", 6, 1080, 1920),
+             ("resize 4K u8 -> 1536^2 f32 (fused transform)", 6, 2160, 3840),
+             ("pyramid + split + im2col -> 36x576x768 bf16", 7, 0, 0),
+             ("depth epilogue 1536^2 -> 1080p", 8, 1080, 1920),
+             ("depth epilogue 1536^2 -> 4K", 8, 2160, 3840),
+             ("unproject 4K + colours", 9, 2160, 3840),
+             ("colorize 1080p", 10, 1080, 1920)]
+
+
+def hbm_bytes(kind, H, W):
+    """Algorithmic bytes (read + write) per launch, SURVEY.md §8(d)."""
+    img = 3 * 1536 * 1536
+    return {6: H * W * 3 + img * 4, 7: img * 4 + 36 * 576 * 768 * 2, 8: 1536 * 1536 * 4 + H * W * 4,
+            9: H * W * (4 + 3) + H * W * 24, 10: H * W * (4 + 3)}[kind]
+
+
+def hbm_kernels(lib, model):
+    """Each HBM-bound kernel timed alone (CUDA events, L2 flushed before every launch) against the
+    measured copy bandwidth."""
+    from depth_pro import _capi
+
+    peaks, _ = _peaks()
+    out = {}
+    for name, kind, H, W in HBM_CASES:
+        ms = ctypes.c_float()
+        _capi.check(lib.dp_kernel_bench(model._engine, kind, H, W, 0, 10, ctypes.byref(ms)))
+        gbs = hbm_bytes(kind, H, W) / (ms.value * 1e-3) / 1e9
+        out[name] = {"us": round(ms.value * 1e3, 2), "MB": round(hbm_bytes(kind, H, W) / 1e6, 2), "GB/s": round(gbs, 1),
+                     "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)}
+    return out
 
 
 class ClockSampler:
@@ -300,7 +351,7 @@ def run_ours(args):
             ach = (work[0] + work[1]) / (t_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
             roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)",
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": _ncu_traffic(),
                     "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                     "launches_per_step": (cnt[0] + cnt[1]) / prof_steps,
                     "kernel_ms_per_step": t_ms / prof_steps,
@@ -309,6 +360,8 @@ def run_ours(args):
             ach = work[4] / (ms[4] * 1e-3) / 1e12
             roof = {"bound": "fp32-fma", "kernel": "gemm_simt_kernel (parity mode)", "achieved": ach, "peak": None,
                     "unit": "TFLOP/s", "frac": None, "traffic": None}
+
+    hbm = hbm_kernels(lib, model) if rank == 0 and world == 1 else None
 
     # ---------------- CPU baseline: the oracle on the host cores (rank 0, N = 1 only)
     cpu = None
@@ -342,7 +395,130 @@ def run_ours(args):
             "p50_ms_per_frame": p50 / B, "p99_ms_per_step": p99,
             "tflops_per_gpu": FLOPS_PER_FRAME * B / (ms_per_step * 1e-3) / 1e12,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "outputs_finite": finite,
-            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": roof, "kernels": kernels, "hbm_kernels": hbm, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ======================================================================================
+# video workloads (BASELINE.json configs[2], configs[3]) through the streaming add-on
+# ======================================================================================
+def run_video(args):
+    import numpy as np
+    import torch
+
+    rank, world, local = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    import depth_pro
+    from depth_pro import synthetic, video
+
+    H, W = (1080, 1920) if args.workload == "clip1080p" else (2160, 3840)
+    unproject = args.workload == "stream4k"
+    fps_step = args.frames_per_step
+    model = depth_pro.DepthPro(device=dev, precision=torch.bfloat16, max_batch=1)
+    model.init_weights("stress", SEED)
+    # a ring of distinct synthetic frames in pinned host memory (moving
+    # low-frequency gradient + N(0,8) noise, seed 7 / 11); frame i of the clip -> rank i % world
+    ring_n = 8
+    seed = 7 if args.workload == "clip1080p" else 11
+    ring = [torch.from_numpy(synthetic.synthetic_frame_u8(rank + world * i, H, W, seed)).pin_memory()
+            for i in range(ring_n)]
+    ring_dev = [f.to(dev) for f in ring]
+    n_frames = args.steps * fps_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    xyz_host = torch.empty((H * W, 3), dtype=torch.float32).pin_memory() if unproject else None
+
+    def device_frame(i):
+        pred = model.infer(ring_dev[i % ring_n])
+        if unproject:
+            video.depth_to_3d(model, pred["depth"], pred["focallength_px"], W, H, rgb=ring_dev[i % ring_n], sync=False)
+        return pred
+
+    def e2e_frames(n):
+        if not unproject:
+            stream = video.DepthStream(model, H, W, batch=1, slots=2)
+            k = 0
+            for r in stream.run(((i, ring[i % ring_n].numpy()) for i in range(n))):
+                k += 1
+            return k
+        for i in range(n):
+            x = ring[i % ring_n].to(dev, non_blocking=True)
+            pred = model.infer(x)
+            pts, _, cols = video.depth_to_3d(model, pred["depth"], pred["focallength_px"], W, H, rgb=x)
+            xyz_host[: pts.shape[0]].copy_(pts, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        return n
+
+    for i in range(max(args.warmup, 3)):
+        out = device_frame(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = model.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record()
+    for i in range(n_frames):
+        out = device_frame(i)
+    b.record()
+    torch.cuda.synchronize(dev)
+    barrier()
+    launches = model.launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(a.elapsed_time(b))
+    value = world * n_frames / (total_ms / 1e3)
+
+    e2e_frames(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_frames(n_frames)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    h2d = H * W * 3 * fps_step
+    d2h = (H * W * 12 + 8 if unproject else H * W * 4 + 4) * fps_step
+    if rank == 0:
+        what = ("uint8 %dx%d frames -> fused transform+resize -> infer -> depth %dx%d" % (W, H, W, H)
+                + (" -> depth_to_3d + colours (N = %d points)" % (H * W) if unproject else ""))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {what}; Depth Pro random-init recipe-B weights",
+                       "frames_per_gpu_per_step": fps_step, "frames_per_gpu": n_frames,
+                       "sharding": f"frame i -> rank i % {world}, no data-path collective",
+                       "l2": "no flush: per-frame working set >> 126 MB L2"},
+            "ms_per_frame": total_ms / n_frames,
+            "e2e": {"value": world * n_frames / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3 / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": ("video.DepthStream.run (pinned uint8 frames in, pinned fp32 depth out, double-buffered)"
+                            if not unproject else
+                            "model.infer(pinned uint8 frame) -> video.depth_to_3d(+rgb) -> xyz to pinned host")},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "outputs_finite": bool(torch.isfinite(out["depth"]).all()),
+            "roofline": None, "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -359,9 +535,13 @@ def main():
     ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=["frame1536", "clip1080p", "stream4k"], default="frame1536")
+    ap.add_argument("--frames-per-step", type=int, default=8, help="video workloads: frames per GPU per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "frame1536":
+        run_video(args)
     else:
         run_ours(args)
 

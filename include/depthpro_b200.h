@@ -129,7 +129,10 @@ int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, i
 
 /* Micro-benchmark of one bf16 core on scratch buffers; mean ms per launch over `iters` launches.
  * kind 0 GEMM+bias, 1 GEMM+bias+GELU, 2 GEMM+bias*gamma+fp32 residual (in place), 3 conv3x3 on an
- * MxM map (Cin=K, Cout=N), 4 attention over M sequences, 5 LayerNorm over M rows. */
+ * MxM map (Cin=K, Cout=N), 4 attention over M sequences, 5 LayerNorm over M rows.  Kinds 6-10 time
+ * the HBM-bound kernels either side of the network on an M x N (H x W) image, L2 flushed before
+ * every launch: 6 uint8 HWC -> fused transform + resize -> fp32 3x1536^2, 7 pyramid + 35-patch split +
+ * im2col of one 1536^2 frame, 8 depth epilogue 1536^2 -> M x N, 9 unprojection + colours, 10 colourise. */
 int dp_kernel_bench(dp_engine* e, int kind, int M, int N, int K, int iters, float* ms_out);
 
 /* Per-launch CUDA-event profiling of the hot kernels (used by bench.py for the roofline line).

@@ -121,6 +121,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   ptx::tc_fence_after();
   // TMEM columns of stream s: S at [256 s, 256 s + 128), O at [256 s + 128, 256 s + 192)
   const uint32_t tmem_base = *tmem_slot + sidx * 256;
+  ptx::pdl_wait();  // PDL: the qkv GEMM's output is visible from here on
+  ptx::pdl_launch_dependents();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -378,7 +380,7 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
   const uint32_t ob[3] = {64, 32, 1};
   const CUtensorMap& tmo = get_tmap_bf16(out, 3, od, os, ob);
   const int ctas = (nseq * NH + 1) / 2;  // two streams per CTA, one (sequence, head) unit at a time each
-  attention_tc_kernel<<<ctas < sms ? ctas : sms, THREADS, SMEM_BYTES, s>>>(tm, tmo, nseq);
+  launch_pdl(attention_tc_kernel, dim3(ctas < sms ? ctas : sms), dim3(THREADS), SMEM_BYTES, s, tm, tmo, nseq);
   DP_LAUNCH_CHECK();
 }
 

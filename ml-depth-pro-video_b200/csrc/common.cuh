@@ -55,6 +55,24 @@ void prof_enable(bool on);
 // sums since prof_enable(true); synchronises the device
 void prof_collect(double* ms_by_class, double* work_by_class, long long* launches_by_class);
 
+// Programmatic dependent launch (PDL): a kernel launched with this attribute may start its CTAs --
+// barrier init, TMEM allocation, tensor-map prefetch -- while the previous kernel of the stream is
+// still draining; it executes `griddepcontrol.wait` before it touches any global memory the
+// previous kernel may have written.  DEPTHPRO_PDL=0 turns the attribute off (the griddepcontrol
+// instructions are then no-ops).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  DP_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 #define DP_LAUNCH_CHECK()                \
   do {                                   \
     ::dp::count_launch();                \

@@ -19,6 +19,14 @@ namespace dp {
 
 int64_t g_launches = 0;
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DEPTHPRO_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // ---------------------------------------------------------------------------- profiler
 namespace {
 struct ProfRec {
@@ -913,6 +921,8 @@ namespace dp {
 //  kind 2: GEMM + bias, *gamma, + fp32 residual in place (proj / fc2)
 //  kind 3: conv3x3 on an MxM map, Cin = K, Cout = N, + bias + ReLU -> bf16
 //  kind 4: attention over M sequences       kind 5: LayerNorm over M rows
+//  kinds 6-10: the HBM-bound kernels either side of the network (resize, split, depth epilogue,
+//  unprojection, colourise) on an M x N image
 // Returns the mean milliseconds per launch over `iters` launches (CUDA events).
 float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   DP_CUDA(cudaSetDevice(device_));
@@ -946,22 +956,76 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
     bf16* q = (bf16*)B((size_t)M * SEQ * 3 * EMB * 2);
     bf16* o = (bf16*)B((size_t)M * SEQ * EMB * 2);
     run = [&, q, o] { attention_bf16_tc(q, o, M, s); };
-  } else {
+  } else if (kind == 5) {
     float* x = (float*)B((size_t)M * EMB * 4);
     bf16* y = (bf16*)B((size_t)M * EMB * 2);
     float* w = (float*)B(EMB * 4);
     run = [&, x, y, w] { layernorm_rows<bf16>(x, y, w, w, M, RowMap(), 1, s); };
+  } else if (kind == 6) {  // uint8 HWC (M x N) -> fused transform + bilinear resize -> fp32 3x1536^2
+    uint8_t* src = (uint8_t*)B((size_t)M * N * 3);
+    float* x = (float*)B((size_t)3 * IMG * IMG * 4);
+    run = [&, src, x] { resize_to_1536(src, 1, 1, M, N, x, s); };
+  } else if (kind == 7) {  // pyramid + 35-patch split + 16x16 im2col, fp32 frame -> bf16 A operands
+    float* x = (float*)B((size_t)3 * IMG * IMG * 4);
+    bf16* a35 = (bf16*)B((size_t)35 * 576 * 768 * 2);
+    bf16* a1 = (bf16*)B((size_t)576 * 768 * 2);
+    run = [&, x, a35, a1] { split_im2col<bf16>(x, 1, a35, a1, s); };
+  } else if (kind == 8 || kind == 9 || kind == 10) {
+    // 8: canonical inverse depth 1536^2 -> metric depth (M x N);  9: depth (M x N) + rgb -> xyz + colours;
+    // 10: depth (M x N) -> colour-mapped uint8 RGB
+    std::vector<float> ones((size_t)IMG * IMG > (size_t)M * N ? (size_t)IMG * IMG : (size_t)M * N, 2.0f);
+    float* canon = (float*)B((size_t)IMG * IMG * 4);
+    float* depth = (float*)B((size_t)M * N * 4);
+    float* f = (float*)B(4);
+    DP_CUDA(cudaMemcpy(canon, ones.data(), (size_t)IMG * IMG * 4, cudaMemcpyHostToDevice));
+    DP_CUDA(cudaMemcpy(depth, ones.data(), (size_t)M * N * 4, cudaMemcpyHostToDevice));
+    const float fpx = 1000.f;
+    DP_CUDA(cudaMemcpy(f, &fpx, 4, cudaMemcpyHostToDevice));
+    if (kind == 8) {
+      run = [&, canon, f, depth] { depth_epilogue(canon, f, 1, M, N, depth, s); };
+    } else if (kind == 9) {
+      uint8_t* rgb = (uint8_t*)B((size_t)M * N * 3);
+      float* xyz = (float*)B((size_t)M * N * 12);
+      float* col = (float*)B((size_t)M * N * 12);
+      int64_t* nv = (int64_t*)B(8);
+      int* scratch = (int*)B(unproject_scratch_ints(M, N) * sizeof(int));
+      run = [&, depth, rgb, f, xyz, col, nv, scratch] { dp::unproject(depth, rgb, M, N, f, xyz, col, nullptr, nv, scratch, s); };
+    } else {
+      uint8_t* lut = (uint8_t*)B(768);
+      uint8_t* out = (uint8_t*)B((size_t)M * N * 3);
+      float* mm = (float*)B(8);
+      run = [&, depth, lut, out, mm] { dp::colorize(depth, M, N, lut, out, mm, s); };
+    }
+  } else {
+    DP_CHECK(false, "kernel_bench: unknown kind");
   }
   for (int i = 0; i < 3; ++i) run();
   cudaEvent_t a, b;
   DP_CUDA(cudaEventCreate(&a));
   DP_CUDA(cudaEventCreate(&b));
-  DP_CUDA(cudaEventRecord(a, s));
-  for (int i = 0; i < iters; ++i) run();
-  DP_CUDA(cudaEventRecord(b, s));
-  DP_CUDA(cudaEventSynchronize(b));
   float ms = 0.f;
-  DP_CUDA(cudaEventElapsedTime(&ms, a, b));
+  if (kind >= 5) {
+    // HBM-bound kernels with working sets near the 126 MB L2: overwrite a 256 MB buffer before every
+    // timed launch so inputs come from HBM, and time each launch on its own
+    const size_t FLUSH = 256u << 20;
+    void* fl = B(FLUSH);
+    for (int i = 0; i < iters; ++i) {
+      DP_CUDA(cudaMemsetAsync(fl, i & 0xff, FLUSH, s));
+      DP_CUDA(cudaEventRecord(a, s));
+      run();
+      DP_CUDA(cudaEventRecord(b, s));
+      DP_CUDA(cudaEventSynchronize(b));
+      float t = 0.f;
+      DP_CUDA(cudaEventElapsedTime(&t, a, b));
+      ms += t;
+    }
+  } else {
+    DP_CUDA(cudaEventRecord(a, s));
+    for (int i = 0; i < iters; ++i) run();
+    DP_CUDA(cudaEventRecord(b, s));
+    DP_CUDA(cudaEventSynchronize(b));
+    DP_CUDA(cudaEventElapsedTime(&ms, a, b));
+  }
   cudaEventDestroy(a), cudaEventDestroy(b);
   for (void* p : bufs) cudaFree(p);
   tmap_cache_clear();

@@ -444,6 +444,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped the previous kernel's tail; nothing below may run before its
+  // writes are visible.  The next kernel may start placing CTAs as ours retire.
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
 
   // register split: the four control warps need few registers, the epilogue warps hold a whole
   // tile's residual values in flight (384 x 168 = 128 x 40 + 256 x 232)
@@ -864,11 +868,20 @@ void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const W
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   DP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL, EPI>, tmA, tmW, op, g));
   count_launch();
 }

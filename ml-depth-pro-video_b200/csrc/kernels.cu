@@ -74,6 +74,21 @@ __device__ __forceinline__ float box4(float a, float b, float c, float d) {
                    __fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, c), __fmul_rn(0.5f, d))));
 }
 
+// 8 consecutive outputs (col is a multiple of 8): one 16-byte (bf16) or two 16-byte (fp32) stores
+__device__ __forceinline__ void store8(float* dst, const float (&v)[8]) {
+  reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* dst, const float (&v)[8]) {
+  uint4 pk;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(v[0], v[1]), pk.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[2], v[3]), pk.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[4], v[5]), pk.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(v[6], v[7]), pk.w = *reinterpret_cast<uint32_t*>(&t);
+  *reinterpret_cast<uint4*>(dst) = pk;
+}
+
 template <typename T>
 __global__ void split_im2col_kernel(const float* __restrict__ x, int B, T* __restrict__ A35, T* __restrict__ A1) {
   // one thread = 8 consecutive kx of one (row, c, ky)
@@ -91,31 +106,30 @@ __global__ void split_im2col_kernel(const float* __restrict__ x, int B, T* __res
   const float* img = x + (static_cast<long long>(b) * 3 + c) * IMG * IMG;
   float v[8];
   if (patch < 25) {
+    // X is a multiple of 8: two aligned 16-byte loads
     const int Y = (patch / 5) * 288 + py, X = (patch % 5) * 288 + px;
-    const float* p = img + static_cast<long long>(Y) * IMG + X;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = p[i];
+    const float4* p = reinterpret_cast<const float4*>(img + static_cast<long long>(Y) * IMG + X);
+    const float4 a = p[0], c4 = p[1];
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = c4.x, v[5] = c4.y, v[6] = c4.z, v[7] = c4.w;
   } else if (patch < 34) {
     const int q = patch - 25;
     const int Y = (q / 3) * 192 + py, X = (q % 3) * 192 + px;
-    const float* p0 = img + static_cast<long long>(2 * Y) * IMG + 2 * X;
-    const float* p1 = p0 + IMG;
+    const float4* p0 = reinterpret_cast<const float4*>(img + static_cast<long long>(2 * Y) * IMG + 2 * X);
+    const float4* p1 = p0 + IMG / 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = box4(p0[2 * i], p0[2 * i + 1], p1[2 * i], p1[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) {
+      const float4 r0 = p0[i], r1 = p1[i];
+      v[2 * i] = box4(r0.x, r0.y, r1.x, r1.y);
+      v[2 * i + 1] = box4(r0.z, r0.w, r1.z, r1.w);
+    }
   } else {
     const float* p0 = img + static_cast<long long>(4 * py + 1) * IMG + 4 * px + 1;
     const float* p1 = p0 + IMG;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = box4(p0[4 * i], p0[4 * i + 1], p1[4 * i], p1[4 * i + 1]);
   }
-  T* dst = A35 + row * 768 + col;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) dst[i] = from_f<T>(v[i]);
-  if (A1 != nullptr && patch == 34) {
-    T* d1 = A1 + (static_cast<long long>(b) * 576 + tok) * 768 + col;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d1[i] = from_f<T>(v[i]);
-  }
+  store8(A35 + row * 768 + col, v);
+  if (A1 != nullptr && patch == 34) store8(A1 + (static_cast<long long>(b) * 576 + tok) * 768 + col, v);
 }
 
 __global__ void im2col_to_ref_kernel(const float* __restrict__ A35, int B, float* __restrict__ patches) {
@@ -166,6 +180,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         long long n_out, RowMap map, int ln, LnGroups grp) {
   const long long d = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: `in` comes from the previous kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (d >= n_out) return;
   if (grp.n > 1) {
     const int gi = (d >= grp.end[0] ? 1 : 0) + (d >= grp.end[1] ? 1 : 0);
@@ -636,6 +652,7 @@ void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x,
 template <typename T>
 void split_im2col(const float* x, int B, T* A35, T* A1, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * 35 * 576 * 96;
+  DP_CHECK(reinterpret_cast<uintptr_t>(x) % 16 == 0, "split: the frame buffer must be 16-byte aligned");
   split_im2col_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(x, B, A35, A1);
   DP_LAUNCH_CHECK();
 }
@@ -656,12 +673,12 @@ void write_cls_rows(float* resid, const float* cls, const float* pos, int nseq, 
 template <typename T>
 void layernorm_rows(const float* in, T* out, const float* w, const float* b, long long n_out, RowMap map, int ln,
                     cudaStream_t s) {
-  layernorm_kernel<T><<<blocks_for(n_out, 8), 256, 0, s>>>(in, out, w, b, n_out, map, ln, LnGroups());
+  launch_pdl(layernorm_kernel<T>, dim3(blocks_for(n_out, 8)), dim3(256), 0, s, in, out, w, b, n_out, map, ln, LnGroups());
   DP_LAUNCH_CHECK();
 }
 template <typename T>
 void layernorm_rows_grouped(const float* in, T* out, const LnGroups& g, long long n_out, cudaStream_t s) {
-  layernorm_kernel<T><<<blocks_for(n_out, 8), 256, 0, s>>>(in, out, g.w[0], g.b[0], n_out, RowMap(), 1, g);
+  launch_pdl(layernorm_kernel<T>, dim3(blocks_for(n_out, 8)), dim3(256), 0, s, in, out, g.w[0], g.b[0], n_out, RowMap(), 1, g);
   DP_LAUNCH_CHECK();
 }
 template void layernorm_rows_grouped<float>(const float*, float*, const LnGroups&, long long, cudaStream_t);

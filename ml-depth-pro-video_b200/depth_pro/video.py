@@ -51,7 +51,8 @@ def colormap_lut(cmap: str = "turbo") -> np.ndarray:
 
 
 def depth_to_3d(model: DepthPro, depth: torch.Tensor, focallength_px, width: int, height: int,
-                rgb: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+                rgb: Optional[torch.Tensor] = None, sync: bool = True
+                ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """GPU ``depth_to_3d`` (img_to_normalized_pointcloud.py:819-856).
 
     Returns ``(points (N,3) float32, valid_mask (H,W) bool, colours (N,3) float32 or None)``; points
@@ -73,6 +74,8 @@ def depth_to_3d(model: DepthPro, depth: torch.Tensor, focallength_px, width: int
     lib = model._ensure_engine(1)
     _capi.check(lib.dp_unproject(model._engine, depth.data_ptr(), _capi.ptr(rgb), height, width, f.data_ptr(),
                                  xyz.data_ptr(), _capi.ptr(cols), mask.data_ptr(), n.data_ptr(), model._stream()))
+    if not sync:
+        return xyz, n, cols
     k = int(n.item())
     return xyz[:k], mask.bool(), (cols[:k] if cols is not None else None)
 

@@ -11,7 +11,20 @@ cases = [("qkv", 0, T, 3072, 1024), ("fc1+gelu", 1, T, 4096, 1024), ("proj+res",
          ("conv768 256->256", 3, 768, 256, 256), ("conv384 256->256", 3, 384, 256, 256),
          ("conv768 256->128", 3, 768, 128, 256), ("conv96 1024->256", 3, 96, 256, 1024),
          ("attention 37 seq", 4, 37, 0, 0), ("layernorm", 5, T, 0, 0),
-         ("fc1 no-gelu", 0, T, 4096, 1024)]
+         ("fc1 no-gelu", 0, T, 4096, 1024),
+         # HBM-bound kernels either side of the network: (kind, H, W); bytes = algorithmic read + write
+         ("resize 1080p u8->1536^2 f32", 6, 1080, 1920, 0), ("resize 4K u8->1536^2 f32", 6, 2160, 3840, 0),
+         ("split+im2col 1536^2 -> 36x576x768 bf16", 7, 0, 0, 0),
+         ("depth epilogue -> 1080p", 8, 1080, 1920, 0), ("depth epilogue -> 4K", 8, 2160, 3840, 0),
+         ("unproject 4K (+rgb)", 9, 2160, 3840, 0), ("unproject 1080p (+rgb)", 9, 1080, 1920, 0),
+         ("colorize 1080p", 10, 1080, 1920, 0)]
+
+
+def hbm_bytes(kind, H, W):
+    """Algorithmic bytes of the HBM-bound kernels."""
+    img = 3 * 1536 * 1536
+    return {6: H * W * 3 + img * 4, 7: img * 4 + 36 * 576 * 768 * 2, 8: 1536 * 1536 * 4 + H * W * 4,
+            9: H * W * (4 + 3) + H * W * 24, 10: H * W * (4 + 3)}[kind]
 out = {}
 if len(sys.argv) > 1:
     cases = [c for c in cases if c[0] in sys.argv[1:]]
@@ -24,6 +37,8 @@ for name, kind, M, N, K in cases:
     else: fl = 0
     tf = fl / (ms.value * 1e-3) / 1e12 if fl else 0
     gbs = (M * 1024 * 6) / (ms.value * 1e-3) / 1e9 if kind == 5 else 0
+    if kind >= 6:
+        gbs = hbm_bytes(kind, M, N) / (ms.value * 1e-3) / 1e9
     out[name] = {"us": round(ms.value * 1e3, 1), "TFLOP/s": round(tf, 1), "GB/s": round(gbs, 1)}
     print(f"{name:22s} {ms.value*1e3:9.1f} us  {tf:8.1f} TF/s {gbs:8.1f} GB/s", flush=True)
 print(json.dumps(out))
