@@ -114,7 +114,11 @@ int dp_tap(dp_engine* e, const char* stage, float* out, int64_t capacity, int64_
  * bf16 backend the high bits select the epilogue form under test: 0x100 bf16 output through the
  * TMA-store epilogue (returned as fp32), 0x200 fp32 residual form  C += bias * (acc + bias)  in
  * place (LayerScale gamma := bias), 0x400 ConvTranspose k2 s2 pixel shuffle (M = S*S pixels,
- * N = 4*Cout; C is the (2S, 2S, Cout) map), 0x800 with 0x100 / 0x400: dual store, C = ReLU twin. */
+ * N = 4*Cout; C is the (2S, 2S, Cout) map), 0x800 with 0x100 / 0x400: dual store, C = ReLU twin;
+ * 0x1000 with 0x100, K = 1024: LayerNorm folded into the GEMM (timm Block: norm1 -> qkv, norm2 -> fc1),
+ * C = LN(A; g, b_ln, eps 1e-6) * W^T + bias with g[k] = 1 + 0.25 sin(0.37 k), b_ln[k] = 0.1 cos(0.11 k);
+ * 0x2000 with 0x200, N = 1024: the residual form also emits bf16(x) and per-row partial sums for the
+ * next folded GEMM; C is (2M, N) and rows [M, 2M) return (x - mean) / sqrt(var + 1e-6) rebuilt from them. */
 int dp_gemm_test(dp_engine* e, int backend, const float* A, const float* Wt, const float* bias,
                  float* C, int M, int N, int K, int act, void* stream);
 /* Same for 3x3 / pad 1 / stride 1 convolution over NHWC fp32 (B,H,W,Cin) with OIHW weights.

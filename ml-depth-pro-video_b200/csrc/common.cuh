@@ -58,8 +58,9 @@ void prof_collect(double* ms_by_class, double* work_by_class, long long* launche
 // Programmatic dependent launch (PDL): a kernel launched with this attribute may start its CTAs --
 // barrier init, TMEM allocation, tensor-map prefetch -- while the previous kernel of the stream is
 // still draining; it executes `griddepcontrol.wait` before it touches any global memory the
-// previous kernel may have written.  DEPTHPRO_PDL=0 turns the attribute off (the griddepcontrol
-// instructions are then no-ops).
+// previous kernel may have written.  Opt-in with DEPTHPRO_PDL=1 (without the attribute the
+// griddepcontrol instructions are no-ops): measured on B200, the frame is power-capped and the hidden
+// launch latency bought nothing.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
@@ -80,6 +81,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   } while (0)
 
 enum Prec { FP32 = 0, BF16 = 1 };
+constexpr int LN_SLOTS = 8;  // partial (sum, sum of squares) pairs per row: 1024 columns / 128 per epilogue warp
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 // How the A operand rows of a GEMM are addressed.
@@ -114,6 +116,7 @@ struct GemmGroup {
   const float* bias = nullptr;
   const float* gamma = nullptr;
   const float* pos = nullptr;
+  const float* ln_c = nullptr;  // LayerNorm-folded GEMM: column sums of the (g * W) weights, see GemmOp::ln_stats
 };
 
 struct GemmOp {
@@ -146,6 +149,17 @@ struct GemmOp {
   const float* dot_w = nullptr; // O_DOT_RELU: head.4 weight (32), dot_b: bias (1)
   const float* dot_b = nullptr;
   const float* head_cb = nullptr;  // O_HEAD_FUSED: [9][32] per-tap bias terms, then [32] full bias
+  // LayerNorm folded into the surrounding GEMMs (bf16 tcgen05 core only).  With x the fp32 residual
+  // stream, LN(x) W^T + b  =  rstd * (x (g*W)^T)  -  rstd * mean * colsum(g*W)  +  (W b_ln + b):
+  //  * producer (the fp32-residual form, proj / fc2, N == 1024): besides x += gamma * (acc + bias) it
+  //    stores bf16(x) to `ln_xb` (ld = ldo) and per-row partial sums (sum x, sum x^2) of its 128-column
+  //    slice to `ln_stats_out[row][LN_SLOTS][2]` -- no atomics, the consumer adds the slots in order;
+  //  * consumer (bf16 output through the TMA-store epilogue, qkv / fc1, K == 1024): A is that raw bf16
+  //    copy, Wt = bf16(g * W), grp.bias = W b_ln + b, grp.ln_c = colsum(Wt); `ln_stats` are the
+  //    producer's partial sums of the A rows.
+  const float* ln_stats = nullptr;
+  void* ln_xb = nullptr;
+  float* ln_stats_out = nullptr;
   // groups
   int ngroups = 1;
   GemmGroup grp[3];

@@ -7,9 +7,11 @@
 //   FOVNetwork.forward        src/depth_pro/network/fov.py:56-82
 #include "engine.cuh"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <type_traits>
 
 #include "attention.cuh"
 #include "gemm.cuh"
@@ -21,8 +23,8 @@ int64_t g_launches = 0;
 
 bool pdl_enabled() {
   static const bool on = [] {
-    const char* e = getenv("DEPTHPRO_PDL");
-    return !(e && e[0] == '0');
+    const char* e = getenv("DEPTHPRO_PDL");  // measured: no gain under the power cap, default off
+    return e && e[0] == '1';
   }();
   return on;
 }
@@ -193,6 +195,8 @@ Engine::Engine(int device, int prec, int max_batch) : device_(device), prec_(pre
   manifest_ = build_manifest();
   const char* a = getenv("DEPTHPRO_ATTN");  // debugging switch: "mma" selects the mma.sync kernel
   attn_legacy_ = a != nullptr && std::string(a) == "mma";
+  const char* lf = getenv("DEPTHPRO_LN_FUSE");  // debugging switch: "0" keeps the stand-alone LayerNorm launches
+  ln_fuse_ = prec_ == BF16 && !(lf != nullptr && lf[0] == '0');
   DP_CUDA(cudaStreamCreateWithFlags(&host_stream_, cudaStreamNonBlocking));
 }
 
@@ -241,8 +245,11 @@ void Engine::set_weight(const std::string& name, const void* data, const int64_t
   const bool bf = prec_ == BF16;
   const bool fusion_tail = starts_with(name, "decoder.fusions.") && name[16] != '0' &&
                            (ends_with(name, ".deconv.weight") || ends_with(name, ".out_conv.weight"));
+  // folded at finalize with the block's norm1 / norm2 affine, from the fp32 originals
+  const bool ln_folded = ln_fuse_ && (ends_with(name, ".attn.qkv.weight") || ends_with(name, ".mlp.fc1.weight") ||
+                                      ends_with(name, ".attn.qkv.bias") || ends_with(name, ".mlp.fc1.bias"));
   if (bf && (name == "head.1.weight" || name == "head.1.bias" || name == "head.2.weight" || name == "head.2.bias" ||
-             fusion_tail)) {
+             fusion_tail || ln_folded)) {
     Packed& rw = raw_[name];
     if (rw.bytes != n * 4) {
       if (rw.ptr) DP_CUDA(cudaFree(rw.ptr));
@@ -316,6 +323,10 @@ VitWeights Engine::vit_weights(const std::string& p) const {
     k.fc1_w = W(b + "mlp.fc1.weight"), k.fc1_b = F(b + "mlp.fc1.bias");
     k.fc2_w = W(b + "mlp.fc2.weight"), k.fc2_b = F(b + "mlp.fc2.bias");
     k.g2 = F(b + "ls2.gamma");
+    if (ln_fuse_) {
+      k.qkv_b = F(b + "attn.qkv.ln_d"), k.qkv_c = F(b + "attn.qkv.ln_c");
+      k.fc1_b = F(b + "mlp.fc1.ln_d"), k.fc1_c = F(b + "mlp.fc1.ln_c");
+    }
   }
   return w;
 }
@@ -325,6 +336,44 @@ void Engine::finalize() {
   if (missing_weights() != 0) {
     for (auto& kv : manifest_)
       if (!packed_.count(kv.first)) throw Error("missing key in state_dict: " + kv.first);
+  }
+  if (ln_fuse_) {
+    // LN(x) W^T + b = rstd (x (g*W)^T) - rstd mean colsum(g*W) + (W b_ln + b): fold norm1 into qkv and
+    // norm2 into fc1, in fp32 from the fp32 originals, rounded to bf16 once.  The fp32 copies are dropped.
+    auto slot = [&](const std::string& k, size_t bytes) {
+      Packed& pk = packed_[k];
+      if (pk.bytes != bytes) {
+        if (pk.ptr) DP_CUDA(cudaFree(pk.ptr));
+        DP_CUDA(cudaMalloc(&pk.ptr, bytes));
+        pk.bytes = bytes;
+      }
+      return pk.ptr;
+    };
+    for (const char* enc : {"encoder.patch_encoder.", "encoder.image_encoder.", "fov.encoder.0."}) {
+      for (int i = 0; i < 24; ++i) {
+        const std::string b = std::string(enc) + "blocks." + std::to_string(i) + ".";
+        const std::pair<const char*, const char*> pairs[2] = {{"attn.qkv", "norm1"}, {"mlp.fc1", "norm2"}};
+        for (auto& pr : pairs) {
+          const std::string lin = b + pr.first, nrm = b + pr.second;
+          auto rw = raw_.find(lin + ".weight"), rb = raw_.find(lin + ".bias");
+          if (rw == raw_.end() || rb == raw_.end()) throw Error("missing key in state_dict: " + lin + ".weight");
+          const int N = static_cast<int>(rb->second.bytes / 4);
+          ln_fold((const float*)rw->second.ptr, F(nrm + ".weight"), F(nrm + ".bias"), (const float*)rb->second.ptr,
+                  (bf16*)packed_.at(lin + ".weight").ptr, (float*)slot(lin + ".ln_c", N * 4), (float*)slot(lin + ".ln_d", N * 4),
+                  N, EMB, nullptr);
+        }
+      }
+    }
+    DP_CUDA(cudaStreamSynchronize(nullptr));
+    for (auto it = raw_.begin(); it != raw_.end();) {
+      if (ends_with(it->first, ".attn.qkv.weight") || ends_with(it->first, ".mlp.fc1.weight") ||
+          ends_with(it->first, ".attn.qkv.bias") || ends_with(it->first, ".mlp.fc1.bias")) {
+        cudaFree(it->second.ptr);
+        it = raw_.erase(it);
+      } else {
+        ++it;
+      }
+    }
   }
   vit_patch_ = vit_weights("encoder.patch_encoder.");
   vit_image_ = vit_weights("encoder.image_encoder.");
@@ -361,6 +410,7 @@ void Engine::finalize() {
   A35_ = alloc(MB * 36 * 576 * 768 * e);
   resid_ = (float*)alloc(T * EMB * 4);
   xn_ = alloc(T * EMB * e);
+  if (ln_fuse_) ln_stats_ = (float*)alloc(T * LN_SLOTS * 2 * 4);
   qkv_ = alloc(T * 3 * EMB * e);
   attn_ = alloc(T * EMB * e);
   hid_ = alloc(T * 4 * EMB * e);
@@ -473,8 +523,13 @@ void Engine::run_vits(int B, cudaStream_t s) {
   LnGroups lg;
   lg.n = 3;
   lg.end[0] = 35LL * B * SEQ, lg.end[1] = 36LL * B * SEQ, lg.end[2] = M;
+  // bf16 mode: norm1 / norm2 are folded into qkv / fc1 (common.cuh GemmOp::ln_stats); xn holds the RAW
+  // bf16 residual stream, written with its row statistics by this one launch for layer 0 and by the
+  // proj / fc2 epilogues from then on
+  const bool fuse = ln_fuse_ && std::is_same<T, bf16>::value;
+  if (fuse) ln_stats_cast(resid, (bf16*)xn, ln_stats_, M, s);
   for (int i = 0; i < 24; ++i) {
-    {
+    if (!fuse) {
       ProfScope ps(s, KC_LAYERNORM, static_cast<double>(M) * EMB * (4 + sizeof(T)));
       for (int g = 0; g < 3; ++g) lg.w[g] = vw[g]->blk[i].n1w, lg.b[g] = vw[g]->blk[i].n1b;
       layernorm_rows_grouped<T>(resid, xn, lg, M, s);
@@ -484,6 +539,10 @@ void Engine::run_vits(int B, cudaStream_t s) {
       op.N = 3 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.out = qkv, op.ldo = 3 * EMB;
       grouped(op, SEQ, false);
       for (int g = 0; g < 3; ++g) op.grp[g].Wt = vw[g]->blk[i].qkv_w, op.grp[g].bias = vw[g]->blk[i].qkv_b;
+      if (fuse) {
+        op.ln_stats = ln_stats_;
+        for (int g = 0; g < 3; ++g) op.grp[g].ln_c = vw[g]->blk[i].qkv_c;
+      }
       gemm(prec_, op, s);
     }
     {
@@ -502,9 +561,10 @@ void Engine::run_vits(int B, cudaStream_t s) {
       grouped(op, SEQ, false);
       for (int g = 0; g < 3; ++g)
         op.grp[g].Wt = vw[g]->blk[i].proj_w, op.grp[g].bias = vw[g]->blk[i].proj_b, op.grp[g].gamma = vw[g]->blk[i].g1;
+      if (fuse) op.ln_xb = xn, op.ln_stats_out = ln_stats_;
       gemm(prec_, op, s);
     }
-    {
+    if (!fuse) {
       ProfScope ps(s, KC_LAYERNORM, static_cast<double>(M) * EMB * (4 + sizeof(T)));
       for (int g = 0; g < 3; ++g) lg.w[g] = vw[g]->blk[i].n2w, lg.b[g] = vw[g]->blk[i].n2b;
       layernorm_rows_grouped<T>(resid, xn, lg, M, s);
@@ -514,6 +574,10 @@ void Engine::run_vits(int B, cudaStream_t s) {
       op.N = 4 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.act = ACT_GELU, op.out = hid, op.ldo = 4 * EMB;
       grouped(op, SEQ, false);
       for (int g = 0; g < 3; ++g) op.grp[g].Wt = vw[g]->blk[i].fc1_w, op.grp[g].bias = vw[g]->blk[i].fc1_b;
+      if (fuse) {
+        op.ln_stats = ln_stats_;
+        for (int g = 0; g < 3; ++g) op.grp[g].ln_c = vw[g]->blk[i].fc1_c;
+      }
       gemm(prec_, op, s);
     }
     {
@@ -523,6 +587,7 @@ void Engine::run_vits(int B, cudaStream_t s) {
       grouped(op, SEQ, false);
       for (int g = 0; g < 3; ++g)
         op.grp[g].Wt = vw[g]->blk[i].fc2_w, op.grp[g].bias = vw[g]->blk[i].fc2_b, op.grp[g].gamma = vw[g]->blk[i].g2;
+      if (fuse && i < 23) op.ln_xb = xn, op.ln_stats_out = ln_stats_;
       gemm(prec_, op, s);
     }
     if (i == 5 || i == 11) {
@@ -819,6 +884,36 @@ void Engine::gemm_test(int backend, const float* A, const float* Wt, const float
     op.A = a, op.Wt = w;
     bf16 *ob = nullptr, *orelu = nullptr;
     const size_t n_out = (size_t)M * N;
+    // 0x1000 LayerNorm-folded consumer (with 0x100): C = LN(A; g, b_ln) W^T + bias, g[k] = 1 + 0.25 sin(0.37 k),
+    //        b_ln[k] = 0.1 cos(0.11 k), computed from the RAW bf16 A + row statistics + folded weights;
+    // 0x2000 LayerNorm-emitting producer (with 0x200, N = 1024): C is (2M, N); rows [M, 2M) receive
+    //        (x - mean) * rstd rebuilt from the epilogue's bf16 copy and partial sums of the updated x
+    float *ln_stats = nullptr, *ln_c = nullptr, *ln_d = nullptr, *ln_g = nullptr, *ln_b = nullptr;
+    bf16* ln_xb = nullptr;
+    if (flags & 0x1000) {
+      DP_CHECK((flags & 0x100) && K == 1024 && bias != nullptr, "LN consumer test: 0x100, K = 1024, bias");
+      std::vector<float> hg(K), hb(K);
+      for (int k = 0; k < K; ++k) hg[k] = 1.f + 0.25f * std::sin(0.37f * k), hb[k] = 0.1f * std::cos(0.11f * k);
+      DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_g), K * 4, s));
+      DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_b), K * 4, s));
+      DP_CUDA(cudaMemcpyAsync(ln_g, hg.data(), K * 4, cudaMemcpyHostToDevice, s));
+      DP_CUDA(cudaMemcpyAsync(ln_b, hb.data(), K * 4, cudaMemcpyHostToDevice, s));
+      DP_CUDA(cudaStreamSynchronize(s));  // the host vectors go out of scope
+      DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_stats), (size_t)M * LN_SLOTS * 8, s));
+      DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_c), N * 4, s));
+      DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_d), N * 4, s));
+      ln_stats_cast(A, a, ln_stats, M, s);
+      ln_fold(Wt, ln_g, ln_b, bias, w, ln_c, ln_d, N, K, s);
+      op.ln_stats = ln_stats;
+      op.grp[0].M = M, op.grp[0].Wt = w, op.grp[0].bias = ln_d, op.grp[0].ln_c = ln_c;
+      op.bias = ln_d;
+    }
+    if (flags & 0x2000) {
+      DP_CHECK((flags & 0x200) && N == 1024, "LN producer test: 0x200, N = 1024");
+      DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_stats), (size_t)M * LN_SLOTS * 8, s));
+      DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_xb), n_out * 2, s));
+      op.ln_xb = ln_xb, op.ln_stats_out = ln_stats;
+    }
     if (flags & 0x200) {
       op.gamma = bias, op.res = C, op.res_f32 = 1, op.ldres = N;
     } else if (flags & (0x100 | 0x400)) {
@@ -838,6 +933,9 @@ void Engine::gemm_test(int backend, const float* A, const float* Wt, const float
     }
     gemm_tc(op, s);
     if (ob) convert<bf16, float>((flags & 0x800) ? orelu : ob, C, (long long)n_out, s);
+    if (flags & 0x2000) ln_apply_from_stats(ln_xb, ln_stats, C + n_out, M, s);
+    for (void* p : {(void*)ln_stats, (void*)ln_c, (void*)ln_d, (void*)ln_g, (void*)ln_b, (void*)ln_xb})
+      if (p) DP_CUDA(cudaFreeAsync(p, s));
     DP_CUDA(cudaFreeAsync(a, s));
     DP_CUDA(cudaFreeAsync(w, s));
     if (ob) DP_CUDA(cudaFreeAsync(ob, s));
@@ -937,14 +1035,20 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   auto B = [&](size_t bytes) { void* p = dalloc(bytes); bufs.push_back(p); return p; };
   GemmOp op;
   std::function<void()> run;
-  if (kind <= 2) {
+  if (kind <= 2 || (kind >= 11 && kind <= 13)) {
+    // 11 / 12 / 13: kinds 0 / 1 / 2 in their LayerNorm-folded forms (consumer, consumer + GELU, producer)
     op.M = M, op.N = N, op.K = K, op.lda = K;
     op.A = B((size_t)M * K * 2), op.Wt = B((size_t)N * K * 2), op.bias = (float*)B((size_t)N * 4);
-    if (kind == 2) {
+    if (kind == 2 || kind == 13) {
       float* r = (float*)B((size_t)M * N * 4);
       op.gamma = (float*)B((size_t)N * 4), op.res = r, op.res_f32 = 1, op.ldres = N, op.out = r, op.out_f32 = 1, op.ldo = N;
+      if (kind == 13) op.ln_xb = B((size_t)M * N * 2), op.ln_stats_out = (float*)B((size_t)M * LN_SLOTS * 8);
     } else {
-      op.out = B((size_t)M * N * 2), op.ldo = N, op.act = kind == 1 ? ACT_GELU : ACT_NONE;
+      op.out = B((size_t)M * N * 2), op.ldo = N, op.act = (kind == 1 || kind == 12) ? ACT_GELU : ACT_NONE;
+      if (kind >= 11) {
+        op.ln_stats = (float*)B((size_t)M * LN_SLOTS * 8);
+        op.grp[0].M = M, op.grp[0].Wt = op.Wt, op.grp[0].bias = op.bias, op.grp[0].ln_c = (float*)B((size_t)N * 4);
+      }
     }
     run = [&] { gemm_tc(op, s); };
   } else if (kind == 3) {
@@ -1004,7 +1108,7 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   DP_CUDA(cudaEventCreate(&a));
   DP_CUDA(cudaEventCreate(&b));
   float ms = 0.f;
-  if (kind >= 5) {
+  if (kind >= 5 && kind <= 10) {
     // HBM-bound kernels with working sets near the 126 MB L2: overwrite a 256 MB buffer before every
     // timed launch so inputs come from HBM, and time each launch on its own
     const size_t FLUSH = 256u << 20;

@@ -17,6 +17,8 @@ struct VitWeights {
   struct Block {
     const float *n1w, *n1b, *qkv_b, *proj_b, *g1, *n2w, *n2b, *fc1_b, *fc2_b, *g2;
     const void *qkv_w, *proj_w, *fc1_w, *fc2_w;
+    // LayerNorm-folded form (bf16 mode): qkv_w / fc1_w then hold bf16(g * W), qkv_b / fc1_b hold W b_ln + b
+    const float *qkv_c = nullptr, *fc1_c = nullptr;  // column sums of the folded weights
   } blk[24];
 };
 
@@ -108,6 +110,8 @@ class Engine {
   size_t himg_bytes_ = 0;
   float* hdepth_ = nullptr;
   size_t hdepth_bytes_ = 0;
+  bool ln_fuse_ = false;       // bf16 mode: LayerNorm folded into qkv / fc1 (DEPTHPRO_LN_FUSE=0 disables)
+  float* ln_stats_ = nullptr;  // (tokens, LN_SLOTS, 2) partial row sums of the residual stream
   float* colorize_mm_ = nullptr;
   int* unproject_scratch_ = nullptr;
   size_t unproject_scratch_ints_ = 0;

@@ -352,11 +352,14 @@ __device__ __forceinline__ void prefetch_res4(const float* __restrict__ res, lon
   for (int i = 0; i < 8; ++i)
     rv[i] = (4 * i + (lane >> 3)) < cs.nv ? *reinterpret_cast<const float4*>(p + 4 * i * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
+template <bool LN_OUT>
 __device__ __forceinline__ void epi_rows4_resid32(float* __restrict__ out, long long ld, const ColSlab& cs, int n0,
                                                   uint32_t stg, int lane, const float4 b4, const float4 g4,
-                                                  const float4 (&rv)[8]) {
+                                                  const float4 (&rv)[8], bf16* __restrict__ xb, float (&ls)[8],
+                                                  float (&lq)[8]) {
   const int rg = lane >> 3, cq = lane & 7;
-  float* p = out + (cs.row0 + rg) * ld + n0 + cq * 4;
+  const long long off = (cs.row0 + rg) * ld + n0 + cq * 4;
+  float* p = out + off;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = 4 * i + rg;
@@ -366,7 +369,19 @@ __device__ __forceinline__ void epi_rows4_resid32(float* __restrict__ out, long 
     o.y = fmaf(a.y + b4.y, g4.y, rv[i].y);
     o.z = fmaf(a.z + b4.z, g4.z, rv[i].z);
     o.w = fmaf(a.w + b4.w, g4.w, rv[i].w);
-    if (row < cs.nv) *reinterpret_cast<float4*>(p + 4 * i * ld) = o;
+    if (row < cs.nv) {
+      *reinterpret_cast<float4*>(p + 4 * i * ld) = o;
+      if constexpr (LN_OUT) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo), pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(xb + off + 4 * i * ld) = pk;
+      }
+    }
+    if constexpr (LN_OUT) {
+      ls[i] += (o.x + o.y) + (o.z + o.w);
+      lq[i] += fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+    }
   }
 }
 
@@ -379,7 +394,10 @@ __device__ __forceinline__ void epi_rows4_resid32(float* __restrict__ out, long 
 //   EPI_RES32 fp32 residual update in place (proj / fc2): smem transpose, column-per-lane, deep prefetch
 //   EPI_MISC  everything else: ConvT scatter and dual (x, relu(x)) stores via TMA, direct stores for
 //             patch-embed placement, fused dots, small / odd shapes
-enum { EPI_TMA = 0, EPI_RES32 = 1, EPI_MISC = 2, EPI_TMA2 = 3 };
+//   EPI_TMA_LN   EPI_TMA for a LayerNorm-folded GEMM (qkv / fc1): acc * rstd[m] - rstd[m] * mean[m] * c[n] + d[n]
+//   EPI_RES32_LN EPI_RES32 that also emits bf16(x) and per-row partial (sum, sum of squares) for the next
+//                LayerNorm-folded GEMM (common.cuh GemmOp::ln_stats)
+enum { EPI_TMA = 0, EPI_RES32 = 1, EPI_MISC = 2, EPI_TMA2 = 3, EPI_TMA_LN = 4, EPI_RES32_LN = 5 };
 
 template <int BN, int CL, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -569,7 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       const int nt = t % g.n_tiles, mu = t / g.n_tiles;
-      long long m;
+      long long m, m_a = 0;  // output row / A row of this thread
       bool valid;
       int gi = 0;
       if (op.a_mode == A_CONV3X3) {
@@ -586,6 +604,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m_local = ((mu - g.unit_start[gi]) * CL + crank) * BM + row;
         valid = m_local < op.grp[gi].M;
         m = op.grp[gi].o_row_off + m_local;
+        m_a = op.grp[gi].a_row_off + m_local;
       }
       const GemmGroup& gp = op.grp[gi];
       const bool active = (BN >= 64 || grp == 0);
@@ -616,7 +635,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
         continue;
       }
-      if constexpr (EPI == EPI_RES32) {
+      if constexpr (EPI == EPI_RES32 || EPI == EPI_RES32_LN) {
+        constexpr bool LN_OUT = EPI == EPI_RES32_LN;
+        float ls[8], lq[8];  // LN_OUT: this lane's partial row sums of rows (lane >> 3) + 4 i
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ls[i] = lq[i] = 0.f;
         // ---- proj / fc2: out = res + gamma * (acc + bias), fp32 in place, column-per-lane through smem.
         // The residual values of TWO chunks are in flight ahead of the one being processed; the first
         // two are requested before the accumulator is even ready.
@@ -654,26 +677,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
           }
           __syncwarp();
-          epi_rows4_resid32(reinterpret_cast<float*>(op.out), op.ldo, cs, col0 + c, tile, lane, b4, g4, resv);
+          epi_rows4_resid32<LN_OUT>(reinterpret_cast<float*>(op.out), op.ldo, cs, col0 + c, tile, lane, b4, g4, resv,
+                                    reinterpret_cast<bf16*>(op.ln_xb), ls, lq);
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j) resv[j] = resn[j], resn[j] = resn2[j];
           b4 = b4n, g4 = g4n;
         }
-      } else if constexpr (EPI == EPI_TMA || EPI == EPI_TMA2) {
+        if constexpr (LN_OUT) {
+          // the 8 lanes that share a row add up their 16 columns x 4 chunks; slot = this warp's 128-column slice
+          static_assert(COLS_PER_GRP == 128, "LN partial sums are kept per 128-column slice");
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float sv = ls[i], qv = lq[i];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              sv += __shfl_xor_sync(0xffffffffu, sv, o);
+              qv += __shfl_xor_sync(0xffffffffu, qv, o);
+            }
+            const int rr = 4 * i + (lane >> 3);
+            if ((lane & 7) == 0 && rr < cs.nv)
+              *reinterpret_cast<float2*>(op.ln_stats_out + ((cs.row0 + rr) * LN_SLOTS + (col0 >> 7)) * 2) = make_float2(sv, qv);
+          }
+        }
+      } else if constexpr (EPI == EPI_TMA || EPI == EPI_TMA2 || EPI == EPI_TMA_LN) {
+        constexpr bool LN_IN = EPI == EPI_TMA_LN;
         // ---- row-per-thread math, bf16 output through a swizzled smem slab + TMA store.  Software
         // pipelined: as soon as chunk c has been copied out of the TMEM-load registers (bias add), the
         // TMEM load, bias and residual of chunk c+1 are issued and fly during the math of chunk c.
         static_assert(COLS_PER_GRP % 64 == 0, "EPI_TMA works on 64-column slabs");
         const uint32_t slab = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;
         const uint32_t slab_relu = EPI == EPI_TMA2 ? slab + 4096 : 0;
-        const bool has_res = op.res != nullptr && valid;
+        const bool has_res = !LN_IN && op.res != nullptr && valid;
         const bf16* resp = reinterpret_cast<const bf16*>(op.res) + m * op.ldres + col0;
         uint32_t r[32];
         float bias[32];
+        float lnc[LN_IN ? 32 : 1];
+        float ln_rs = 0.f, ln_nm = 0.f;  // rstd and -rstd * mean of this thread's row
+        if constexpr (LN_IN) {
+          if (valid) {
+            const float4* sp = reinterpret_cast<const float4*>(op.ln_stats + m_a * (2 * LN_SLOTS));
+            const float4 p0 = sp[0], p1 = sp[1], p2 = sp[2], p3 = sp[3];  // (s0 q0 s1 q1) (s2 q2 s3 q3) ...
+            const float sum = ((p0.x + p0.z) + (p1.x + p1.z)) + ((p2.x + p2.z) + (p3.x + p3.z));
+            const float sq = ((p0.y + p0.w) + (p1.y + p1.w)) + ((p2.y + p2.w) + (p3.y + p3.w));
+            const float mean = sum * (1.f / 1024.f);
+            const float var = fmaxf(fmaf(-mean, mean, sq * (1.f / 1024.f)), 0.f);
+            ln_rs = 1.f / sqrtf(var + 1e-6f);
+            ln_nm = -ln_rs * mean;
+          }
+        }
         uint4 resc[4], resn[4];
         auto prefetch = [&](int c) {  // bias + residual of the chunk at column offset c
           if (gp.bias) load32<float>(gp.bias + (op.bias_mod ? (col0 + c) % op.bias_mod : col0 + c), bias);
+          if constexpr (LN_IN) load32<float>(gp.ln_c + col0 + c, lnc);
           if (has_res) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) resn[i] = reinterpret_cast<const uint4*>(resp + c)[i];
@@ -691,8 +747,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool more = cc + 32 < COLS_PER_GRP;
             float v[32];
             ptx::tmem_ld_wait();
+            if constexpr (LN_IN) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (gp.bias ? bias[j] : 0.f);
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), ln_rs, fmaf(ln_nm, lnc[j], bias[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (gp.bias ? bias[j] : 0.f);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) resc[i] = resn[i];
             if (more) {
@@ -1015,6 +1076,24 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   const bool tma_epi = g.tma_out && !(op.res && op.res_f32);
   const int epi = resid32 ? EPI_RES32 : (tma_epi ? (op.out_relu ? EPI_TMA2 : EPI_TMA) : EPI_MISC);
   g.tma_out = tma_epi ? 1 : 0;
+  if (op.ln_stats != nullptr || op.ln_xb != nullptr) {
+    // LayerNorm-folded forms exist for the ViT shapes only (BN = 256)
+    DP_CHECK(bn == 256 && op.a_mode == A_ROWMAJOR, "LN-folded GEMM: N must be a multiple of 256");
+    if (op.ln_stats != nullptr) {
+      DP_CHECK(epi == EPI_TMA && op.K == 1024 && op.res == nullptr && op.res2 == nullptr && op.gamma == nullptr,
+               "LN-folded consumer: bf16 row-major output, K = 1024, no residual");
+      for (int i = 0; i < op.ngroups; ++i)
+        DP_CHECK(op.grp[i].ln_c != nullptr && op.grp[i].bias != nullptr && op.grp[i].gamma == nullptr, "LN-folded consumer: ln_c / bias per group");
+      if (cl == 2) launch<256, 2, EPI_TMA_LN>(op, g, *tmA, tmW, stream);
+      else launch<256, 1, EPI_TMA_LN>(op, g, *tmA, tmW, stream);
+    } else {
+      DP_CHECK(epi == EPI_RES32 && op.N == 1024 && op.ldo == 1024 && op.ln_stats_out != nullptr,
+               "LN-folded producer: fp32 residual form with N = 1024");
+      if (cl == 2) launch<256, 2, EPI_RES32_LN>(op, g, *tmA, tmW, stream);
+      else launch<256, 1, EPI_RES32_LN>(op, g, *tmA, tmW, stream);
+    }
+    return;
+  }
 #define DP_LAUNCH(BN_, CL_)                                                          \
   do {                                                                               \
     if (epi == EPI_RES32) launch<BN_, CL_, EPI_RES32>(op, g, *tmA, tmW, stream);     \

@@ -235,6 +235,78 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// LayerNorm folded into the ViT GEMMs (common.cuh GemmOp::ln_stats)
+// ------------------------------------------------------------------------------------------
+// Entry of the folded chain (the residual stream right after patch embed): x fp32 -> raw bf16 copy +
+// per-row (sum, sum of squares) in slot 0, the other slots zero.  Later layers get both from the
+// proj / fc2 epilogues.
+__global__ void __launch_bounds__(256) ln_stats_cast_kernel(const float* __restrict__ in, bf16* __restrict__ xb,
+                                                            float* __restrict__ stats, long long rows) {
+  const long long d = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (d >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(in + d * 1024);
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = src[lane + 32 * i];
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    q += fmaf(v[i].x, v[i].x, v[i].y * v[i].y) + fmaf(v[i].z, v[i].z, v[i].w * v[i].w);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x, v[i].y), hi = __floats2bfloat162_rn(v[i].z, v[i].w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo), pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(xb + d * 1024 + (lane + 32 * i) * 4) = pk;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
+  if (lane < 2 * LN_SLOTS) stats[d * (2 * LN_SLOTS) + lane] = lane == 0 ? s : (lane == 1 ? q : 0.f);
+}
+
+// Weight fold, one block per output feature n (K = 1024):  wf[n,k] = bf16(g[k] * w[n,k]),
+// c[n] = sum_k wf[n,k] (of the ROUNDED values: it cancels the mean of what the tensor core multiplies),
+// d[n] = bias[n] + sum_k b_ln[k] * w[n,k].
+__global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ w, const float* __restrict__ g,
+                                                      const float* __restrict__ b_ln, const float* __restrict__ bias,
+                                                      bf16* __restrict__ wf, float* __restrict__ c, float* __restrict__ d,
+                                                      int K) {
+  const int n = blockIdx.x;
+  float cs = 0.f, ds = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float wv = w[static_cast<long long>(n) * K + k];
+    const bf16 r = __float2bfloat16_rn(g[k] * wv);
+    wf[static_cast<long long>(n) * K + k] = r;
+    cs += __bfloat162float(r);
+    ds = fmaf(b_ln[k], wv, ds);
+  }
+  __shared__ float red[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o), ds += __shfl_xor_sync(0xffffffffu, ds, o);
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = cs, red[1][threadIdx.x >> 5] = ds;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < 8; ++i) a += red[0][i], b += red[1][i];
+    c[n] = a;
+    d[n] = bias[n] + b;
+  }
+}
+
+// Test helper: y[m,n] = (xb[m,n] - mean_m) * rstd_m from the producer's outputs (fp32 out).
+__global__ void ln_apply_from_stats_kernel(const bf16* __restrict__ xb, const float* __restrict__ stats,
+                                           float* __restrict__ y, long long rows) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= rows * 1024) return;
+  const long long m = idx >> 10;
+  float s = 0.f, q = 0.f;
+  for (int i = 0; i < LN_SLOTS; ++i) s += stats[(m * LN_SLOTS + i) * 2], q += stats[(m * LN_SLOTS + i) * 2 + 1];
+  const float mean = s * (1.f / 1024.f);
+  const float var = fmaxf(q * (1.f / 1024.f) - mean * mean, 0.f);
+  y[idx] = (__bfloat162float(xb[idx]) - mean) * (1.f / sqrtf(var + 1e-6f));
+}
+
 __global__ void merge_f32_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int C,
                                  RowMap map) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -685,6 +757,20 @@ template void layernorm_rows_grouped<float>(const float*, float*, const LnGroups
 template void layernorm_rows_grouped<bf16>(const float*, bf16*, const LnGroups&, long long, cudaStream_t);
 template void layernorm_rows<float>(const float*, float*, const float*, const float*, long long, RowMap, int, cudaStream_t);
 template void layernorm_rows<bf16>(const float*, bf16*, const float*, const float*, long long, RowMap, int, cudaStream_t);
+
+void ln_stats_cast(const float* in, bf16* xb, float* stats, long long rows, cudaStream_t s) {
+  ln_stats_cast_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(in, xb, stats, rows);
+  DP_LAUNCH_CHECK();
+}
+void ln_fold(const float* w, const float* g, const float* b_ln, const float* bias, bf16* wf, float* c, float* d, int N,
+             int K, cudaStream_t s) {
+  ln_fold_kernel<<<N, 256, 0, s>>>(w, g, b_ln, bias, wf, c, d, K);
+  DP_LAUNCH_CHECK();
+}
+void ln_apply_from_stats(const bf16* xb, const float* stats, float* y, long long rows, cudaStream_t s) {
+  ln_apply_from_stats_kernel<<<blocks_for(rows * 1024, 256), 256, 0, s>>>(xb, stats, y, rows);
+  DP_LAUNCH_CHECK();
+}
 
 void merge_rows_f32(const float* in, float* out, int B, int C, RowMap map, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * map.S * map.S * C;

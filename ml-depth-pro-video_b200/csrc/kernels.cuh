@@ -63,6 +63,15 @@ void im2col_nhwc(const T* x, T* cols, int B, int H, int W, int C, int k, int str
 template <typename T>
 void fov_final(const T* x, const float* w_hwio, const float* bias, float* fov_deg, int B, cudaStream_t s);
 
+// ---- LayerNorm folded into the ViT GEMMs (common.cuh GemmOp::ln_stats) -------------------------
+// x fp32 (rows, 1024) -> raw bf16 copy + per-row partial sums [rows][LN_SLOTS][2] (slot 0 filled)
+void ln_stats_cast(const float* in, bf16* xb, float* stats, long long rows, cudaStream_t s);
+// wf = bf16(g * w) [N,K], c = colsum(wf), d = bias + w b_ln   (w fp32 [N,K], K = 1024)
+void ln_fold(const float* w, const float* g, const float* b_ln, const float* bias, bf16* wf, float* c, float* d, int N,
+             int K, cudaStream_t s);
+// test helper: (xb - mean) * rstd from the producer epilogue's outputs
+void ln_apply_from_stats(const bf16* xb, const float* stats, float* y, long long rows, cudaStream_t s);
+
 // ---- metric depth epilogue ----------------------------------------------------------------
 // f_px[b] = f_px_in ? f_px_in[b] : 0.5*W / tan(0.5*deg2rad(fov_deg[b]))   (depth_pro.py:282-283)
 void compute_fpx(const float* fov_deg, const float* f_px_in, int W, float* f_px, int B, cudaStream_t s);

@@ -93,6 +93,57 @@ def test_gemm_bf16_fp32_residual_epilogue(M, N, K):
     assert relerr(C, ref) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,act,offset", [(300, 256, 0, 0.0), (21349, 3072, 0, 0.3), (21349, 4096, 2, -0.5),
+                                            (577, 1024, 0, 2.0)])
+def test_gemm_bf16_layernorm_folded_consumer(M, N, act, offset):
+    """qkv / fc1 with norm1 / norm2 folded in: LN(A) W^T + b computed as rstd * (A (g*W)^T) - rstd * mean *
+    colsum(g*W) + (W b_ln + b) from the RAW bf16 rows and their (sum, sum of squares)."""
+    K = 1024
+    g = torch.Generator(device=DEV).manual_seed(5 * M + N)
+    # rows with different scales and a common offset: the mean term must cancel
+    A = torch.randn(M, K, device=DEV, generator=g) * (0.5 + torch.rand(M, 1, device=DEV, generator=g) * 4) + offset
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    got = _gemm(1, A, W, b, act | 0x100 | 0x1000)
+    k = torch.arange(K, device=DEV, dtype=torch.float32)
+    gam, bet = 1 + 0.25 * torch.sin(0.37 * k), 0.1 * torch.cos(0.11 * k)
+    y = F.layer_norm(A.double(), (K,), gam.double(), bet.double(), eps=1e-6)
+    ref = _ref_gemm(y, W, b, act)
+    # the fp32 LayerNorm + bf16 GEMM path this replaces rounds LN(A) and W to bf16 (2^-9 relative each) before a
+    # K = 1024 dot product; the folded form rounds A and g*W instead.  Same error budget: a few 1e-3 of the
+    # output scale, plus the bf16 rounding of the output itself.
+    err = (got - ref).abs()
+    scale = float(ref.abs().mean())
+    assert float(err.mean()) < 4e-3 * scale, (float(err.mean()), scale)
+    assert float(err.max()) < 6e-2 * float(ref.abs().max()), float(err.max())
+    # and against the stand-alone path's own error on the same data
+    base = _ref_gemm(_bf16r(y.float()), _bf16r(W), b, act)
+    assert float(err.mean()) < 2.5 * float((base - ref).abs().mean()) + 2e-3 * scale
+
+
+@pytest.mark.parametrize("M,K", [(300, 128), (21349, 1024), (21349, 4096)])
+def test_gemm_bf16_layernorm_emitting_producer(M, K):
+    """proj / fc2 form that also emits what the next folded GEMM needs: bf16(x) and per-row partial sums."""
+    N = 1024
+    g = torch.Generator(device=DEV).manual_seed(M + K)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    res = torch.randn(M, N, device=DEV, generator=g) * 3 + 0.7
+    C = torch.zeros(2 * M, N, device=DEV)
+    C[:M] = res
+    _capi.check(lib().dp_gemm_test(engine(), 1, A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K,
+                                   0x200 | 0x2000, stream()))
+    torch.cuda.synchronize()
+    ref = res.double() + b.double() * (_bf16r(A).double() @ _bf16r(W).double().t() + b.double())
+    assert relerr(C[:M], ref) < 2e-5                      # the residual update itself is unchanged
+    ln = F.layer_norm(C[:M].double(), (N,), eps=1e-6)     # statistics of the UPDATED stream
+    err = (C[M:].double() - ln).abs()
+    # (bf16(x) - mean) * rstd: bf16 rounding of x relative to the row's spread
+    assert float(err.max()) < 2.0 ** -8 * float((C[:M].abs().max(dim=1).values / C[:M].std(dim=1)).max()) + 1e-4
+    assert float(err.mean()) < 2e-3
+
+
 @pytest.mark.parametrize("S,Cout,K,dual", [(32, 64, 128, 0), (96, 256, 256, 0), (192, 256, 256, 1), (32, 128, 64, 1)])
 def test_gemm_bf16_convt_pixel_shuffle_epilogue(S, Cout, K, dual):
     """ConvTranspose2d k2 s2 as GEMM (N = (dy, dx, o)) + pixel shuffle through a 5-D TMA store; dual = ReLU twin."""
