@@ -1032,7 +1032,17 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
     return p;
   };
   std::vector<void*> bufs;
-  auto B = [&](size_t bytes) { void* p = dalloc(bytes); bufs.push_back(p); return p; };
+  // Tensor-core operands are filled with random bf16 values unless DEPTHPRO_BENCH_DATA=zeros: measured on
+  // B200, a GEMM on zero-filled operands runs at the full 1965 MHz (913 W), the same kernel on real data is
+  // power-capped to ~1.5 GHz -- zeros overstate the sustained rate by ~40 %.
+  static const bool zeros = [] { const char* e = getenv("DEPTHPRO_BENCH_DATA"); return e && std::string(e) == "zeros"; }();
+  const bool tensor_kind = kind <= 4 || (kind >= 11 && kind <= 13);
+  auto B = [&](size_t bytes) {
+    void* p = dalloc(bytes);
+    if (tensor_kind && !zeros && bytes >= 2) fill_random_bf16(p, bytes, 0x9e3779b9u + static_cast<unsigned>(bufs.size()), s);
+    bufs.push_back(p);
+    return p;
+  };
   GemmOp op;
   std::function<void()> run;
   if (kind <= 2 || (kind >= 11 && kind <= 13)) {

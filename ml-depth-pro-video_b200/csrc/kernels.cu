@@ -23,44 +23,60 @@ inline int blocks_for(long long n, int threads) { return static_cast<int>((n + t
 // resize: src/depth_pro/depth_pro.py:125-132 (ToTensor, Normalize) + :273-279 (F.interpolate,
 // bilinear, align_corners=False, no antialias).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float src_px(const void* src, int fmt, int b, int c, int y, int x, int H, int W) {
-  if (fmt == 0) return reinterpret_cast<const float*>(src)[((static_cast<long long>(b) * 3 + c) * H + y) * W + x];
-  const uint8_t u = reinterpret_cast<const uint8_t*>(src)[((static_cast<long long>(b) * H + y) * W + x) * 3 + c];
-  const float t = __fdiv_rn(static_cast<float>(u), 255.f);  // ToTensor
-  return __fmul_rn(__fsub_rn(t, 0.5f), 2.f);                // Normalize(0.5, 0.5)
-}
-
-__global__ void resize_kernel(const void* __restrict__ src, int fmt, int B, int H, int W, float* __restrict__ x) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * 3 * IMG * IMG;
-  if (idx >= total) return;
-  const int ox = static_cast<int>(idx % IMG);
-  const int oy = static_cast<int>((idx / IMG) % IMG);
-  const int c = static_cast<int>((idx / (static_cast<long long>(IMG) * IMG)) % 3);
-  const int b = static_cast<int>(idx / (3LL * IMG * IMG));
-  if (H == IMG && W == IMG) {
-    x[idx] = src_px(src, fmt, b, c, oy, ox, H, W);
-    return;
+// One thread = one output pixel, all three channels (the index arithmetic and the bilinear weights are
+// shared); one block = 256 consecutive pixels of one output row: 32-bit arithmetic only, planar stores
+// coalesced across the warp.  uint8 sources go through a 256-entry table of the exact
+// ToTensor + Normalize values ((u / 255 - 0.5) * 2, each step rounded like ATen does).
+template <int FMT>
+__global__ void __launch_bounds__(256) resize_kernel(const void* __restrict__ src, int H, int W, float* __restrict__ x) {
+  __shared__ float lut[256];
+  if (FMT == 1) {
+    const float t = __fdiv_rn(static_cast<float>(threadIdx.x), 255.f);  // ToTensor
+    lut[threadIdx.x] = __fmul_rn(__fsub_rn(t, 0.5f), 2.f);              // Normalize(0.5, 0.5)
+    __syncthreads();
   }
-  const float sh = static_cast<float>(H) / IMG, sw = static_cast<float>(W) / IMG;
-  // ATen's CPU kernels (x86-64 AVX2 / AVX-512 builds) contract scale*(dst+0.5)-0.5 into one FMA;
-  // the single rounding matters: the product is O(1e3), so an unfused multiply moves the source
-  // index by up to ~5e-5 whenever in/out is not exactly representable.
-  float fy = fmaf(sh, oy + 0.5f, -0.5f);
-  float fx = fmaf(sw, ox + 0.5f, -0.5f);
-  fy = fy < 0.f ? 0.f : fy;
-  fx = fx < 0.f ? 0.f : fx;
-  int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-  y0 = y0 > H - 1 ? H - 1 : y0;
-  x0 = x0 > W - 1 ? W - 1 : x0;
-  const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
-  const float ly1 = fminf(fmaxf(fy - y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - x0, 0.f), 1.f);
+  const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y, b = blockIdx.z;
+  int y0 = oy, x0 = ox, y1 = oy, x1 = ox;
+  float ly1 = 0.f, lx1 = 0.f;
+  const bool same = H == IMG && W == IMG;
+  if (!same) {
+    const float sh = static_cast<float>(H) / IMG, sw = static_cast<float>(W) / IMG;
+    // ATen's CPU kernels (x86-64 AVX2 / AVX-512 builds) contract scale*(dst+0.5)-0.5 into one FMA;
+    // the single rounding matters: the product is O(1e3), so an unfused multiply moves the source
+    // index by up to ~5e-5 whenever in/out is not exactly representable.
+    float fy = fmaf(sh, oy + 0.5f, -0.5f);
+    float fx = fmaf(sw, ox + 0.5f, -0.5f);
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    y0 = y0 > H - 1 ? H - 1 : y0;
+    x0 = x0 > W - 1 ? W - 1 : x0;
+    y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    ly1 = fminf(fmaxf(fy - y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - x0, 0.f), 1.f);
+  }
   const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-  const float p00 = src_px(src, fmt, b, c, y0, x0, H, W), p01 = src_px(src, fmt, b, c, y0, x1, H, W);
-  const float p10 = src_px(src, fmt, b, c, y1, x0, H, W), p11 = src_px(src, fmt, b, c, y1, x1, H, W);
-  const float t0 = __fadd_rn(__fmul_rn(lx0, p00), __fmul_rn(lx1, p01));
-  const float t1 = __fadd_rn(__fmul_rn(lx0, p10), __fmul_rn(lx1, p11));
-  x[idx] = __fadd_rn(__fmul_rn(ly0, t0), __fmul_rn(ly1, t1));
+  float* dst = x + (static_cast<size_t>(b) * 3 * IMG + oy) * IMG + ox;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float p00, p01, p10, p11;
+    if (FMT == 1) {
+      const uint8_t* im = reinterpret_cast<const uint8_t*>(src) + static_cast<size_t>(b) * H * W * 3 + c;
+      const size_t r0 = static_cast<size_t>(y0) * W, r1 = static_cast<size_t>(y1) * W;
+      p00 = lut[im[(r0 + x0) * 3]], p01 = lut[im[(r0 + x1) * 3]];
+      p10 = lut[im[(r1 + x0) * 3]], p11 = lut[im[(r1 + x1) * 3]];
+    } else {
+      const float* im = reinterpret_cast<const float*>(src) + (static_cast<size_t>(b) * 3 + c) * H * W;
+      const size_t r0 = static_cast<size_t>(y0) * W, r1 = static_cast<size_t>(y1) * W;
+      p00 = im[r0 + x0], p01 = im[r0 + x1], p10 = im[r1 + x0], p11 = im[r1 + x1];
+    }
+    float v = p00;
+    if (!same) {
+      const float t0 = __fadd_rn(__fmul_rn(lx0, p00), __fmul_rn(lx1, p01));
+      const float t1 = __fadd_rn(__fmul_rn(lx0, p10), __fmul_rn(lx1, p11));
+      v = __fadd_rn(__fmul_rn(ly0, t0), __fmul_rn(ly1, t1));
+    }
+    dst[static_cast<size_t>(c) * IMG * IMG] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -395,35 +411,33 @@ __global__ void fpx_kernel(const float* fov_deg, const float* f_px_in, int W, fl
   }
 }
 
-__global__ void depth_epilogue_kernel(const float* __restrict__ canon, const float* __restrict__ f_px, int B, int H,
-                                      int W, float* __restrict__ depth) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * W;
-  if (idx >= total) return;
-  const int ox = static_cast<int>(idx % W), oy = static_cast<int>((idx / W) % H);
-  const int b = static_cast<int>(idx / (static_cast<long long>(H) * W));
+// one thread = one output pixel, one block = 256 consecutive pixels of one output row (32-bit arithmetic)
+__global__ void __launch_bounds__(256) depth_epilogue_kernel(const float* __restrict__ canon, const float* __restrict__ f_px,
+                                                             int H, int W, float* __restrict__ depth) {
+  const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y, b = blockIdx.z;
+  if (ox >= W) return;
   const float scale = static_cast<float>(W) / f_px[b];
-  const float* src = canon + static_cast<long long>(b) * IMG * IMG;
+  const float* src = canon + static_cast<size_t>(b) * IMG * IMG;
   float inv;
   if (H == IMG && W == IMG) {
-    inv = src[static_cast<long long>(oy) * IMG + ox] * scale;
+    inv = src[oy * IMG + ox] * scale;
   } else {
     const float sh = static_cast<float>(IMG) / H, sw = static_cast<float>(IMG) / W;
     float fy = fmaf(sh, oy + 0.5f, -0.5f);  // see resize_kernel
     float fx = fmaf(sw, ox + 0.5f, -0.5f);
     fy = fy < 0.f ? 0.f : fy;
     fx = fx < 0.f ? 0.f : fx;
-    int y0 = min(static_cast<int>(fy), IMG - 1), x0 = min(static_cast<int>(fx), IMG - 1);
+    const int y0 = min(static_cast<int>(fy), IMG - 1), x0 = min(static_cast<int>(fx), IMG - 1);
     const int y1 = y0 + (y0 < IMG - 1 ? 1 : 0), x1 = x0 + (x0 < IMG - 1 ? 1 : 0);
     const float ly1 = fminf(fmaxf(fy - y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - x0, 0.f), 1.f);
     const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-    const float p00 = src[static_cast<long long>(y0) * IMG + x0] * scale, p01 = src[static_cast<long long>(y0) * IMG + x1] * scale;
-    const float p10 = src[static_cast<long long>(y1) * IMG + x0] * scale, p11 = src[static_cast<long long>(y1) * IMG + x1] * scale;
+    const float p00 = src[y0 * IMG + x0] * scale, p01 = src[y0 * IMG + x1] * scale;
+    const float p10 = src[y1 * IMG + x0] * scale, p11 = src[y1 * IMG + x1] * scale;
     const float t0 = __fadd_rn(__fmul_rn(lx0, p00), __fmul_rn(lx1, p01));
     const float t1 = __fadd_rn(__fmul_rn(lx0, p10), __fmul_rn(lx1, p11));
     inv = __fadd_rn(__fmul_rn(ly0, t0), __fmul_rn(ly1, t1));
   }
-  depth[idx] = 1.0f / fminf(fmaxf(inv, 1e-4f), 1e4f);
+  depth[(static_cast<size_t>(b) * H + oy) * W + ox] = 1.0f / fminf(fmaxf(inv, 1e-4f), 1e4f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -522,7 +536,8 @@ __global__ void unproject_write_kernel(const float* __restrict__ depth, const ui
     for (int i = 0; i < wid; ++i) before += warp_cnt[i];
     if (ok) {
       const long long dst = blk_off + before + __popc(bal & ((1u << lane) - 1));
-      const int u = static_cast<int>(p % W), v = static_cast<int>(p / W);
+      const unsigned pu = static_cast<unsigned>(p);  // n < 2^31 (checked on the host): 32-bit division
+      const int v = static_cast<int>(pu / static_cast<unsigned>(W)), u = static_cast<int>(pu - static_cast<unsigned>(v) * W);
       // x = -(u - W/2) * z / f ; y = -(v - H/2) * z / f ; z = d
       xyz[dst * 3 + 0] = __fdiv_rn(__fmul_rn(-(static_cast<float>(u) - cx), d), f);
       xyz[dst * 3 + 1] = __fdiv_rn(__fmul_rn(-(static_cast<float>(v) - cy), d), f);
@@ -556,16 +571,22 @@ __global__ void minmax_init_kernel(unsigned* mm) {
   mm[0] = 0xffffffffu;
   mm[1] = 0u;
 }
-__global__ void minmax_kernel(const float* __restrict__ d, long long n, unsigned* mm) {
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ d, long long n, unsigned* mm) {
   unsigned lo = 0xffffffffu, hi = 0u;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float v = d[i];
+  auto take = [&](float v) {
     if (!isnan(v)) {
       const unsigned o = f2ord(v);
       lo = min(lo, o), hi = max(hi, o);
     }
+  };
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n4 = (reinterpret_cast<uintptr_t>(d) % 16 == 0) ? n / 4 : 0;  // 16-byte loads when aligned
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 v = reinterpret_cast<const float4*>(d)[i];
+    take(v.x), take(v.y), take(v.z), take(v.w);
   }
+  for (long long i = n4 * 4 + tid; i < n; i += nth) take(d[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -576,25 +597,53 @@ __global__ void minmax_kernel(const float* __restrict__ d, long long n, unsigned
     atomicMax(&mm[1], hi);
   }
 }
-__global__ void colorize_kernel(const float* __restrict__ d, long long n, const unsigned* __restrict__ mm,
-                                const uint8_t* __restrict__ lut, void* __restrict__ out) {
-  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= n) return;
-  const float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
-  const float v = d[i];
-  const float norm = __fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo));
+// one thread = 4 consecutive pixels: one 16-byte load, 12 bytes (three 32-bit words) or four uint16 out
+__global__ void __launch_bounds__(256) colorize_kernel(const float* __restrict__ d, long long n,
+                                                       const unsigned* __restrict__ mm, const uint8_t* __restrict__ lut,
+                                                       void* __restrict__ out, int vec) {
+  __shared__ uint8_t slut[768];
   if (lut) {
-    uint8_t* o = reinterpret_cast<uint8_t*>(out) + i * 3;
-    if (isnan(norm)) {
-      o[0] = o[1] = o[2] = 0;
-      return;
-    }
-    const float c = fminf(fmaxf(norm, 0.f), 1.f);
-    int k = static_cast<int>(c * 256.f);
-    k = k > 255 ? 255 : k;
-    o[0] = lut[k * 3], o[1] = lut[k * 3 + 1], o[2] = lut[k * 3 + 2];
+    for (int i = threadIdx.x; i < 768; i += 256) slut[i] = lut[i];
+    __syncthreads();
+  }
+  const long long i0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  const float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
+  const float span = __fsub_rn(hi, lo);
+  const int cnt = n - i0 < 4 ? static_cast<int>(n - i0) : 4;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (vec && cnt == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(d + i0);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
   } else {
-    reinterpret_cast<uint16_t*>(out)[i] = static_cast<uint16_t>(static_cast<int>(norm * 65535.f));
+    for (int j = 0; j < cnt; ++j) v[j] = d[i0 + j];
+  }
+  if (lut) {
+    uint8_t px[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float norm = __fdiv_rn(__fsub_rn(v[j], lo), span);
+      int k = static_cast<int>(fminf(fmaxf(norm, 0.f), 1.f) * 256.f);
+      k = k > 255 ? 255 : k;
+      const bool bad = isnan(norm);
+      px[3 * j] = bad ? 0 : slut[k * 3], px[3 * j + 1] = bad ? 0 : slut[k * 3 + 1], px[3 * j + 2] = bad ? 0 : slut[k * 3 + 2];
+    }
+    uint8_t* o = reinterpret_cast<uint8_t*>(out) + i0 * 3;
+    if (vec && cnt == 4) {
+      uint32_t w[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) w[q] = px[4 * q] | (px[4 * q + 1] << 8) | (px[4 * q + 2] << 16) | (px[4 * q + 3] << 24);
+      uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
+      o32[0] = w[0], o32[1] = w[1], o32[2] = w[2];
+    } else {
+      for (int j = 0; j < 3 * cnt; ++j) o[j] = px[j];
+    }
+  } else {
+    uint16_t* o = reinterpret_cast<uint16_t*>(out) + i0;
+    for (int j = 0; j < cnt; ++j) {
+      const float norm = __fdiv_rn(__fsub_rn(v[j], lo), span);
+      o[j] = static_cast<uint16_t>(static_cast<int>(norm * 65535.f));
+    }
   }
 }
 
@@ -716,8 +765,10 @@ void compose_head(const float* w1, const float* b1, const float* w2, const float
 }
 
 void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x, cudaStream_t s) {
-  const long long total = static_cast<long long>(B) * 3 * IMG * IMG;
-  resize_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, src_fmt, B, H, W, x);
+  static_assert(IMG % 256 == 0, "one block = 256 pixels of a row");
+  const dim3 grid(IMG / 256, IMG, B);
+  if (src_fmt == 1) resize_kernel<1><<<grid, 256, 0, s>>>(src, H, W, x);
+  else resize_kernel<0><<<grid, 256, 0, s>>>(src, H, W, x);
   DP_LAUNCH_CHECK();
 }
 
@@ -757,6 +808,23 @@ template void layernorm_rows_grouped<float>(const float*, float*, const LnGroups
 template void layernorm_rows_grouped<bf16>(const float*, bf16*, const LnGroups&, long long, cudaStream_t);
 template void layernorm_rows<float>(const float*, float*, const float*, const float*, long long, RowMap, int, cudaStream_t);
 template void layernorm_rows<bf16>(const float*, bf16*, const float*, const float*, long long, RowMap, int, cudaStream_t);
+
+// micro-benchmark operands: bf16 values uniform in [-1, 1) from a counter hash (an fp32 view of the same
+// bytes is a float in that range too).  Zero-filled operands hide most of the tensor-core power.
+__global__ void fill_random_bf16_kernel(uint16_t* __restrict__ p, long long n, unsigned seed) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  unsigned h = static_cast<unsigned>(i) * 2654435761u ^ seed;
+  h ^= h >> 16, h *= 0x7feb352du, h ^= h >> 15, h *= 0x846ca68bu, h ^= h >> 16;
+  const float v = static_cast<float>(h >> 8) * (2.f / 16777216.f) - 1.f;
+  const bf16 b = __float2bfloat16_rn(v);
+  p[i] = *reinterpret_cast<const uint16_t*>(&b);
+}
+void fill_random_bf16(void* p, size_t bytes, unsigned seed, cudaStream_t s) {
+  const long long n = static_cast<long long>(bytes / 2);
+  fill_random_bf16_kernel<<<blocks_for(n, 256), 256, 0, s>>>(reinterpret_cast<uint16_t*>(p), n, seed);
+  DP_LAUNCH_CHECK();
+}
 
 void ln_stats_cast(const float* in, bf16* xb, float* stats, long long rows, cudaStream_t s) {
   ln_stats_cast_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(in, xb, stats, rows);
@@ -817,8 +885,8 @@ void compute_fpx(const float* fov_deg, const float* f_px_in, int W, float* f_px,
 }
 
 void depth_epilogue(const float* canon, const float* f_px, int B, int H, int W, float* depth, cudaStream_t s) {
-  const long long total = static_cast<long long>(B) * H * W;
-  depth_epilogue_kernel<<<blocks_for(total, 256), 256, 0, s>>>(canon, f_px, B, H, W, depth);
+  DP_CHECK(H <= 65535 && B <= 65535, "depth epilogue: image too tall");
+  depth_epilogue_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, s>>>(canon, f_px, H, W, depth);
   DP_LAUNCH_CHECK();
 }
 
@@ -830,6 +898,7 @@ size_t unproject_scratch_ints(int H, int W) {
 void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float* f_px, float* xyz, float* rgb_out,
                uint8_t* valid_mask, int64_t* n_valid, int* scratch, cudaStream_t s) {
   const long long n = static_cast<long long>(H) * W;
+  DP_CHECK(n < (1LL << 31), "unproject: image too large");
   const int nblk = static_cast<int>((n + UNP_BLK - 1) / UNP_BLK);
   int* counts = scratch;
   long long* offsets = reinterpret_cast<long long*>(scratch + ((nblk + 1) & ~1));
@@ -848,7 +917,9 @@ void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, f
   DP_LAUNCH_CHECK();
   minmax_kernel<<<592, 256, 0, s>>>(depth, n, mm);
   DP_LAUNCH_CHECK();
-  colorize_kernel<<<blocks_for(n, 256), 256, 0, s>>>(depth, n, mm, lut, out);
+  // 4 pixels per thread; the packed 32-bit stores need 16-byte aligned buffers (4 pixels = 12 output bytes)
+  const int vec = reinterpret_cast<uintptr_t>(depth) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0;
+  colorize_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(depth, n, mm, lut, out, vec);
   DP_LAUNCH_CHECK();
 }
 

@@ -63,6 +63,9 @@ void im2col_nhwc(const T* x, T* cols, int B, int H, int W, int C, int k, int str
 template <typename T>
 void fov_final(const T* x, const float* w_hwio, const float* bias, float* fov_deg, int B, cudaStream_t s);
 
+// micro-benchmark operands: bf16 uniform in [-1, 1)
+void fill_random_bf16(void* p, size_t bytes, unsigned seed, cudaStream_t s);
+
 // ---- LayerNorm folded into the ViT GEMMs (common.cuh GemmOp::ln_stats) -------------------------
 // x fp32 (rows, 1024) -> raw bf16 copy + per-row partial sums [rows][LN_SLOTS][2] (slot 0 filled)
 void ln_stats_cast(const float* in, bf16* xb, float* stats, long long rows, cudaStream_t s);
