@@ -3,20 +3,25 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
-timeout 600 $B > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; exit 1; }
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1000 -c 500 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu.log 2>&1; echo "ncu list exit $?"
-# first launch of a frame = split_im2col: find a frame start inside the list, derive the skip counts
-F=$(python - <<'PY'
+timeout 600 $B > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 600 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu.log 2>&1; echo "ncu list exit $?"
+# frame structure from the kernel names: a frame starts at split_im2col; ViT block 12 = qkv, attention, proj,
+# fc1, fc2 around the frame's 13th attention launch; the decoder follows the frame's last layernorm launch
+read F V D N <<< $(python - <<'PY'
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/launches.csv')) if len(r)>5]
 h=rows[0]; ik=h.index("Kernel Name"); ii=h.index("ID")
-starts=[int(r[ii]) for r in rows[1:] if 'split_im2col' in r[ik]]
-print(starts[1])
+ids=[(int(r[ii]), r[ik]) for r in rows[1:]]
+starts=[i for i,(_,k) in enumerate(ids) if 'split_im2col' in k]
+a,b=starts[1],starts[2]
+fr=ids[a:b]
+att=[i for i,(_,k) in enumerate(fr) if 'attention_tc' in k]
+ln=[i for i,(_,k) in enumerate(fr) if 'layernorm_kernel' in k]
+print(fr[0][0], fr[att[12]-1][0], fr[ln[-1]+1][0], len(fr)-(ln[-1]+1))
 PY
 )
-echo "frame starts at launch $F"
-# ViT block 12 of that frame: LN, qkv, attention, proj, LN, fc1, fc2
-timeout 900 ncu --set full --clock-control none --import-source on -s $((F + 5 + 84)) -c 7 -o gpurun_out/prof_vit_block $B > gpurun_out/ncu2.log 2>&1; echo "ncu vit exit $?"
-# decoder + heads: the 54 launches after the ViT
-timeout 1200 ncu --set full --clock-control none -s $((F + 180)) -c 54 --csv --page raw --log-file gpurun_out/ncu_decoder_raw.csv $B > gpurun_out/ncu4.log 2>&1; echo "ncu decoder exit $?"
-ls -la gpurun_out | head -30; du -sh gpurun_out
+echo "frame starts at launch $F, ViT block 12 at $V, decoder at $D ($N launches)"
+timeout 900 ncu --set full --clock-control none --import-source on -s $V -c 5 -o gpurun_out/prof_vit_block $B > gpurun_out/ncu2.log 2>&1; echo "ncu vit exit $?"
+timeout 600 ncu -i gpurun_out/prof_vit_block.ncu-rep --page raw --csv > gpurun_out/ncu_vit_block_raw.csv 2> gpurun_out/ncu3.log; echo "ncu vit export exit $?"
+timeout 1200 ncu --set full --clock-control none -s $D -c $N --csv --page raw --log-file gpurun_out/ncu_decoder_raw.csv $B > gpurun_out/ncu4.log 2>&1; echo "ncu decoder exit $?"
+ls -la gpurun_out | head -40; du -sh gpurun_out
