@@ -4,20 +4,24 @@ mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 timeout 600 $B > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 600 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu.log 2>&1; echo "ncu list exit $?"
+# weight upload + LayerNorm folding take ~1270 launches before the first frame; the IDs in the list are
+# relative to the first captured launch
+SKIP=1400
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c 600 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu.log 2>&1; echo "ncu list exit $?"
 # frame structure from the kernel names: a frame starts at split_im2col; ViT block 12 = qkv, attention, proj,
 # fc1, fc2 around the frame's 13th attention launch; the decoder follows the frame's last layernorm launch
-read F V D N <<< $(python - <<'PY'
-import csv
+read F V D N <<< $(SKIP=$SKIP python - <<'PY'
+import csv, os
+skip = int(os.environ["SKIP"])
 rows=[r for r in csv.reader(open('gpurun_out/launches.csv')) if len(r)>5]
 h=rows[0]; ik=h.index("Kernel Name"); ii=h.index("ID")
 ids=[(int(r[ii]), r[ik]) for r in rows[1:]]
 starts=[i for i,(_,k) in enumerate(ids) if 'split_im2col' in k]
-a,b=starts[1],starts[2]
+a,b=starts[0],starts[1]
 fr=ids[a:b]
 att=[i for i,(_,k) in enumerate(fr) if 'attention_tc' in k]
 ln=[i for i,(_,k) in enumerate(fr) if 'layernorm_kernel' in k]
-print(fr[0][0], fr[att[12]-1][0], fr[ln[-1]+1][0], len(fr)-(ln[-1]+1))
+print(skip+fr[0][0], skip+fr[att[12]-1][0], skip+fr[ln[-1]+1][0], len(fr)-(ln[-1]+1))
 PY
 )
 echo "frame starts at launch $F, ViT block 12 at $V, decoder at $D ($N launches)"
