@@ -64,7 +64,9 @@ def _ncu_traffic():
     if not os.path.exists(p):
         return None
     try:
-        return json.load(open(p))["gemm_tc_kernel"]
+        d = json.load(open(p))["gemm_tc_kernel"]
+        return {"bytes_per_launch": d["dram_bytes_per_launch_mean"], "launches_captured": d["launches_captured"],
+                "source": d["source"]}
     except (KeyError, ValueError):
         return None
 
@@ -351,7 +353,8 @@ def run_ours(args):
             ach = (work[0] + work[1]) / (t_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
             roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)",
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": _ncu_traffic(),
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": (_ncu_traffic() or {}).get("bytes_per_launch"), "traffic_detail": _ncu_traffic(),
                     "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                     "launches_per_step": (cnt[0] + cnt[1]) / prof_steps,
                     "kernel_ms_per_step": t_ms / prof_steps,
