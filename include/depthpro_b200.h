@@ -52,6 +52,9 @@ int dp_engine_destroy(dp_engine* e);
  * repacks into its kernel-native layout (bf16 / fp32, K-major, conv taps outermost). */
 int dp_engine_set_weight(dp_engine* e, const char* name, const void* data,
                          const int64_t* shape, int ndim, int on_device);
+/* bf16 engines fold each ViT block's norm1 / norm2 into attn.qkv / mlp.fc1 at finalize and drop the
+ * originals: to change any of those tensors later, hand over the block's norm and qkv / fc1 weight + bias
+ * again before the next dp_engine_finalize (the Python shim always re-sends every parameter). */
 /* Number of reference tensors still missing (0 = complete). */
 int dp_engine_missing_weights(dp_engine* e);
 /* Allocate workspace, build TMA descriptors.  Must follow the last set_weight. */

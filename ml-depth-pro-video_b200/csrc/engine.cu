@@ -356,7 +356,9 @@ void Engine::finalize() {
         for (auto& pr : pairs) {
           const std::string lin = b + pr.first, nrm = b + pr.second;
           auto rw = raw_.find(lin + ".weight"), rb = raw_.find(lin + ".bias");
-          if (rw == raw_.end() || rb == raw_.end()) throw Error("missing key in state_dict: " + lin + ".weight");
+          if (rw == raw_.end() || rb == raw_.end())
+            throw Error("LayerNorm folding needs " + lin + ".weight / .bias set again together with " + nrm +
+                        ".weight / .bias before dp_engine_finalize (the folded copy replaced the original)");
           const int N = static_cast<int>(rb->second.bytes / 4);
           ln_fold((const float*)rw->second.ptr, F(nrm + ".weight"), F(nrm + ".bias"), (const float*)rb->second.ptr,
                   (bf16*)packed_.at(lin + ".weight").ptr, (float*)slot(lin + ".ln_c", N * 4), (float*)slot(lin + ".ln_d", N * 4),

@@ -132,6 +132,34 @@ def test_bf16_vs_oracle(model_bf16, oracle_run):
     assert float((~ok).float().mean()) <= 1e-3
 
 
+def test_bf16_layernorm_fold_matches_standalone_layernorm(model_bf16, oracle_run, monkeypatch):
+    """The LayerNorm-folded ViT (default) and the stand-alone LayerNorm launches (DEPTHPRO_LN_FUSE=0, read at
+    engine creation) are two roundings of the same arithmetic: they must agree far inside the bf16 tolerance,
+    and be equally close to the fp32 reference."""
+    x, ref, _ = oracle_run
+    folded = model_bf16.infer(x.to(DEV))
+    monkeypatch.setenv("DEPTHPRO_LN_FUSE", "0")
+    plain_model = depth_pro.DepthPro(device=DEV, precision=torch.bfloat16).init_weights("stress", 1234).eval()
+    plain = plain_model.infer(x.to(DEV))
+    monkeypatch.delenv("DEPTHPRO_LN_FUSE")
+    n0 = plain_model.launch_count()
+    plain_model.infer(x.to(DEV))
+    per_frame_plain = plain_model.launch_count() - n0
+    n0 = model_bf16.launch_count()
+    model_bf16.infer(x.to(DEV))
+    per_frame_folded = model_bf16.launch_count() - n0
+    assert per_frame_plain - per_frame_folded == 48 - 1     # 48 LayerNorm launches gone, one statistics pass added
+    d_f, d_p, d_r = folded["depth"].cpu(), plain["depth"].cpu(), ref["depth"]
+    ok = (d_r < 1e4 - 1) & (d_f < 1e4 - 1) & (d_p < 1e4 - 1)
+    between = _pix_rel(d_f, d_p)[ok].float()
+    e_f, e_p = _pix_rel(d_f, d_r)[ok].float().median(), _pix_rel(d_p, d_r)[ok].float().median()
+    print(f"LN fold vs stand-alone: median rel diff {float(between.median()):.3e}; vs fp32 reference: folded "
+          f"{float(e_f):.3e}, stand-alone {float(e_p):.3e}")
+    assert float(between.median()) <= 3e-3
+    assert float(e_f) <= 5e-3 and float(e_f) <= 1.5 * float(e_p) + 5e-4
+    del plain_model
+
+
 def test_batch_is_bit_identical(model_bf16):
     """Frames are independent units: a 2-frame batch must equal two single-frame calls bit for bit."""
     frames = np.stack([O.synthetic_frame_u8(i, 540, 960) for i in range(2)])
