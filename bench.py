@@ -101,7 +101,60 @@ def hbm_kernels(lib, model):
         gbs = hbm_bytes(kind, H, W) / (ms.value * 1e-3) / 1e9
         out[name] = {"us": round(ms.value * 1e3, 2), "MB": round(hbm_bytes(kind, H, W) / 1e6, 2), "GB/s": round(gbs, 1),
                      "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)}
+    out.update(ground_kernels(lib, model, peaks))
     return out
+
+
+def ground_kernels(lib, model, peaks):
+    """Ground normalisation of a 1080p cloud (N = 2 073 600 points): multi-pass (exact np.percentile by radix
+    select), timed per call with CUDA events; algorithmic bytes = one read and one write of what changes."""
+    import torch
+    from depth_pro import _capi
+
+    dev = model._device
+    n = 1080 * 1920
+    g = torch.Generator(device=dev).manual_seed(5)
+    k = n // 2
+    # same construction as the tests' synthetic room: noisy floor + boxes, camera pitched 15 degrees
+    pts = torch.empty(n, 3, device=dev)
+    pts[:, 0] = torch.rand(n, device=dev, generator=g) * 8 - 4
+    pts[:, 2] = torch.rand(n, device=dev, generator=g) * 8 + 1
+    pts[:k, 1] = torch.randn(k, device=dev, generator=g) * 0.012
+    pts[:k // 8, 1] += torch.rand(k // 8, device=dev, generator=g) * 0.16 + 0.02
+    pts[k:, 1] = torch.rand(n - k, device=dev, generator=g) * 2.7 - 0.3
+    a = 0.2618
+    rot = torch.tensor([[1, 0, 0], [0, float(torch.cos(torch.tensor(a))), -float(torch.sin(torch.tensor(a)))],
+                        [0, float(torch.sin(torch.tensor(a))), float(torch.cos(torch.tensor(a)))]], device=dev)
+    cam = pts @ rot.T + torch.tensor([0.0, -1.4, 0.0], device=dev)
+    normal = (ctypes.c_double * 3)(0.0, float(rot[1, 1]), float(rot[2, 1]))
+    d = 1.4 * float(rot[1, 1])
+    st = torch.cuda.current_stream(dev).cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    res = {}
+
+    def timed(fn, src):
+        tot = 0.0
+        for i in range(6):
+            work = src.clone()
+            flush.fill_(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(work)
+            e1.record()
+            e1.synchronize()
+            if i:
+                tot += e0.elapsed_time(e1)
+        return tot / 5, work
+
+    ms, normed = timed(lambda w: _capi.check(lib.dp_ground_normalize(model._engine, w.data_ptr(), n, normal, d, None, st)), cam)
+    res["ground normalize 1080p cloud (9 launches)"] = {"us": round(ms * 1e3, 1), "MB": round(n * 24 / 1e6, 2),
+                                                        "GB/s": round(n * 24 / ms / 1e6, 1),
+                                                        "frac_of_hbm_peak": round(n * 24 / ms / 1e6 / peaks["hbm_gbs"], 4)}
+    ms, _ = timed(lambda w: _capi.check(lib.dp_ground_grid_adjust(model._engine, w.data_ptr(), n, 20, 5.0, None, st)), normed)
+    res["ground grid adjust 1080p cloud (14 launches)"] = {"us": round(ms * 1e3, 1), "MB": round(n * 16 / 1e6, 2),
+                                                           "GB/s": round(n * 16 / ms / 1e6, 1),
+                                                           "frac_of_hbm_peak": round(n * 16 / ms / 1e6 / peaks["hbm_gbs"], 4)}
+    return res
 
 
 class ClockSampler:

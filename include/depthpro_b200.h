@@ -106,6 +106,22 @@ int dp_unproject(dp_engine* e, const float* depth, const uint8_t* rgb, int H, in
 int dp_colorize(dp_engine* e, const float* depth, int H, int W, const uint8_t* lut,
                 void* out, void* stream);
 
+/* img_to_normalized_pointcloud.py:880-975  normalize_point_cloud_to_ground, on the points dp_unproject
+ * produced: xyz float32 (n,3) on the device, updated IN PLACE.  `normal3` (host, 3 doubles) and `d` are the
+ * fitted ground plane a x + b y + c z + d = 0 (the fit itself, :376-816, stays on the CPU).  Distances to the
+ * plane, Rodrigues rotation of the normal onto +y, shift so that the 2nd percentile of the near-plane
+ * heights is y = 0, ground points below 0 -> 0, other points below -0.1 -> -0.1; arithmetic in double,
+ * np.percentile reproduced exactly (radix select).  `counters` (device, 6 x uint64, may be NULL) receives
+ * [0] points within 5 cm of the plane, [1] points set to y = 0, [2] points limited to -0.1. */
+int dp_ground_normalize(dp_engine* e, float* xyz, int64_t n, const double* normal3, double d,
+                        uint64_t* counters, void* stream);
+/* img_to_normalized_pointcloud.py:977-1118  grid_based_ground_adjustment: grid_size x grid_size cells over
+ * the XZ bounding box; every cell with >= 10 points and >= 5 points below 0.2 whose `percentile`-th
+ * percentile of those low heights exceeds 0.01 is lowered by it (fully below 0.1, linearly fading to 0 at
+ * 1.5), clamped at y = 0.  counters[3] points lowered, [4] cells with >= 10 points, [5] cells adjusted. */
+int dp_ground_grid_adjust(dp_engine* e, float* xyz, int64_t n, int grid_size, double percentile,
+                          uint64_t* counters, void* stream);
+
 /* Parity taps: copy a named stage tensor of the LAST dp_forward as float32 in the
  * reference's layout (NCHW / (n,577,C)).  Returns the element count in *numel. */
 int dp_tap(dp_engine* e, const char* stage, float* out, int64_t capacity, int64_t* numel,

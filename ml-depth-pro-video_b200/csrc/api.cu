@@ -79,6 +79,14 @@ int dp_unproject(dp_engine* e, const float* depth, const uint8_t* rgb, int H, in
 int dp_colorize(dp_engine* e, const float* depth, int H, int W, const uint8_t* lut, void* out, void* stream) {
   return guard([&] { E(e)->colorize(depth, H, W, lut, out, S(stream)); });
 }
+int dp_ground_normalize(dp_engine* e, float* xyz, int64_t n, const double* normal3, double d, uint64_t* counters,
+                        void* stream) {
+  return guard([&] { E(e)->ground_normalize(xyz, n, normal3, d, counters, S(stream)); });
+}
+int dp_ground_grid_adjust(dp_engine* e, float* xyz, int64_t n, int grid_size, double percentile, uint64_t* counters,
+                          void* stream) {
+  return guard([&] { E(e)->ground_grid_adjust(xyz, n, grid_size, percentile, counters, S(stream)); });
+}
 int dp_tap(dp_engine* e, const char* stage, float* out, int64_t capacity, int64_t* numel, void* stream) {
   return guard([&] {
     const int64_t n = E(e)->tap(stage, out, capacity, S(stream));

@@ -825,6 +825,29 @@ void Engine::unproject(const float* depth, const uint8_t* rgb, int H, int W, con
   dp::unproject(depth, rgb, H, W, f_px_dev, xyz, rgb_out, valid_mask, n_valid, unproject_scratch_, s);
 }
 
+void* Engine::ground_scratch(int64_t n, int grid_size) {
+  const size_t need = ground_scratch_bytes(n, grid_size);
+  if (ground_scratch_bytes_ < need) {  // grows monotonically; earlier blocks stay owned by the engine
+    ground_scratch_ = alloc(need);
+    ground_scratch_bytes_ = need;
+  }
+  return ground_scratch_;
+}
+void Engine::ground_normalize(float* xyz, int64_t n, const double* normal3, double d, uint64_t* counters, cudaStream_t s) {
+  DP_CUDA(cudaSetDevice(device_));
+  if (n == 0) return;
+  DP_CHECK(xyz != nullptr && normal3 != nullptr && n > 0, "ground_normalize: bad arguments");
+  dp::ground_normalize(xyz, n, normal3, d, ground_scratch(n, 1), reinterpret_cast<unsigned long long*>(counters), s);
+}
+void Engine::ground_grid_adjust(float* xyz, int64_t n, int grid_size, double percentile, uint64_t* counters, cudaStream_t s) {
+  DP_CUDA(cudaSetDevice(device_));
+  if (n == 0) return;
+  DP_CHECK(xyz != nullptr && n > 0, "ground_grid_adjust: bad arguments");
+  DP_CHECK(percentile >= 0.0 && percentile <= 100.0, "ground_grid_adjust: percentile outside [0, 100]");
+  dp::ground_grid_adjust(xyz, n, grid_size, percentile, ground_scratch(n, grid_size),
+                         reinterpret_cast<unsigned long long*>(counters), s);
+}
+
 void Engine::colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, cudaStream_t s) {
   DP_CUDA(cudaSetDevice(device_));
   if (!colorize_mm_) colorize_mm_ = (float*)alloc(64);

@@ -47,6 +47,9 @@ class Engine {
   void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float* f_px_dev, float* xyz, float* rgb_out,
                  uint8_t* valid_mask, int64_t* n_valid, cudaStream_t s);
   void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, cudaStream_t s);
+  // img_to_normalized_pointcloud.py:880-1118 on the GPU (ground.cu); `counters` = 6 x uint64 on the device or null
+  void ground_normalize(float* xyz, int64_t n, const double* normal3, double d, uint64_t* counters, cudaStream_t s);
+  void ground_grid_adjust(float* xyz, int64_t n, int grid_size, double percentile, uint64_t* counters, cudaStream_t s);
   int64_t tap(const std::string& stage, float* out, int64_t capacity, cudaStream_t s);
 
   void gemm_test(int backend, const float* A, const float* Wt, const float* bias, float* C, int M, int N, int K, int act,
@@ -113,6 +116,9 @@ class Engine {
   bool ln_fuse_ = false;       // bf16 mode: LayerNorm folded into qkv / fc1 (DEPTHPRO_LN_FUSE=0 disables)
   float* ln_stats_ = nullptr;  // (tokens, LN_SLOTS, 2) partial row sums of the residual stream
   float* colorize_mm_ = nullptr;
+  void* ground_scratch_ = nullptr;
+  size_t ground_scratch_bytes_ = 0;
+  void* ground_scratch(int64_t n, int grid_size);
   int* unproject_scratch_ = nullptr;
   size_t unproject_scratch_ints_ = 0;
   cudaStream_t host_stream_ = nullptr;

@@ -87,6 +87,16 @@ void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float
 size_t unproject_scratch_ints(int H, int W);
 void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, float* minmax, cudaStream_t s);
 
+// ---- ground normalisation of a point cloud (ground.cu; img_to_normalized_pointcloud.py:880-1118) -------
+// xyz float32 (n,3) in place; `scratch` >= ground_scratch_bytes(n, grid_size) bytes; `counters` (device, 6 x
+// uint64, optional): ground points, set to y=0, limited to -0.1, lowered by the grid pass, cells with >= 10
+// points, cells adjusted
+size_t ground_scratch_bytes(long long n, int grid_size);
+void ground_normalize(float* xyz, long long n, const double normal[3], double d, void* scratch,
+                      unsigned long long* counters, cudaStream_t s);
+void ground_grid_adjust(float* xyz, long long n, int grid_size, double percentile, void* scratch,
+                        unsigned long long* counters, cudaStream_t s);
+
 // ---- layout / dtype helpers ---------------------------------------------------------------
 template <typename TI, typename TO>
 void convert(const TI* in, TO* out, long long n, cudaStream_t s);

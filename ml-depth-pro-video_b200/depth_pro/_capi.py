@@ -35,6 +35,8 @@ SIGNATURES = {
     "dp_infer_host": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dp_unproject": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dp_colorize": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "dp_ground_normalize": (_i, [_vp, _vp, _i64, C.POINTER(C.c_double), C.c_double, _vp, _vp]),
+    "dp_ground_grid_adjust": (_i, [_vp, _vp, _i64, _i, C.c_double, _vp, _vp]),
     "dp_tap": (_i, [_vp, C.c_char_p, _vp, _i64, C.POINTER(_i64), _vp]),
     "dp_gemm_test": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dp_conv3x3_test": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

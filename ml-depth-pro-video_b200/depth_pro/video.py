@@ -103,6 +103,51 @@ def depth_to_uint16(model: DepthPro, depth: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _ground_counters(dev) -> torch.Tensor:
+    return torch.zeros(6, dtype=torch.int64, device=dev)
+
+
+def normalize_point_cloud_to_ground(model: DepthPro, points_3d: torch.Tensor, ground_model: Dict[str, object],
+                                    stats: Optional[dict] = None) -> torch.Tensor:
+    """GPU ``normalize_point_cloud_to_ground`` (img_to_normalized_pointcloud.py:880-975).
+
+    ``points_3d`` is the (N,3) float32 CUDA tensor ``depth_to_3d`` returned; ``ground_model`` the reference's
+    dictionary with ``'normal'`` and ``'d'`` (the plane fit itself stays on the CPU).  Returns a new (N,3) float32
+    tensor with the ground at y = 0.  The reference prints three counts; pass ``stats={}`` to receive them
+    (``ground_points``, ``set_to_zero``, ``limited_to_minus_10cm``) -- reading them synchronises.
+    """
+    assert points_3d.is_cuda and points_3d.dtype == torch.float32 and points_3d.dim() == 2 and points_3d.shape[1] == 3
+    out = points_3d.contiguous().clone()
+    normal = (ctypes.c_double * 3)(*[float(v) for v in np.asarray(ground_model["normal"], dtype=np.float64).reshape(3)])
+    ctr = _ground_counters(out.device) if stats is not None else None
+    lib = model._ensure_engine(1)
+    with torch.cuda.device(out.device):
+        _capi.check(lib.dp_ground_normalize(model._engine, out.data_ptr(), out.shape[0], normal, float(ground_model["d"]),
+                                            _capi.ptr(ctr), model._stream()))
+    if stats is not None:
+        c = ctr.tolist()
+        stats.update(ground_points=c[0], set_to_zero=c[1], limited_to_minus_10cm=c[2])
+    return out
+
+
+def grid_based_ground_adjustment(model: DepthPro, points_3d: torch.Tensor, grid_size: int = 20, percentile: float = 5,
+                                 stats: Optional[dict] = None) -> torch.Tensor:
+    """GPU ``grid_based_ground_adjustment`` (img_to_normalized_pointcloud.py:977-1118); same arguments, (N,3)
+    float32 CUDA tensor in and out.  ``stats={}`` receives the reference's summary (``points_adjusted``,
+    ``cells_with_points``, ``cells_adjusted``)."""
+    assert points_3d.is_cuda and points_3d.dtype == torch.float32 and points_3d.dim() == 2 and points_3d.shape[1] == 3
+    out = points_3d.contiguous().clone()
+    ctr = _ground_counters(out.device) if stats is not None else None
+    lib = model._ensure_engine(1)
+    with torch.cuda.device(out.device):
+        _capi.check(lib.dp_ground_grid_adjust(model._engine, out.data_ptr(), out.shape[0], int(grid_size), float(percentile),
+                                              _capi.ptr(ctr), model._stream()))
+    if stats is not None:
+        c = ctr.tolist()
+        stats.update(points_adjusted=c[3], cells_with_points=c[4], cells_adjusted=c[5])
+    return out
+
+
 @dataclass
 class FrameResult:
     index: int

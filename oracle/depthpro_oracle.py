@@ -314,3 +314,79 @@ def depth_to_u16(depth: np.ndarray) -> np.ndarray:
     """generate_depth_maps.py:136-139 — 16-bit normalised raw depth."""
     lo, hi = np.nanmin(depth), np.nanmax(depth)
     return ((depth - lo) / (hi - lo) * 65535).astype(np.uint16)
+
+
+def synthetic_room_points(n: int = 20000, seed: int = 3, tilt_deg: float = 12.0):
+    """Seeded stand-in for an unprojected indoor frame: a noisy floor seen by a tilted camera plus boxes and
+    walls above it.  Returns (float32 (n,3) points, unit normal (3,), d) with the floor on normal . p + d = 0."""
+    rng = np.random.default_rng(seed)
+    k = n // 2
+    floor = np.column_stack((rng.uniform(-4, 4, k), rng.normal(0, 0.012, k), rng.uniform(1, 9, k)))
+    floor[: k // 8, 1] += rng.uniform(0.02, 0.18, k // 8)          # bumps: cells whose low points float above y = 0
+    boxes = np.column_stack((rng.uniform(-3, 3, n - k), rng.uniform(-0.3, 2.4, n - k), rng.uniform(2, 8, n - k)))
+    pts = np.vstack((floor, boxes))
+    a = np.deg2rad(tilt_deg)
+    rot = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    cam = pts @ rot.T + np.array([0.0, -1.4, 0.0])                 # camera 1.4 m above the floor, pitched down
+    normal = rot @ np.array([0.0, 1.0, 0.0])
+    d = 1.4 * normal[1] - normal @ np.array([0.0, 0.0, 0.0])       # floor point (0,0,0) maps to (0,-1.4,0)
+    return cam.astype(np.float32), normal, float(d)
+
+
+def normalize_point_cloud_to_ground(points_3d, normal, d):
+    """img_to_normalized_pointcloud.py:880-975 restated.  Signed distances with the unit normal (:873-878);
+    Rodrigues rotation of the normal onto +y unless |normal.y| > 0.99 (:912-934); plane to y = const via the
+    rotated RAW normal (:939-944); 2nd percentile of the heights within 0.1 of the plane becomes y = 0 when more
+    than 10 such points exist (:947-954); points within 0.05 of the plane and below 0 -> 0, other points below
+    -0.1 -> -0.1 (:958-972).  float64 in, float64 out."""
+    p = np.asarray(points_3d, dtype=np.float64)
+    normal = np.asarray(normal, dtype=np.float64)
+    unit = normal / np.linalg.norm(normal)
+    dist = p @ unit + d
+    up = np.array([0.0, 1.0, 0.0])
+    if abs(float(normal @ up)) > 0.99:
+        out = p.copy()
+    else:
+        axis = np.cross(unit, up)
+        axis /= np.linalg.norm(axis)
+        ang = np.arccos(np.clip(unit @ up, -1.0, 1.0))
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+        out = p @ R.T
+        out[:, 1] -= -d / (R @ normal)[1]
+    near = out[np.abs(dist) < 0.1, 1]
+    if near.size > 10:
+        out[:, 1] -= np.percentile(near, 2)
+    ground = np.abs(dist) < 0.05
+    out[(out[:, 1] < 0) & ground, 1] = 0.0
+    out[(out[:, 1] < -0.1) & ~ground, 1] = -0.1
+    return out
+
+
+def grid_based_ground_adjustment(points_3d, grid_size=20, percentile=5):
+    """img_to_normalized_pointcloud.py:977-1118 restated with a segmented formulation instead of the per-cell
+    loop: cells = digitize on linspace edges over the XZ bounds, clipped (:1009-1031); a cell qualifies with >= 10
+    points (:1046) and >= 5 heights below 0.2 (:1058-1062); p = percentile of those low heights (:1068); if
+    p > 0.01 every point of the cell is lowered by p (y < 0.1), by p * (1 - (y - 0.1) / 1.4) (0.1 <= y < 1.5) or not
+    at all, then clamped at 0 (:1075-1106)."""
+    p = np.asarray(points_3d, dtype=np.float64)
+    out = p.copy()
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    xe = np.linspace(x.min(), x.max(), grid_size + 1)
+    ze = np.linspace(z.min(), z.max(), grid_size + 1)
+    cell = np.clip(np.digitize(x, xe) - 1, 0, grid_size - 1) * grid_size + np.clip(np.digitize(z, ze) - 1, 0, grid_size - 1)
+    order = np.argsort(cell, kind="stable")
+    bounds = np.flatnonzero(np.diff(cell[order], prepend=-1, append=grid_size * grid_size + 1))
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        idx = order[a:b]
+        if idx.size < 10:
+            continue
+        cy = y[idx]
+        low = cy[cy < 0.2]
+        if low.size < 5:
+            continue
+        pc = np.percentile(low, percentile)
+        if pc > 0.01:
+            adj = np.where(cy < 0.1, pc, np.where(cy < 1.5, pc * (1.0 - (cy - 0.1) / 1.4), 0.0))
+            out[idx, 1] = np.maximum(cy - adj, 0.0)
+    return out

@@ -93,6 +93,40 @@ def depth_to_3d_fixture():
     print("wrote depth_to_3d.npz", pts.shape, pts.dtype)
 
 
+def ground_fixture():
+    """Execute the reference's own normalize_point_cloud_to_ground / grid_based_ground_adjustment
+    (img_to_normalized_pointcloud.py:858-1118) on a seeded synthetic room and pin the oracle to them."""
+    import contextlib
+    import io
+
+    src_path = "/root/reference/img_to_normalized_pointcloud.py"
+    tree = ast.parse(open(src_path).read())
+    want = ("point_plane_distances", "normalize_point_cloud_to_ground", "grid_based_ground_adjustment")
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert len(fns) == 3
+    ns = {"np": np}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), src_path, "exec"), ns)
+    out = {}
+    for tag, tilt, seed in (("tilt12", 12.0, 3), ("tilt3", 3.0, 4)):   # tilt3: |normal.y| > 0.99, no rotation branch
+        pts32, normal, d = O.synthetic_room_points(20000, seed, tilt)
+        pts = pts32.astype(np.float64)
+        with contextlib.redirect_stdout(io.StringIO()):
+            norm = ns["normalize_point_cloud_to_ground"](pts, {"normal": normal, "d": d})
+            # the second stage sees float32 points (what the GPU path hands over), widened again
+            norm32 = norm.astype(np.float32)
+            grid = ns["grid_based_ground_adjustment"](norm32.astype(np.float64), grid_size=20, percentile=5)
+        o_norm = O.normalize_point_cloud_to_ground(pts, normal, d)
+        o_grid = O.grid_based_ground_adjustment(norm32.astype(np.float64), 20, 5)
+        assert np.max(np.abs(o_norm - norm)) <= 1e-12, np.max(np.abs(o_norm - norm))
+        assert np.array_equal(o_grid, grid), np.max(np.abs(o_grid - grid))
+        print(f"ground fixture {tag}: normalize max diff {np.max(np.abs(o_norm - norm)):.2e}; grid adjusted "
+              f"{int((grid[:, 1] != norm32[:, 1]).sum())} points")
+        out[tag + "_points"], out[tag + "_normal"], out[tag + "_d"] = pts32, normal, np.float64(d)
+        out[tag + "_normalized"], out[tag + "_grid"] = norm.astype(np.float32), grid.astype(np.float32)
+    np.savez_compressed(os.path.join(GOLD, "ground_normalize.npz"), **out)
+    print("wrote ground_normalize.npz")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -100,6 +134,7 @@ def main():
     enc_cls = sys.modules["ref_depth_pro.network.encoder"].DepthProEncoder
     index_fixtures(enc_cls)
     depth_to_3d_fixture()
+    ground_fixture()
 
     t0 = time.time()
     sd = W.stress_init(1234)

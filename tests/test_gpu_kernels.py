@@ -165,3 +165,80 @@ def test_colorize_and_u16():
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), ref)
     assert np.array_equal(out16.cpu().numpy().view(np.uint16), O.depth_to_u16(depth.numpy()))
+
+
+# ---- ground normalisation (img_to_normalized_pointcloud.py:880-1118) -------------------------------------
+def _ground_call(fn, pts32, *args):
+    import ctypes
+
+    xyz = torch.from_numpy(pts32).to(DEV).contiguous()
+    ctr = torch.zeros(6, dtype=torch.int64, device=DEV)
+    _capi.check(fn(engine(), xyz.data_ptr(), xyz.shape[0], *args, ctr.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    return xyz.cpu().numpy(), ctr.tolist()
+
+
+def _normalize_gpu(pts32, normal, d):
+    import ctypes
+
+    n3 = (ctypes.c_double * 3)(*[float(v) for v in normal])
+    return _ground_call(lib().dp_ground_normalize, pts32, n3, float(d))
+
+
+def _grid_gpu(pts32, grid_size=20, percentile=5.0):
+    return _ground_call(lib().dp_ground_grid_adjust, pts32, int(grid_size), float(percentile))
+
+
+@pytest.mark.parametrize("tag", ["tilt12", "tilt3"])
+def test_ground_normalize_golden(tag, golden_dir):
+    """Against outputs of the reference's own functions (rotation branch and the |normal.y| > 0.99 branch)."""
+    g = np.load(os.path.join(golden_dir, "ground_normalize.npz"))
+    pts, normal, d = g[tag + "_points"], g[tag + "_normal"], float(g[tag + "_d"])
+    got, ctr = _normalize_gpu(pts, normal, d)
+    ref = g[tag + "_normalized"]
+    # double arithmetic on both sides, one float32 rounding at the end; the order statistics are float32-rounded
+    # heights on the GPU (1e-7 relative) -- a continuous effect, never a different branch
+    assert np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64))) <= 2e-6
+    assert np.array_equal(got[:, 1] == 0, ref[:, 1] == 0) and np.array_equal(got[:, 1] == np.float32(-0.1), ref[:, 1] == np.float32(-0.1))
+    dist = pts.astype(np.float64) @ normal + d
+    assert ctr[0] == int((np.abs(dist) < 0.05).sum()) and ctr[1] == int((ref[:, 1] == 0).sum())
+    # second stage on the reference's first-stage output: identical input on both sides -> identical selection
+    got2, ctr2 = _grid_gpu(ref)
+    ref2 = g[tag + "_grid"]
+    assert np.max(np.abs(got2.astype(np.float64) - ref2.astype(np.float64))) <= 1e-6
+    assert np.array_equal(got2[:, [0, 2]], ref[:, [0, 2]])                       # x and z are never touched
+    assert ctr2[3] == int((ref2[:, 1] != ref[:, 1]).sum()) or ctr2[3] >= int((ref2[:, 1] != ref[:, 1]).sum())
+    assert 0 < ctr2[5] <= ctr2[4] <= 400
+
+
+@pytest.mark.parametrize("n,seed,tilt,grid,pct", [(200_000, 11, 20.0, 20, 5.0), (1_000_003, 12, 7.0, 32, 10.0),
+                                                   (5_000, 13, 35.0, 7, 50.0), (2_073_600, 14, 15.0, 20, 5.0)])
+def test_ground_stages_vs_oracle(n, seed, tilt, grid, pct):
+    """Full-size clouds (up to a 1080p frame) against the float64 oracle on the same float32 points."""
+    pts, normal, d = O.synthetic_room_points(n, seed, tilt)
+    got, _ = _normalize_gpu(pts, normal * 1.7, d * 1.0)       # a non-unit normal: distances use the unit normal,
+    ref = O.normalize_point_cloud_to_ground(pts.astype(np.float64), normal * 1.7, d)   # the shift the raw one (:873, :939)
+    assert np.max(np.abs(got.astype(np.float64) - ref)) <= 3e-6
+    got2, ctr = _grid_gpu(got, grid, pct)
+    ref2 = O.grid_based_ground_adjustment(got.astype(np.float64), grid, pct)
+    assert np.max(np.abs(got2.astype(np.float64) - ref2)) <= 1e-6
+    assert ctr[3] > 0 and ctr[5] > 0
+    assert float(got2[:, 1].min()) >= -0.1 - 1e-6
+
+
+def test_ground_edge_cases():
+    # fewer than 11 near-plane points: no percentile shift; every point far above the plane is untouched
+    far = np.array([[0.0, 5.0, 1.0], [1.0, 6.0, 2.0], [2.0, 7.0, 3.0]], dtype=np.float32)
+    got, ctr = _normalize_gpu(far, np.array([0.0, 1.0, 0.0]), 0.0)
+    assert np.array_equal(got, far) and ctr[:3] == [0, 0, 0]
+    got2, ctr2 = _grid_gpu(far)
+    assert np.array_equal(got2, far) and ctr2[3:] == [0, 0, 0]
+    # duplicates everywhere (order statistics with multiplicity), all points in one cell column
+    rng = np.random.default_rng(0)
+    dup = np.column_stack((np.zeros(4000), rng.integers(0, 6, 4000) * 0.03 + 0.03, rng.uniform(1, 2, 4000))).astype(np.float32)
+    got3, _ = _grid_gpu(dup, 4, 5.0)
+    ref3 = O.grid_based_ground_adjustment(dup.astype(np.float64), 4, 5.0)
+    assert np.max(np.abs(got3.astype(np.float64) - ref3)) <= 1e-6 and (got3[:, 1] != dup[:, 1]).any()
+    # n = 0 is a no-op
+    empty = torch.empty((0, 3), device=DEV)
+    _capi.check(lib().dp_ground_grid_adjust(engine(), empty.data_ptr(), 0, 20, 5.0, None, stream()))

@@ -119,3 +119,29 @@ def test_pipeline_process_frames(model, tmp_path):
     # everything is recorded; a resumed run has nothing left to do
     s2 = pipeline.process_frames(str(src), str(out), model, consumer, resume=True)
     assert s2.skipped == 4 and s2.processed == 0
+
+
+def test_ground_normalisation_wrappers(model):
+    """video.normalize_point_cloud_to_ground / grid_based_ground_adjustment (reference names and arguments) on a
+    real unprojected frame, against the float64 oracle on the same float32 points."""
+    H, W = 270, 480
+    frame = O.synthetic_frame_u8(3, H, W)
+    pred = model.infer(torch.from_numpy(frame))
+    pts, _, _ = video.depth_to_3d(model, pred["depth"], pred["focallength_px"], W, H)
+    p64 = pts.cpu().double().numpy()
+    # a plausible floor: the plane through the lowest part of the cloud, slightly pitched
+    normal = np.array([0.02, 0.97, 0.24])
+    normal /= np.linalg.norm(normal)
+    d = -float(np.percentile(p64 @ normal, 3))
+    ground = {"normal": normal, "d": d}
+    stats = {}
+    norm = video.normalize_point_cloud_to_ground(model, pts, ground, stats=stats)
+    ref = O.normalize_point_cloud_to_ground(p64, normal, d)
+    assert norm.shape == pts.shape and norm.data_ptr() != pts.data_ptr()
+    assert np.max(np.abs(norm.cpu().double().numpy() - ref)) <= 1e-5 * max(1.0, float(np.abs(ref).max()))
+    assert stats["ground_points"] == int((np.abs(p64 @ normal + d) < 0.05).sum())
+    stats2 = {}
+    adj = video.grid_based_ground_adjustment(model, norm, grid_size=20, percentile=5, stats=stats2)
+    ref2 = O.grid_based_ground_adjustment(norm.cpu().double().numpy(), 20, 5)
+    assert np.max(np.abs(adj.cpu().double().numpy() - ref2)) <= 1e-5 * max(1.0, float(np.abs(ref2).max()))
+    assert set(stats2) == {"points_adjusted", "cells_with_points", "cells_adjusted"} and stats2["cells_with_points"] > 0

@@ -100,3 +100,26 @@ def test_oracle_vs_live_reference():
         ref = vit(img)
         got, _ = O.vit_forward(sd, "v.", img)
     assert torch.equal(ref, got)
+
+
+def test_ground_normalisation_oracle_matches_reference_outputs(golden_dir):
+    """oracle restatement of img_to_normalized_pointcloud.py:880-1118 vs outputs of the reference's own functions
+    (tests/golden/ground_normalize.npz, written by oracle/make_golden.py: rotation branch and |normal.y| > 0.99)."""
+    g = np.load(os.path.join(golden_dir, "ground_normalize.npz"))
+    for tag in ("tilt12", "tilt3"):
+        pts, normal, d = g[tag + "_points"], g[tag + "_normal"], float(g[tag + "_d"])
+        p2, n2, d2 = O.synthetic_room_points(20000, 3 if tag == "tilt12" else 4, 12.0 if tag == "tilt12" else 3.0)
+        assert np.array_equal(p2, pts) and np.array_equal(n2, normal) and d2 == d      # seeded input is reproducible
+        norm = O.normalize_point_cloud_to_ground(pts.astype(np.float64), normal, d)
+        assert np.array_equal(norm.astype(np.float32), g[tag + "_normalized"])
+        grid = O.grid_based_ground_adjustment(g[tag + "_normalized"].astype(np.float64), 20, 5)
+        assert np.array_equal(grid.astype(np.float32), g[tag + "_grid"])
+        assert (np.abs(normal[1]) > 0.99) == (tag == "tilt3")
+        # the stages do something on this input: ground at y = 0, clamps hit, cells lowered
+        assert (norm[:, 1] == 0).sum() > 10 and (norm[:, 1] == -0.1).sum() > 10
+        assert (grid[:, 1] != g[tag + "_normalized"][:, 1].astype(np.float64)).sum() > 1000
+    # degenerate inputs: fewer than 11 near-plane points -> no percentile shift; tiny clouds pass through the grid stage
+    far = np.array([[0.0, 5.0, 1.0], [1.0, 6.0, 2.0], [2.0, 7.0, 3.0]])
+    out = O.normalize_point_cloud_to_ground(far, np.array([0.0, 1.0, 0.0]), 0.0)
+    assert np.array_equal(out, far)
+    assert np.array_equal(O.grid_based_ground_adjustment(far, 20, 5), far)
