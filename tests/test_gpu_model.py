@@ -175,3 +175,45 @@ def test_errors():
         depth_pro.create_model_and_transforms(device=torch.device("cpu"))
     with pytest.raises(KeyError):
         depth_pro.depth_pro.create_backbone_model("nope")
+
+
+def test_infer_edge_shapes_and_argument_forms(model_bf16):
+    """Ragged / extreme inputs of DepthPro.infer (depth_pro.py:243-298): tiny and odd image sizes, 3-D vs 4-D input,
+    non-contiguous tensors, every accepted form of f_px, and the error paths."""
+    rng = np.random.default_rng(9)
+    for H, W in ((1, 1), (1, 7), (5, 3), (17, 23), (1536, 1536), (2001, 333)):
+        img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+        pred = model_bf16.infer(img)                          # ndarray straight from load_rgb
+        d = pred["depth"]
+        assert d.shape == ((H, W) if H > 1 and W > 1 else torch.Size([s for s in (H, W) if s > 1]))   # reference squeezes
+        assert d.dtype == torch.float32 and d.is_cuda and bool(torch.isfinite(d).all())
+        assert float(d.min()) >= 1e-4 - 1e-9 and float(d.max()) <= 1e4 * (1 + 1e-6)                  # clamp(1e-4, 1e4) of the inverse
+        assert pred["focallength_px"].dim() == 0 and float(pred["focallength_px"]) > 0
+    # float CHW in [-1, 1] (the reference's transformed tensor), 3-D and 4-D, contiguous or not: same result
+    x = torch.rand(3, 40, 56) * 2 - 1
+    a = model_bf16.infer(x)["depth"]
+    b = model_bf16.infer(x[None])["depth"]
+    c = model_bf16.infer(x.permute(1, 2, 0).contiguous().permute(2, 0, 1))["depth"]     # non-contiguous view
+    assert a.shape == (40, 56) and torch.equal(a, b) and torch.equal(a, c)
+    assert torch.equal(model_bf16.infer(x.double())["depth"], a)                        # any float dtype is accepted
+    # f_px: python float, 0-d tensor, 1-element tensor, per-image tensor; the value is passed through (:285-286)
+    for f in (500.0, torch.tensor(500.0), torch.tensor([500.0])):
+        p = model_bf16.infer(x, f_px=f)
+        assert float(p["focallength_px"]) == 500.0
+    two = torch.stack([x, x.flip(-1)])
+    p2 = model_bf16.infer(two, f_px=torch.tensor([400.0, 800.0]))
+    assert p2["depth"].shape == (2, 40, 56)
+    one = model_bf16.infer(x, f_px=400.0)["depth"]
+    assert torch.equal(p2["depth"][0], one)
+    # depth scales with W / f_px: doubling f_px doubles metric depth wherever neither hits the clamp
+    far = model_bf16.infer(x, f_px=800.0)["depth"]
+    ok = (one < 4e3) & (one > 1e-3)
+    assert float(((far / one)[ok] - 2.0).abs().max()) < 1e-5
+    with pytest.raises(NotImplementedError):
+        model_bf16.infer(x, interpolation_mode="bicubic")
+    with pytest.raises(AssertionError):
+        model_bf16.infer(torch.rand(4, 40, 56))               # not 3 channels
+    with pytest.raises(AssertionError):
+        model_bf16.forward(torch.rand(1, 3, 384, 384))        # forward is 1536^2 only (:231)
+    with pytest.raises(AssertionError):
+        model_bf16.infer(x, f_px=torch.tensor([1.0, 2.0, 3.0]))
