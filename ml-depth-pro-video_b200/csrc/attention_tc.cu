@@ -29,6 +29,23 @@
 #include "ptx.cuh"
 
 namespace dp {
+#ifdef ATTN_PROFILE
+// Phase timing of the softmax warps (scripts/ubench/attn_prof.cu): cycles per phase summed over quadrant-0
+// softmax warps of every stream, [8] = number of blocks counted.
+__device__ unsigned long long g_attn_prof[10];
+__device__ unsigned long long g_attn_prof_sj[5];    // softmax: cycles waiting for S, by key block j
+__device__ unsigned long long g_attn_prof_mma[8];   // MMA warp: q_full, k_full, s_empty, QK issue, v_full+o_empty, p_full, PV issue, #blocks
+#define PROF_DECL long long prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_last = clock64();
+#define PROF_T(i)                          \
+  {                                        \
+    const long long _t = clock64();        \
+    prof_acc[i] += _t - prof_last;         \
+    prof_last = _t;                        \
+  }
+#else
+#define PROF_DECL
+#define PROF_T(i)
+#endif
 namespace {
 
 constexpr int SEQ = 577, HD = 64, NH = 16, LDQ = 3 * NH * HD, LDO = NH * HD;
@@ -163,15 +180,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       const uint32_t v_lo = k_lo + (RING * TILE_BYTES >> 4);
       const uint32_t p_lo = v_lo + (RING * TILE_BYTES >> 4);
       const uint32_t tS = tmem_base, tO = tmem_base + 128;
-      int T = 0;
-      for (int u = slot; u < n_units; u += n_slots) {
-        for (int qt = 0; qt < NQT; ++qt, ++T) {
-          // O += P V of key block jj, then release that V stage
-          auto issue_pv = [&](int jj) {
-            const int G = T * NB + jj, st = G % RING;
+      // O += P V of key block jj of tile Tt, then release that V stage
+#ifdef ATTN_PROFILE
+      long long mp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      long long mlast = clock64();
+#define MPROF(i) { const long long _t = clock64(); mp[i] += _t - mlast; mlast = _t; }
+#else
+#define MPROF(i)
+#endif
+      auto issue_pv = [&](int Tt, int jj) {
+            const int G = Tt * NB + jj, st = G % RING;
             ptx::mbar_wait(&v_full[st], (G / RING) & 1);
-            if (jj == 0) ptx::mbar_wait(o_empty, (T & 1) ^ 1);  // the previous tile's O has been read out
+            if (jj == 0) ptx::mbar_wait(o_empty, (Tt & 1) ^ 1);  // the previous tile's O has been read out
+            MPROF(4)
             ptx::mbar_wait(p_full, G & 1);
+            MPROF(5)
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
               const int nks = jj == NB - 1 ? LAST_N / 16 : KB / 16;
@@ -187,12 +210,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               ptx::umma_commit(&v_empty[st]);
             }
             __syncwarp();
-          };
+            MPROF(6)
+      };
+      // (Issuing the last P V of tile T after the first Q K^T of tile T+1 was measured and changed nothing: the
+      // single-buffered Q tile and the first K block of the next tile arrive too late for it to matter.)
+      int T = 0;
+      for (int u = slot; u < n_units; u += n_slots) {
+        for (int qt = 0; qt < NQT; ++qt, ++T) {
           ptx::mbar_wait(q_full, T & 1);
+          MPROF(0)
           for (int j = 0; j < NB; ++j) {
             const int G = T * NB + j, st = G % RING;
             ptx::mbar_wait(&k_full[st], (G / RING) & 1);
+            MPROF(1)
             ptx::mbar_wait(s_empty, (G & 1) ^ 1);
+            MPROF(2)
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
 #pragma unroll
@@ -204,11 +236,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               if (j == NB - 1) ptx::umma_commit(q_empty);  // the Q tile is free once its last Q K^T retires
             }
             __syncwarp();
-            if (j > 0) issue_pv(j - 1);
+            MPROF(3)
+#ifdef ATTN_PROFILE
+            mp[7] += 1;
+#endif
+            if (j > 0) issue_pv(T, j - 1);
           }
-          issue_pv(NB - 1);
+          issue_pv(T, NB - 1);
         }
       }
+#ifdef ATTN_PROFILE
+      if (lane == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_attn_prof_mma[i], static_cast<unsigned long long>(mp[i]));
+#endif
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
@@ -230,6 +270,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const int n_pp = (u_a < u_b ? u_a : u_b) * NQT * NB;   // blocks that ping-pong
     const int bar_mine = 1 + q + 4 * sidx, bar_peer = 1 + q + 4 * (sidx ^ 1);
     int T = 0;
+    PROF_DECL
     for (int u = slot; u < n_units; u += n_slots) {
       const int h = u % NH, seq = u / NH;
       for (int qt = 0; qt < NQT; ++qt, ++T) {
@@ -244,22 +285,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           const int G = T * NB + j;
           ptx::mbar_wait(s_full, G & 1);
           ptx::tc_fence_after();
+#ifdef ATTN_PROFILE
+          if (q == 0 && lane == 0) atomicAdd(&g_attn_prof_sj[j], static_cast<unsigned long long>(clock64() - prof_last));
+#endif
+          PROF_T(0)  // waiting for S
           uint32_t sr[NCH][32];
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) ptx::tmem_ld32(tS + ch * 32, sr[ch]);
           ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           ptx::mbar_arrive(s_empty);  // S is in registers: the next Q K^T may overwrite it
+          PROF_T(1)  // TMEM load
           // row maximum over the valid keys, four independent chains
           float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int k = 0; k < NKEY; ++k) mx4[k & 3] = fmaxf(mx4[k & 3], __uint_as_float(sr[k >> 5][k & 31]));
           const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          PROF_T(2)  // row maximum
           // P and O are single-buffered: the previous block's P V must have retired
           if (j > 0) {
             ptx::mbar_wait(pv_done, (G - 1) & 1);
             ptx::tc_fence_after();
           }
+          PROF_T(3)  // waiting for the previous P V
           if (j == 0) {
             m_ref = mx;
           } else if (__any_sync(0xffffffffu, (mx - m_ref) * c > RESCALE_LOG2)) {
@@ -279,7 +327,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             ptx::tmem_st_wait();
           }
           // my turn on the MUFU: stream A leads, B follows A's block G, A's block G follows B's block G-1
+          PROF_T(4)  // lazy-maximum check / rescale
           if (G < n_pp && (sidx == 1 || G > 0)) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");
+          PROF_T(5)  // waiting for the MUFU turn
           if (j == 0) {  // the previous tile's output store must have drained this warp's P rows
             if (lane == 0) ptx::tma_store_wait_read();
             __syncwarp();
@@ -302,10 +352,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             ptx::sts_u4(prow + (g8 >> 3) * TILE_BYTES + (((g8 & 7) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
           l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+          PROF_T(6)  // exponentials + P stores
           if (G < n_pp && (sidx == 0 || G < n_pp - 1)) asm volatile("bar.arrive %0, 64;" ::"r"(bar_peer) : "memory");
           ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
           ptx::tc_fence_before();
           ptx::mbar_arrive(p_full);
+          PROF_T(7)  // hand-off
+#ifdef ATTN_PROFILE
+          prof_acc[8] += 1;
+#endif
         };
         for (int j = 0; j < NB - 1; ++j) block(j, std::false_type{});
         block(NB - 1, std::true_type{});
@@ -343,8 +398,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           ptx::tma_store_3d(&tmOut, ptx::smem_u32(sP) + q * 4096, h * HD, qt * QT + q * 32, seq);
           ptx::tma_store_commit();
         }
+#ifdef ATTN_PROFILE
+        {  // O read-out, normalisation, store: accounted separately
+          const long long _t = clock64();
+          if (q == 0 && lane == 0) atomicAdd(&g_attn_prof[9], static_cast<unsigned long long>(_t - prof_last));
+          prof_last = _t;
+        }
+#endif
       }
     }
+#ifdef ATTN_PROFILE
+    if (q == 0 && lane == 0)
+      for (int i = 0; i < 9; ++i) atomicAdd(&g_attn_prof[i], static_cast<unsigned long long>(prof_acc[i]));
+#endif
   }
 
   if (warp >= 4 && lane == 0) ptx::tma_store_wait_read();  // smem must outlive the bulk stores
@@ -363,6 +429,21 @@ const CUtensorMap& get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims
                                  const uint32_t* box);  // gemm_tc.cu
 const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
                                     uint32_t box_rows);  // gemm_tc.cu
+
+#ifdef ATTN_PROFILE
+void attn_prof_read(unsigned long long* host10, bool reset) {
+  DP_CUDA(cudaDeviceSynchronize());
+  DP_CUDA(cudaMemcpyFromSymbol(host10, g_attn_prof, sizeof(unsigned long long) * 10));
+  DP_CUDA(cudaMemcpyFromSymbol(host10 + 10, g_attn_prof_sj, sizeof(unsigned long long) * 5));
+  DP_CUDA(cudaMemcpyFromSymbol(host10 + 15, g_attn_prof_mma, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[10] = {0};
+    DP_CUDA(cudaMemcpyToSymbol(g_attn_prof, z, sizeof(z)));
+    DP_CUDA(cudaMemcpyToSymbol(g_attn_prof_sj, z, sizeof(unsigned long long) * 5));
+    DP_CUDA(cudaMemcpyToSymbol(g_attn_prof_mma, z, sizeof(unsigned long long) * 8));
+  }
+}
+#endif
 
 void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
   static bool configured = false;
