@@ -91,3 +91,37 @@ def test_synthetic_generators_match_oracle_copy():
 
     assert torch.equal(synthetic.synthetic_image_1536(3), O.synthetic_image_1536(3))
     assert np.array_equal(synthetic.synthetic_frame_u8(2, 90, 160), O.synthetic_frame_u8(2, 90, 160))
+
+
+def test_reference_call_sites_are_covered_by_the_drop_in_package():
+    """Every `depth_pro.<name>` the reference's scripts touch, and every keyword they pass to
+    create_model_and_transforms / infer, exists with the same spelling in the drop-in package (skipped where
+    /root/reference is not mounted, e.g. on the GPU box)."""
+    import ast
+    import inspect
+
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present")
+    scripts = ["generate_depth_maps.py", "img_to_normalized_pointcloud.py", "pointcloud_cleaner.py", "pointcloud_to_mesh.py",
+               "src/depth_pro/cli/run.py"]
+    attrs, create_kw, infer_kw = set(), set(), set()
+    for rel in scripts:
+        tree = ast.parse(open(os.path.join(ref, rel)).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id == "depth_pro":
+                attrs.add(node.attr)
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute):
+                if node.func.attr == "create_model_and_transforms":
+                    create_kw |= {k.arg for k in node.keywords}
+                if node.func.attr == "infer":
+                    infer_kw |= {k.arg for k in node.keywords}
+    assert {"create_model_and_transforms", "load_rgb"} <= attrs
+    for a in attrs:
+        assert hasattr(depth_pro, a), f"reference scripts use depth_pro.{a}"
+    assert create_kw <= set(inspect.signature(depth_pro.create_model_and_transforms).parameters), create_kw
+    assert infer_kw <= set(inspect.signature(depth_pro.DepthPro.infer).parameters), infer_kw
+    # the reference's signatures, parameter for parameter (depth_pro.py:72-76, 243-249)
+    assert list(inspect.signature(depth_pro.create_model_and_transforms).parameters) == ["config", "device", "precision"]
+    assert list(inspect.signature(depth_pro.DepthPro.infer).parameters) == ["self", "x", "f_px", "interpolation_mode"]
+    assert list(inspect.signature(depth_pro.load_rgb).parameters) == ["path", "auto_rotate", "remove_alpha"]
