@@ -122,9 +122,10 @@ def ground_kernels(lib, model, peaks):
     pts[:k, 1] = torch.randn(k, device=dev, generator=g) * 0.012
     pts[:k // 8, 1] += torch.rand(k // 8, device=dev, generator=g) * 0.16 + 0.02
     pts[k:, 1] = torch.rand(n - k, device=dev, generator=g) * 2.7 - 0.3
-    a = 0.2618
-    rot = torch.tensor([[1, 0, 0], [0, float(torch.cos(torch.tensor(a))), -float(torch.sin(torch.tensor(a)))],
-                        [0, float(torch.sin(torch.tensor(a))), float(torch.cos(torch.tensor(a)))]], device=dev)
+    import math
+
+    ca, sa = math.cos(math.radians(15.0)), math.sin(math.radians(15.0))
+    rot = torch.tensor([[1.0, 0.0, 0.0], [0.0, ca, -sa], [0.0, sa, ca]], device=dev)
     cam = pts @ rot.T + torch.tensor([0.0, -1.4, 0.0], device=dev)
     normal = (ctypes.c_double * 3)(0.0, float(rot[1, 1]), float(rot[2, 1]))
     d = 1.4 * float(rot[1, 1])
