@@ -7,4 +7,7 @@ namespace dp {
 void attention_f32(const float* qkv, float* out, int nseq, cudaStream_t s);
 void attention_bf16(const bf16* qkv, bf16* out, int nseq, cudaStream_t s);      // mma.sync (legacy tensor path)
 void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s);   // tcgen05 + TMEM + TMA
+// Experiment switch of the tcgen05 kernel (process-wide; overrides DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG):
+// expv 0..4 = share of the exponentials evaluated on the FMA pipe (see attention_tc.cu), pingpong 0/1.
+void attention_tc_set_variant(int expv, int pingpong);
 }  // namespace dp

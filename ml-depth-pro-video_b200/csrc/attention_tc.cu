@@ -23,6 +23,7 @@
 //                                 After the last block: O from TMEM, 1/l, bf16 store.
 // 296 stream slots x 2 units = 592 = 37 sequences x 16 heads: a frame's attention is perfectly balanced.
 // Register budget: the control warps drop to 40 registers, the softmax warps grow to 232 (setmaxnreg).
+#include <cstdlib>
 #include <type_traits>
 
 #include "attention.cuh"
@@ -84,8 +85,60 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// ---- exp2 variants of the softmax loop (template parameter EXPV, selected by DEPTHPRO_ATTN_EXP) -------------
+// For d = 64 the kernel's only hard bound is the MUFU (1024 cycles per 128x128 block against 512 of MMA,
+// DESIGN.md §9).  EXPV >= 1 processes the scores as fp32x2 pairs (fma.rn.f32x2 / add.rn.f32x2: half the issue
+// slots of the scalar chain); EXPV >= 2 additionally evaluates a compile-time share of the pairs on the FMA pipe
+// instead of the MUFU: round-to-nearest split x = n + f by the 1.5 * 2^23 magic add, degree-3 minimax polynomial
+// of 2^f on [-0.5, 0.5] (relative error 7.5e-5: 50x below the bf16 rounding of P), exponent patched in with
+// an integer add (bits(t) << 23 keeps exactly the low bits of n).  x is clamped at -125 so the exponent field
+// cannot wrap; 2^-125 contributes nothing to l.
+struct F2 {
+  unsigned long long u;
+};
+__device__ __forceinline__ F2 pack_f2(float a, float b) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.u) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(F2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v.u)); }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.u) : "l"(a.u), "l"(b.u), "l"(c.u));
+  return r;
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u));
+  return r;
+}
+__device__ __forceinline__ void exp2_poly2(F2 x, float& p0, float& p1) {
+  constexpr float MAGIC = 12582912.f;  // 1.5 * 2^23: x + MAGIC rounds x to the nearest integer in the low mantissa bits
+  float x0, x1;
+  unpack_f2(x, x0, x1);
+  const F2 xc = pack_f2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const F2 t = add2(xc, pack_f2(MAGIC, MAGIC));
+  const F2 n = add2(t, pack_f2(-MAGIC, -MAGIC));
+  const F2 f = fma2(n, pack_f2(-1.f, -1.f), xc);  // x - n, exact, in [-0.5, 0.5]
+  F2 p = fma2(f, pack_f2(0.0551716685295105f, 0.0551716685295105f), pack_f2(0.2426111251115799f, 0.2426111251115799f));
+  p = fma2(p, f, pack_f2(0.6932609677314758f, 0.6932609677314758f));
+  p = fma2(p, f, pack_f2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  unpack_f2(p, q0, q1);
+  unpack_f2(t, t0, t1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+// which (8-key group, pair) slots go to the FMA pipe: 0 / 0 / 25 % / 37.5 % / 50 % of the exponentials
+template <int EXPV>
+__device__ __forceinline__ constexpr bool poly_pair(int g8, int w) {
+  return EXPV == 2 ? w == 3 : EXPV == 3 ? (w == 3 || (w == 1 && (g8 & 1))) : EXPV == 4 ? (w & 1) != 0 : false;
+}
+
+template <int EXPV>
 __global__ void __launch_bounds__(THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, int nseq) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, int nseq,
+                    int pingpong) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -267,7 +320,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     // under the other's non-MUFU work.  Only the first min(blocks A, blocks B) blocks take part.
     auto units_of = [&](int sl) { return sl < n_units ? (n_units - sl + n_slots - 1) / n_slots : 0; };
     const int u_a = units_of(blockIdx.x), u_b = units_of(blockIdx.x + gridDim.x);
-    const int n_pp = (u_a < u_b ? u_a : u_b) * NQT * NB;   // blocks that ping-pong
+    const int n_pp = pingpong ? (u_a < u_b ? u_a : u_b) * NQT * NB : 0;   // blocks that ping-pong
     const int bar_mine = 1 + q + 4 * sidx, bar_peer = 1 + q + 4 * (sidx ^ 1);
     int T = 0;
     PROF_DECL
@@ -335,6 +388,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             __syncwarp();
           }
           const float mc = m_ref * c;
+          if constexpr (EXPV > 0) {
+            const F2 c2 = pack_f2(c, c), nmc2 = pack_f2(-mc, -mc);
+            F2 rs2[2] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
+#pragma unroll
+            for (int g8 = 0; g8 < NG; ++g8) {
+              uint32_t pk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const int k0 = g8 * 8 + 2 * w;  // even: k0 and k0 + 1 sit in the same 32-column chunk
+                if (k0 < NKEY) {
+                  const F2 x = fma2(pack_f2(__uint_as_float(sr[k0 >> 5][k0 & 31]), __uint_as_float(sr[k0 >> 5][(k0 & 31) + 1])),
+                                    c2, nmc2);
+                  float p0, p1;
+                  if (poly_pair<EXPV>(g8, w)) {
+                    exp2_poly2(x, p0, p1);
+                  } else {
+                    float x0, x1;
+                    unpack_f2(x, x0, x1);
+                    p0 = ex2(x0), p1 = ex2(x1);
+                  }
+                  if (k0 + 1 >= NKEY) p1 = 0.f;
+                  rs2[w & 1] = add2(rs2[w & 1], pack_f2(p0, p1));
+                  pk[w] = pack_bf16(p0, p1);
+                }
+              }
+              ptx::sts_u4(prow + (g8 >> 3) * TILE_BYTES + (((g8 & 7) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+            }
+            float a0, a1, b0, b1;
+            unpack_f2(rs2[0], a0, a1);
+            unpack_f2(rs2[1], b0, b1);
+            l += (a0 + a1) + (b0 + b1);
+          } else {
           float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int g8 = 0; g8 < NG; ++g8) {
@@ -352,6 +437,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             ptx::sts_u4(prow + (g8 >> 3) * TILE_BYTES + (((g8 & 7) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
           l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+          }
           PROF_T(6)  // exponentials + P stores
           if (G < n_pp && (sidx == 0 || G < n_pp - 1)) asm volatile("bar.arrive %0, 64;" ::"r"(bar_peer) : "memory");
           ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -445,23 +531,54 @@ void attn_prof_read(unsigned long long* host10, bool reset) {
 }
 #endif
 
-void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
+template <int EXPV>
+static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int nseq, int ctas, int pingpong, cudaStream_t s) {
   static bool configured = false;
-  static int sms = 0;
   if (!configured) {
-    DP_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    DP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<EXPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    configured = true;
+  }
+  launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM_BYTES, s, tm, tmo, nseq, pingpong);
+}
+
+// Experiment switches.  DEPTHPRO_ATTN_EXP = 0 (default: scalar chain, every exponential on
+// the MUFU) | 1 (fp32x2 chain) | 2 / 3 / 4 (fp32x2 chain, 25 / 37.5 / 50 % of the exponentials as a polynomial on the
+// FMA pipe).  DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams' exp phases overlap freely.
+static int g_expv = -1, g_pingpong = 1;
+
+void attention_tc_set_variant(int expv, int pingpong) {
+  if (expv < 0 || expv > 4) throw std::runtime_error("attention variant must be 0..4");
+  g_expv = expv, g_pingpong = pingpong != 0;
+}
+
+void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
+  static int sms = 0;
+  if (!sms) {
     int dev;
     DP_CUDA(cudaGetDevice(&dev));
     DP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
   }
+  if (g_expv < 0) {  // first call and no explicit choice: the environment, else the default
+    const char* e = getenv("DEPTHPRO_ATTN_EXP");
+    const char* p = getenv("DEPTHPRO_ATTN_PINGPONG");
+    attention_tc_set_variant(e ? atoi(e) : 0, p ? atoi(p) : 1);
+  }
+  const int expv = g_expv, pingpong = g_pingpong;
   const CUtensorMap& tm = get_tmap_2d_bf16(qkv, LDQ, static_cast<uint64_t>(nseq) * SEQ, LDQ, 64, 128);
   const uint64_t od[3] = {(uint64_t)LDO, (uint64_t)SEQ, (uint64_t)nseq};
   const uint64_t os[2] = {(uint64_t)LDO * 2, (uint64_t)SEQ * LDO * 2};
   const uint32_t ob[3] = {64, 32, 1};
   const CUtensorMap& tmo = get_tmap_bf16(out, 3, od, os, ob);
-  const int ctas = (nseq * NH + 1) / 2;  // two streams per CTA, one (sequence, head) unit at a time each
-  launch_pdl(attention_tc_kernel, dim3(ctas < sms ? ctas : sms), dim3(THREADS), SMEM_BYTES, s, tm, tmo, nseq);
+  int ctas = (nseq * NH + 1) / 2;  // two streams per CTA, one (sequence, head) unit at a time each
+  if (ctas > sms) ctas = sms;
+  switch (expv) {
+    case 0: launch_attention<0>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 1: launch_attention<1>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 2: launch_attention<2>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 3: launch_attention<3>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 4: launch_attention<4>(tm, tmo, nseq, ctas, pingpong, s); break;
+    default: throw std::runtime_error("attention variant not compiled in");
+  }
   DP_LAUNCH_CHECK();
 }
 

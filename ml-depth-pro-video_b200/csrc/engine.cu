@@ -1024,7 +1024,9 @@ void Engine::attention_test(int backend, const float* qkv, float* out, int n, cu
     bf16* q = to_dev<bf16>(qkv, nq, s);
     bf16* o = nullptr;
     DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&o), no * 2, s));
-    if (backend == 2) attention_bf16(q, o, n, s);
+    // backend bits 8-11: tcgen05 kernel variant + 1 (exp2 share on the FMA pipe), bit 12: no MUFU ping-pong
+    if ((backend >> 8) & 0xF) attention_tc_set_variant(((backend >> 8) & 0xF) - 1, !((backend >> 12) & 1));
+    if ((backend & 0xFF) == 2) attention_bf16(q, o, n, s);
     else attention_bf16_tc(q, o, n, s);
     convert<bf16, float>(o, out, (long long)no, s);
     DP_CUDA(cudaStreamSynchronize(s));
@@ -1049,6 +1051,10 @@ namespace dp {
 // Returns the mean milliseconds per launch over `iters` launches (CUDA events).
 float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   DP_CUDA(cudaSetDevice(device_));
+  // A/B bits (process-wide, sticky): 0x100 / 0x200 switch the fp32-residual L2 prefetch on / off
+  if (kind & 0x100) gemm_tc_set_res_prefetch(1);
+  if (kind & 0x200) gemm_tc_set_res_prefetch(0);
+  kind &= 0xFF;
   cudaStream_t s = nullptr;
   auto dalloc = [&](size_t bytes) {
     void* p = nullptr;
@@ -1094,6 +1100,7 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   } else if (kind == 4) {
     bf16* q = (bf16*)B((size_t)M * SEQ * 3 * EMB * 2);
     bf16* o = (bf16*)B((size_t)M * SEQ * EMB * 2);
+    if (N > 0) attention_tc_set_variant((N - 1) & 7, !(((N - 1) >> 3) & 1));  // N = 1 + variant + 8 * no-ping-pong
     run = [&, q, o] { attention_bf16_tc(q, o, M, s); };
   } else if (kind == 5) {
     float* x = (float*)B((size_t)M * EMB * 4);

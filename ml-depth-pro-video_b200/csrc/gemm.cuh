@@ -9,6 +9,7 @@ void gemm_simt(const GemmOp& op, cudaStream_t stream);
 // bf16 tcgen05 / TMEM / TMA path: activations / weights are bf16, fp32 accumulate.
 void gemm_tc(const GemmOp& op, cudaStream_t stream);
 void tmap_cache_clear();
+void gemm_tc_set_res_prefetch(int on);  // A/B switch of the fp32-residual forms' L2 prefetch (gemm_tc.cu)
 
 inline void gemm(int prec, const GemmOp& op, cudaStream_t stream) {
   double rows = op.M;

@@ -55,6 +55,7 @@ struct TileGeom {
   int unit_start[4];     // first unit of every group, unit_start[ngroups..3] = m_units
   int tiles_in_group[3]; // real m-tiles per group (tiles beyond are padding: loaded, not stored)
   int tma_out;           // 1: bf16 row-major output goes smem -> TMA store (full-line writes)
+  int res_prefetch;      // 1: fp32-residual forms: the producer warp pulls each tile's residual rows into L2
 };
 struct WeightMaps {
   CUtensorMap b[3];      // one weight tensor map per group
@@ -397,6 +398,7 @@ __device__ __forceinline__ void epi_rows4_resid32(float* __restrict__ out, long 
 //   EPI_TMA_LN   EPI_TMA for a LayerNorm-folded GEMM (qkv / fc1): acc * rstd[m] - rstd[m] * mean[m] * c[n] + d[n]
 //   EPI_RES32_LN EPI_RES32 that also emits bf16(x) and per-row partial (sum, sum of squares) for the next
 //                LayerNorm-folded GEMM (common.cuh GemmOp::ln_stats)
+constexpr int RES_PREFETCH_DEFAULT = 0;  // measured A/B pending: opt-in
 enum { EPI_TMA = 0, EPI_RES32 = 1, EPI_MISC = 2, EPI_TMA2 = 3, EPI_TMA_LN = 4, EPI_RES32_LN = 5 };
 
 template <int BN, int CL, int EPI>
@@ -494,6 +496,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int lmt = (mu - g.unit_start[gi]) * CL + crank;
           a_row = static_cast<int>(op.grp[gi].a_row_off) + lmt * BM;
           tmB = &tmW.b[gi];
+          if constexpr (EPI == EPI_RES32 || EPI == EPI_RES32_LN) {
+            // The epilogue reads this CTA's 128 x BN fp32 residual tile as 128-byte row segments (one per
+            // 32-column chunk): scattered at the DRAM page level, and proj / fc2 are bound by exactly that
+            // traffic.  Request the tile's rows as whole BN*4-byte runs into L2 one main loop ahead of the
+            // epilogue that consumes them.
+            if (g.res_prefetch) {
+              const int rows = op.grp[gi].M - lmt * BM;
+              const float* rp = reinterpret_cast<const float*>(op.res) +
+                                (op.grp[gi].o_row_off + static_cast<long long>(lmt) * BM) * op.ldres;
+              if (op.N == op.ldres) {
+                // full-width rows: the n-tiles of an m-unit run concurrently on neighbouring clusters, so the
+                // CTA of n-tile 0 requests its 128 whole rows for all of them -- one contiguous block, 4 rows
+                // (16 KB at N = 1024) per instruction (UBLKPF takes its address from a uniform register: the
+                // per-lane requests are issued one after the other)
+                const int r0 = 4 * lane, nr = rows - r0 < 4 ? rows - r0 : 4;
+                if (nt == 0 && nr > 0) ptx::prefetch_l2_bulk(rp + static_cast<long long>(r0) * op.ldres, nr * op.ldres * 4);
+              } else {
+                const int cols = op.N - nt * BN < BN ? op.N - nt * BN : BN;
+                for (int r = lane; r < BM && r < rows; r += 32)
+                  ptx::prefetch_l2_bulk(rp + static_cast<long long>(r) * op.ldres + nt * BN, cols * 4);
+              }
+              __syncwarp();
+            }
+          }
         }
         int tap = 0, c0 = 0;  // conv: running (filter tap, channel offset) of the k-block
         for (int kb = 0; kb < g.k_blocks; ++kb) {
@@ -966,6 +992,17 @@ const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t row
   return get_tmap(ptr, 2, dims, str, box);
 }
 
+// Residual L2 prefetch switch: DEPTHPRO_RES_PREFETCH=0/1 in the environment, or gemm_tc_set_res_prefetch() (A/B runs).
+static int g_res_prefetch = -1;
+void gemm_tc_set_res_prefetch(int on) { g_res_prefetch = on != 0; }
+static bool res_prefetch_enabled() {
+  if (g_res_prefetch < 0) {
+    const char* e = getenv("DEPTHPRO_RES_PREFETCH");
+    g_res_prefetch = e ? (atoi(e) != 0) : RES_PREFETCH_DEFAULT;
+  }
+  return g_res_prefetch != 0;
+}
+
 void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   GemmOp op = op_in;
   op.finish();
@@ -1076,6 +1113,8 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   const bool tma_epi = g.tma_out && !(op.res && op.res_f32);
   const int epi = resid32 ? EPI_RES32 : (tma_epi ? (op.out_relu ? EPI_TMA2 : EPI_TMA) : EPI_MISC);
   g.tma_out = tma_epi ? 1 : 0;
+  g.res_prefetch = (resid32 && res_prefetch_enabled() && op.ldres % 4 == 0 && op.N % 4 == 0 &&
+                    reinterpret_cast<uintptr_t>(op.res) % 16 == 0) ? 1 : 0;
   if (op.ln_stats != nullptr || op.ln_xb != nullptr) {
     // LayerNorm-folded forms exist for the ViT shapes only (BN = 256)
     DP_CHECK(bn == 256 && op.a_mode == A_ROWMAJOR, "LN-folded GEMM: N must be a multiple of 256");
