@@ -146,7 +146,10 @@ int dp_gemm_test(dp_engine* e, int backend, const float* A, const float* Wt, con
 int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float* w_oihw,
                     const float* bias, float* y_nhwc, int B, int H, int W, int Cin, int Cout,
                     void* stream);
-/* Attention core: qkv fp32 (n,577,3072) -> out fp32 (n,577,1024), 16 heads x 64. */
+/* Attention core: qkv fp32 (n,577,3072) -> out fp32 (n,577,1024), 16 heads x 64.  `backend` low byte: 0 fp32
+ * CUDA-core, 1 bf16 tcgen05, 2 bf16 mma.sync.  For backend 1, bits 8-11 = 1 + exp2 variant (0 default, 1 packed
+ * fp32x2 chain, 2 / 3 / 4 = 25 / 37.5 / 50 % of the exponentials on the FMA pipe) and bit 12 = no MUFU ping-pong;
+ * the choice is process-wide and sticky (same switch as DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG). */
 int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, int n,
                       void* stream);
 
@@ -155,7 +158,10 @@ int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, i
  * MxM map (Cin=K, Cout=N), 4 attention over M sequences, 5 LayerNorm over M rows.  Kinds 6-10 time
  * the HBM-bound kernels either side of the network on an M x N (H x W) image, L2 flushed before
  * every launch: 6 uint8 HWC -> fused transform + resize -> fp32 3x1536^2, 7 pyramid + 35-patch split +
- * im2col of one 1536^2 frame, 8 depth epilogue 1536^2 -> M x N, 9 unprojection + colours, 10 colourise. */
+ * im2col of one 1536^2 frame, 8 depth epilogue 1536^2 -> M x N, 9 unprojection + colours, 10 colourise.
+ * Kinds 11 / 12 / 13: kinds 0 / 1 / 2 in their LayerNorm-folded forms.  A/B bits (process-wide, sticky):
+ * kind | 0x100 / 0x200 switches the fp32-residual forms' L2 prefetch on / off (DEPTHPRO_RES_PREFETCH); for kind 4,
+ * N = 1 + exp2 variant + 8 * (no ping-pong) selects the attention variant (0 leaves it unchanged). */
 int dp_kernel_bench(dp_engine* e, int kind, int M, int N, int K, int iters, float* ms_out);
 
 /* Per-launch CUDA-event profiling of the hot kernels (used by bench.py for the roofline line).

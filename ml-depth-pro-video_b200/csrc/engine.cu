@@ -1054,6 +1054,10 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   // A/B bits (process-wide, sticky): 0x100 / 0x200 switch the fp32-residual L2 prefetch on / off
   if (kind & 0x100) gemm_tc_set_res_prefetch(1);
   if (kind & 0x200) gemm_tc_set_res_prefetch(0);
+  // 0x400: L2 persistence of the fp32 residual stream on, set-aside = `iters >> 16` MB (0 -> 96); 0x800: off
+  if (kind & 0x400) gemm_tc_set_l2_persist((iters >> 16) ? (iters >> 16) : 96);
+  if (kind & 0x800) gemm_tc_set_l2_persist(0);
+  iters &= 0xFFFF;
   kind &= 0xFF;
   cudaStream_t s = nullptr;
   auto dalloc = [&](size_t bytes) {

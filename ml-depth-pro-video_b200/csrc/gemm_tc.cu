@@ -16,6 +16,8 @@
 //   warps 4-11  epilogue      : tcgen05.ld (thread = one output row, 32 columns per load),
 //                               bias / GELU / ReLU / LayerScale / residual / pixel-shuffle
 //                               scatter, vectorised global stores; overlaps the next tile's MMA.
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <unordered_map>
 #include <vector>
@@ -937,6 +939,46 @@ int num_sms() {
   return n;
 }
 
+// L2 persistence of the fp32 residual stream (opt-in: DEPTHPRO_L2_PERSIST_MB=<MB>, or gemm_tc_set_l2_persist()).
+// The set-aside is device-wide (cudaLimitPersistingL2CacheSize) and comes out of every other kernel's L2.
+static long long g_l2_persist_req = -1;   // requested MB; -1 = read the environment on first use
+static size_t g_l2_carve = 0, g_l2_window = 0;
+static bool g_l2_applied = false;
+static void set_l2_persist_impl(int mb) {
+  g_l2_persist_req = mb < 0 ? 0 : mb;
+  g_l2_applied = false;
+}
+static void l2_apply() {
+  if (g_l2_persist_req < 0) {
+    const char* e = getenv("DEPTHPRO_L2_PERSIST_MB");
+    g_l2_persist_req = e ? atoll(e) : 0;
+  }
+  static bool ever_on = false;
+  if (g_l2_persist_req == 0 && !ever_on) {  // default path: never touch the device limits
+    g_l2_carve = 0, g_l2_applied = true;
+    return;
+  }
+  ever_on = true;
+  int dev = 0, max_persist = 0, max_window = 0;
+  DP_CUDA(cudaGetDevice(&dev));
+  DP_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  DP_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  size_t want = static_cast<size_t>(g_l2_persist_req) << 20;
+  if (want > static_cast<size_t>(max_persist)) want = static_cast<size_t>(max_persist);
+  DP_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+  if (want == 0) DP_CUDA(cudaCtxResetPersistingL2Cache());
+  g_l2_carve = want, g_l2_window = static_cast<size_t>(max_window);
+  g_l2_applied = true;
+  if (getenv("DEPTHPRO_VERBOSE"))
+    fprintf(stderr, "[depthpro] L2 persisting set-aside %zu MB (device max %d MB, window max %d MB)\n", want >> 20,
+            max_persist >> 20, max_window >> 20);
+}
+static size_t l2_persist_bytes() {
+  if (!g_l2_applied) l2_apply();
+  return g_l2_carve;
+}
+static size_t l2_window_max() { return g_l2_window; }
+
 template <int BN, int CL, int EPI>
 void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const WeightMaps& tmW,
             cudaStream_t stream) {
@@ -955,8 +997,26 @@ void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const W
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int na = 0;
+  if constexpr (EPI == EPI_RES32 || EPI == EPI_RES32_LN) {
+    // Keep the fp32 residual stream resident in L2 across the block's kernels: accesses of THIS launch that fall
+    // into x's window are marked persisting (proj / fc2 are bound by x's HBM round trip, scripts/ubench/rmw.cu).
+    const size_t carve = l2_persist_bytes();
+    if (carve) {
+      long long rows = 0;
+      for (int i = 0; i < op.ngroups; ++i) rows = std::max<long long>(rows, op.grp[i].o_row_off + op.grp[i].M);
+      size_t bytes = static_cast<size_t>(rows) * op.ldres * 4;
+      if (bytes > l2_window_max()) bytes = l2_window_max();
+      attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[na].val.accessPolicyWindow.base_ptr = const_cast<void*>(op.res);
+      attr[na].val.accessPolicyWindow.num_bytes = bytes;
+      attr[na].val.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : static_cast<float>(static_cast<double>(carve) / bytes);
+      attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      ++na;
+    }
+  }
   if (CL > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = CL, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
@@ -995,6 +1055,7 @@ const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t row
 // Residual L2 prefetch switch: DEPTHPRO_RES_PREFETCH=0/1 in the environment, or gemm_tc_set_res_prefetch() (A/B runs).
 static int g_res_prefetch = -1;
 void gemm_tc_set_res_prefetch(int on) { g_res_prefetch = on != 0; }
+void gemm_tc_set_l2_persist(int mb) { set_l2_persist_impl(mb); }
 static bool res_prefetch_enabled() {
   if (g_res_prefetch < 0) {
     const char* e = getenv("DEPTHPRO_RES_PREFETCH");

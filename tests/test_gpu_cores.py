@@ -221,3 +221,54 @@ def test_attention(backend, n, tol):
     q, k, v = src.reshape(n, 577, 3, 16, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n, 577, 1024)
     assert relerr(out, ref) < tol
+
+
+@pytest.mark.parametrize("expv,pingpong", [(1, 1), (2, 1), (3, 1), (4, 1), (0, 0), (2, 0), (4, 0)])
+def test_attention_exp2_variants(expv, pingpong):
+    """Opt-in variants of the tcgen05 kernel's exp2 chain (DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG, selected here
+    through the backend bits): packed fp32x2 chain, 25 / 37.5 / 50 % of the exponentials as a degree-3 polynomial on
+    the FMA pipe, with and without the MUFU ping-pong.  Same tolerance as the default kernel, and within 2e-3 of it."""
+    n = 3
+    g = torch.Generator(device=DEV).manual_seed(100 + n)
+    qkv = torch.randn(n, 577, 3072, device=DEV, generator=g)
+    qkv[1] *= 3.0   # sharper softmax: scores far below the row maximum go through the clamped polynomial range
+    out = torch.empty(n, 577, 1024, device=DEV)
+    base = torch.empty_like(out)
+    try:
+        backend = 1 | ((expv + 1) << 8) | ((1 - pingpong) << 12)
+        _capi.check(lib().dp_attention_test(engine(), backend, qkv.data_ptr(), out.data_ptr(), n, stream()))
+    finally:  # the switch is process-wide: always go back to the default kernel
+        _capi.check(lib().dp_attention_test(engine(), 1 | (1 << 8), qkv.data_ptr(), base.data_ptr(), n, stream()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.bfloat16().double().reshape(n, 577, 3, 16, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n, 577, 1024)
+    assert relerr(out, ref) < 1.5e-2
+    assert float((out - base).abs().mean() / base.abs().mean()) < 2e-3
+
+
+def test_residual_l2_prefetch_is_a_pure_hint():
+    """DEPTHPRO_RES_PREFETCH (cp.async.bulk.prefetch.L2 of the fp32 residual rows by the producer warp) must not
+    change a single bit of the proj / fc2 form's output.  Switched through dp_kernel_bench's A/B bits."""
+    import ctypes
+
+    M, N, K = 21349, 1024, 1024
+    g = torch.Generator(device=DEV).manual_seed(77)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    res = torch.randn(M, N, device=DEV, generator=g)
+    ms = ctypes.c_float()
+    outs = []
+    try:
+        for bit in (0x200, 0x100):  # off, on
+            _capi.check(lib().dp_kernel_bench(engine(), 2 | bit, 256, 256, 64, 1, ctypes.byref(ms)))
+            C = res.clone()
+            _capi.check(lib().dp_gemm_test(engine(), 1, A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K,
+                                           0x200, stream()))
+            torch.cuda.synchronize()
+            outs.append(C)
+    finally:
+        _capi.check(lib().dp_kernel_bench(engine(), 2 | 0x200, 256, 256, 64, 1, ctypes.byref(ms)))
+    assert torch.equal(outs[0], outs[1])
+    ref = res.double() + b.double() * (_bf16r(A).double() @ _bf16r(W).double().t() + b.double())
+    assert relerr(outs[1], ref) < 2e-5
