@@ -147,9 +147,11 @@ int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float*
                     const float* bias, float* y_nhwc, int B, int H, int W, int Cin, int Cout,
                     void* stream);
 /* Attention core: qkv fp32 (n,577,3072) -> out fp32 (n,577,1024), 16 heads x 64.  `backend` low byte: 0 fp32
- * CUDA-core, 1 bf16 tcgen05, 2 bf16 mma.sync.  For backend 1, bits 8-11 = 1 + exp2 variant (0 default, 1 packed
- * fp32x2 chain, 2 / 3 / 4 = 25 / 37.5 / 50 % of the exponentials on the FMA pipe) and bit 12 = no MUFU ping-pong;
- * the choice is process-wide and sticky (same switch as DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG). */
+ * CUDA-core, 1 bf16 tcgen05, 2 bf16 mma.sync.  For backend 1, bits 8-11 = 1 + variant of the softmax exp2 chain
+ * (0 scalar chain + strict MUFU ping-pong, 1 packed fp32x2 chain, 2 / 3 / 4 = 25 / 37.5 / 50 % of the exponentials
+ * on the FMA pipe, 5-8 early hand-over of the MUFU turn; 5 is the default), 0xF = back to the default, and
+ * bit 12 = no MUFU ping-pong; the choice is process-wide and sticky (same switch as DEPTHPRO_ATTN_EXP /
+ * DEPTHPRO_ATTN_PINGPONG). */
 int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, int n,
                       void* stream);
 
@@ -161,7 +163,7 @@ int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, i
  * im2col of one 1536^2 frame, 8 depth epilogue 1536^2 -> M x N, 9 unprojection + colours, 10 colourise.
  * Kinds 11 / 12 / 13: kinds 0 / 1 / 2 in their LayerNorm-folded forms.  A/B bits (process-wide, sticky):
  * kind | 0x100 / 0x200 switches the fp32-residual forms' L2 prefetch on / off (DEPTHPRO_RES_PREFETCH); for kind 4,
- * N = 1 + exp2 variant + 8 * (no ping-pong) selects the attention variant (0 leaves it unchanged). */
+ * N = 1 + exp2 variant + 16 * (no ping-pong) selects the attention variant (0 leaves it unchanged). */
 int dp_kernel_bench(dp_engine* e, int kind, int M, int N, int K, int iters, float* ms_out);
 
 /* Per-launch CUDA-event profiling of the hot kernels (used by bench.py for the roofline line).

@@ -8,6 +8,6 @@ void attention_f32(const float* qkv, float* out, int nseq, cudaStream_t s);
 void attention_bf16(const bf16* qkv, bf16* out, int nseq, cudaStream_t s);      // mma.sync (legacy tensor path)
 void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s);   // tcgen05 + TMEM + TMA
 // Experiment switch of the tcgen05 kernel (process-wide; overrides DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG):
-// expv 0..4 = share of the exponentials evaluated on the FMA pipe (see attention_tc.cu), pingpong 0/1.
+// expv 0..8 = form of the softmax exp2 chain (see attention_tc.cu), -1 = back to the default; pingpong 0/1.
 void attention_tc_set_variant(int expv, int pingpong);
 }  // namespace dp

@@ -135,6 +135,14 @@ __device__ __forceinline__ constexpr bool poly_pair(int g8, int w) {
   return EXPV == 2 ? w == 3 : EXPV == 3 ? (w == 3 || (w == 1 && (g8 & 1))) : EXPV == 4 ? (w & 1) != 0 : false;
 }
 
+// Variants 5-8 keep every exponential on the MUFU but hand the MUFU turn to the other stream EARLY, after 12 or 8
+// of the block's 16 eight-key groups, so the peer's first exponentials overlap this stream's last ones
+// (5 / 6: packed chain, 7 / 8: scalar chain).
+template <int EXPV>
+__device__ __forceinline__ constexpr bool packed_chain() { return (EXPV >= 1 && EXPV <= 6); }
+template <int EXPV>
+__device__ __forceinline__ constexpr int arrive_at() { return (EXPV == 5 || EXPV == 7) ? 12 : (EXPV == 6 || EXPV == 8) ? 8 : 16; }
+
 template <int EXPV>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, int nseq,
@@ -388,11 +396,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             __syncwarp();
           }
           const float mc = m_ref * c;
-          if constexpr (EXPV > 0) {
+          constexpr int ARR = arrive_at<EXPV>() >= 16 ? 16 : (LAST ? arrive_at<EXPV>() * NG / 16 : arrive_at<EXPV>());
+          const bool pp_arrive = G < n_pp && (sidx == 0 || G < n_pp - 1);
+          if constexpr (packed_chain<EXPV>()) {
             const F2 c2 = pack_f2(c, c), nmc2 = pack_f2(-mc, -mc);
             F2 rs2[2] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
 #pragma unroll
             for (int g8 = 0; g8 < NG; ++g8) {
+              if (ARR < 16 && g8 == ARR && pp_arrive) asm volatile("bar.arrive %0, 64;" ::"r"(bar_peer) : "memory");
               uint32_t pk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
               for (int w = 0; w < 4; ++w) {
@@ -423,6 +434,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int g8 = 0; g8 < NG; ++g8) {
+            if (ARR < 16 && g8 == ARR && pp_arrive) asm volatile("bar.arrive %0, 64;" ::"r"(bar_peer) : "memory");
             uint32_t pk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -439,7 +451,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
           }
           PROF_T(6)  // exponentials + P stores
-          if (G < n_pp && (sidx == 0 || G < n_pp - 1)) asm volatile("bar.arrive %0, 64;" ::"r"(bar_peer) : "memory");
+          if (ARR >= 16 && pp_arrive) asm volatile("bar.arrive %0, 64;" ::"r"(bar_peer) : "memory");
           ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
           ptx::tc_fence_before();
           ptx::mbar_arrive(p_full);
@@ -541,13 +553,22 @@ static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int 
   launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM_BYTES, s, tm, tmo, nseq, pingpong);
 }
 
-// Experiment switches.  DEPTHPRO_ATTN_EXP = 0 (default: scalar chain, every exponential on
-// the MUFU) | 1 (fp32x2 chain) | 2 / 3 / 4 (fp32x2 chain, 25 / 37.5 / 50 % of the exponentials as a polynomial on the
-// FMA pipe).  DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams' exp phases overlap freely.
+// Variants of the softmax exp2 chain, DEPTHPRO_ATTN_EXP = 0..8:
+//   0 scalar chain, every exponential on the MUFU, strict MUFU ping-pong between the two streams (the round's v5 kernel)
+//   1 packed fp32x2 chain;  2 / 3 / 4 packed chain with 25 / 37.5 / 50 % of the exponentials as a polynomial on the FMA pipe
+//   5 / 6 packed chain, the MUFU turn handed to the other stream after 12 / 8 of a block's 16 eight-key groups
+//   7 / 8 the same hand-over with the scalar chain
+// Default 5.  DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams' exp phases overlap freely (slower).
 static int g_expv = -1, g_pingpong = 1;
 
+constexpr int ATTN_EXP_DEFAULT = 5;  // measured on B200 (profiles/r1_v6_attention_*): 92.9 -> 89.2 us per layer, +1.8 % frames/s
+
 void attention_tc_set_variant(int expv, int pingpong) {
-  if (expv < 0 || expv > 4) throw std::runtime_error("attention variant must be 0..4");
+  if (expv < 0) {  // back to the environment's / built-in default on the next launch
+    g_expv = -1;
+    return;
+  }
+  if (expv > 8) throw std::runtime_error("attention variant must be 0..8");
   g_expv = expv, g_pingpong = pingpong != 0;
 }
 
@@ -561,7 +582,7 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
   if (g_expv < 0) {  // first call and no explicit choice: the environment, else the default
     const char* e = getenv("DEPTHPRO_ATTN_EXP");
     const char* p = getenv("DEPTHPRO_ATTN_PINGPONG");
-    attention_tc_set_variant(e ? atoi(e) : 0, p ? atoi(p) : 1);
+    attention_tc_set_variant(e && atoi(e) >= 0 ? atoi(e) : ATTN_EXP_DEFAULT, p ? atoi(p) : 1);
   }
   const int expv = g_expv, pingpong = g_pingpong;
   const CUtensorMap& tm = get_tmap_2d_bf16(qkv, LDQ, static_cast<uint64_t>(nseq) * SEQ, LDQ, 64, 128);
@@ -577,6 +598,10 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
     case 2: launch_attention<2>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 3: launch_attention<3>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 4: launch_attention<4>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 5: launch_attention<5>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 6: launch_attention<6>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 7: launch_attention<7>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 8: launch_attention<8>(tm, tmo, nseq, ctas, pingpong, s); break;
     default: throw std::runtime_error("attention variant not compiled in");
   }
   DP_LAUNCH_CHECK();

@@ -6,7 +6,7 @@
   3. the full frame (model.infer, bf16) with the default and with the fastest variant: frames/s from CUDA events
      and depth parity against the reference's recorded output (tests/golden/reference_outputs.npz).
 
-    python scripts/attn_variants.py [--no-model] > gpurun_out/attn_variants.json
+    [ATTN_VARIANTS=0,1,5,6,7,8 ATTN_PINGPONG=1] python scripts/attn_variants.py [--no-model] > gpurun_out/attn_variants.json
 """
 import ctypes
 import json
@@ -29,7 +29,10 @@ h = ctypes.c_void_p()
 _capi.check(lib.dp_engine_create(0, _capi.PREC_BF16, 1, ctypes.byref(h)))
 st = torch.cuda.current_stream(dev).cuda_stream
 NAMES = {0: "scalar, all MUFU (default)", 1: "fp32x2 chain, all MUFU", 2: "fp32x2, 25% poly", 3: "fp32x2, 37.5% poly",
-         4: "fp32x2, 50% poly"}
+         4: "fp32x2, 50% poly", 5: "fp32x2 chain, MUFU turn handed over at 12/16", 6: "fp32x2 chain, handed over at 8/16",
+         7: "scalar chain, handed over at 12/16", 8: "scalar chain, handed over at 8/16"}
+VARIANTS = [int(v) for v in os.environ.get("ATTN_VARIANTS", "0,1,2,3,4").split(",")]
+PPS = [int(v) for v in os.environ.get("ATTN_PINGPONG", "1,0").split(",")]
 
 
 def parity(v, pp, n):
@@ -46,13 +49,13 @@ def parity(v, pp, n):
 
 def timed(v, pp, iters=30):
     ms = ctypes.c_float()
-    _capi.check(lib.dp_kernel_bench(h, 4, 37, 1 + v + 8 * (1 - pp), 0, iters, ctypes.byref(ms)))
+    _capi.check(lib.dp_kernel_bench(h, 4, 37, 1 + v + 16 * (1 - pp), 0, iters, ctypes.byref(ms)))
     return ms.value * 1e3
 
 
 res = {"variants": []}
-for pp in (1, 0):
-    for v in range(5):
+for pp in PPS:
+    for v in VARIANTS:
         e3 = parity(v, pp, 3)
         e37 = parity(v, pp, 37) if pp == 1 else None
         us = min(timed(v, pp), timed(v, pp))

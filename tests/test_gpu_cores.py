@@ -223,11 +223,12 @@ def test_attention(backend, n, tol):
     assert relerr(out, ref) < tol
 
 
-@pytest.mark.parametrize("expv,pingpong", [(1, 1), (2, 1), (3, 1), (4, 1), (0, 0), (2, 0), (4, 0)])
+@pytest.mark.parametrize("expv,pingpong", [(0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (6, 1), (7, 1), (8, 1), (0, 0), (2, 0), (5, 0)])
 def test_attention_exp2_variants(expv, pingpong):
-    """Opt-in variants of the tcgen05 kernel's exp2 chain (DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG, selected here
-    through the backend bits): packed fp32x2 chain, 25 / 37.5 / 50 % of the exponentials as a degree-3 polynomial on
-    the FMA pipe, with and without the MUFU ping-pong.  Same tolerance as the default kernel, and within 2e-3 of it."""
+    """Non-default variants of the tcgen05 kernel's exp2 chain (DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG, selected
+    here through the backend bits): scalar / packed fp32x2 chain, 25 / 37.5 / 50 % of the exponentials as a degree-3
+    polynomial on the FMA pipe, early hand-over of the MUFU turn, with and without the ping-pong.  Same tolerance as
+    the default kernel (variant 5), and within 2e-3 of it."""
     n = 3
     g = torch.Generator(device=DEV).manual_seed(100 + n)
     qkv = torch.randn(n, 577, 3072, device=DEV, generator=g)
@@ -238,7 +239,7 @@ def test_attention_exp2_variants(expv, pingpong):
         backend = 1 | ((expv + 1) << 8) | ((1 - pingpong) << 12)
         _capi.check(lib().dp_attention_test(engine(), backend, qkv.data_ptr(), out.data_ptr(), n, stream()))
     finally:  # the switch is process-wide: always go back to the default kernel
-        _capi.check(lib().dp_attention_test(engine(), 1 | (1 << 8), qkv.data_ptr(), base.data_ptr(), n, stream()))
+        _capi.check(lib().dp_attention_test(engine(), 1 | (0xF << 8), qkv.data_ptr(), base.data_ptr(), n, stream()))
     torch.cuda.synchronize()
     q, k, v = qkv.bfloat16().double().reshape(n, 577, 3, 16, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n, 577, 1024)
