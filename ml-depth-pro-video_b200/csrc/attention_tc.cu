@@ -132,16 +132,19 @@ __device__ __forceinline__ void exp2_poly2(F2 x, float& p0, float& p1) {
 // which (8-key group, pair) slots go to the FMA pipe: 0 / 0 / 25 % / 37.5 % / 50 % of the exponentials
 template <int EXPV>
 __device__ __forceinline__ constexpr bool poly_pair(int g8, int w) {
-  return EXPV == 2 ? w == 3 : EXPV == 3 ? (w == 3 || (w == 1 && (g8 & 1))) : EXPV == 4 ? (w & 1) != 0 : false;
+  return (EXPV == 2 || EXPV == 11) ? w == 3 : EXPV == 3 ? (w == 3 || (w == 1 && (g8 & 1))) : EXPV == 4 ? (w & 1) != 0 : false;
 }
 
 // Variants 5-8 keep every exponential on the MUFU but hand the MUFU turn to the other stream EARLY, after 12 or 8
 // of the block's 16 eight-key groups, so the peer's first exponentials overlap this stream's last ones
-// (5 / 6: packed chain, 7 / 8: scalar chain).
+// (5 / 6: packed chain, 7 / 8: scalar chain; 9 / 10: packed chain, hand-over after 14 / 10 groups; 11: variant 2's
+// 25 % polynomial share with the hand-over after 12).
 template <int EXPV>
-__device__ __forceinline__ constexpr bool packed_chain() { return (EXPV >= 1 && EXPV <= 6); }
+__device__ __forceinline__ constexpr bool packed_chain() { return (EXPV >= 1 && EXPV <= 6) || EXPV >= 9; }
 template <int EXPV>
-__device__ __forceinline__ constexpr int arrive_at() { return (EXPV == 5 || EXPV == 7) ? 12 : (EXPV == 6 || EXPV == 8) ? 8 : 16; }
+__device__ __forceinline__ constexpr int arrive_at() {
+  return (EXPV == 5 || EXPV == 7 || EXPV == 11) ? 12 : (EXPV == 6 || EXPV == 8) ? 8 : EXPV == 9 ? 14 : EXPV == 10 ? 10 : 16;
+}
 
 template <int EXPV>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -553,11 +556,11 @@ static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int 
   launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM_BYTES, s, tm, tmo, nseq, pingpong);
 }
 
-// Variants of the softmax exp2 chain, DEPTHPRO_ATTN_EXP = 0..8:
+// Variants of the softmax exp2 chain, DEPTHPRO_ATTN_EXP = 0..11:
 //   0 scalar chain, every exponential on the MUFU, strict MUFU ping-pong between the two streams (the round's v5 kernel)
 //   1 packed fp32x2 chain;  2 / 3 / 4 packed chain with 25 / 37.5 / 50 % of the exponentials as a polynomial on the FMA pipe
 //   5 / 6 packed chain, the MUFU turn handed to the other stream after 12 / 8 of a block's 16 eight-key groups
-//   7 / 8 the same hand-over with the scalar chain
+//   7 / 8 the same hand-over with the scalar chain;  9 / 10 packed chain, hand-over after 14 / 10;  11 = 2 + hand-over after 12
 // Default 5.  DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams' exp phases overlap freely (slower).
 static int g_expv = -1, g_pingpong = 1;
 
@@ -568,7 +571,7 @@ void attention_tc_set_variant(int expv, int pingpong) {
     g_expv = -1;
     return;
   }
-  if (expv > 8) throw std::runtime_error("attention variant must be 0..8");
+  if (expv > 11) throw std::runtime_error("attention variant must be 0..11");
   g_expv = expv, g_pingpong = pingpong != 0;
 }
 
@@ -602,6 +605,9 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
     case 6: launch_attention<6>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 7: launch_attention<7>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 8: launch_attention<8>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 9: launch_attention<9>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 10: launch_attention<10>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 11: launch_attention<11>(tm, tmo, nseq, ctas, pingpong, s); break;
     default: throw std::runtime_error("attention variant not compiled in");
   }
   DP_LAUNCH_CHECK();

@@ -30,7 +30,9 @@ _capi.check(lib.dp_engine_create(0, _capi.PREC_BF16, 1, ctypes.byref(h)))
 st = torch.cuda.current_stream(dev).cuda_stream
 NAMES = {0: "scalar, all MUFU (default)", 1: "fp32x2 chain, all MUFU", 2: "fp32x2, 25% poly", 3: "fp32x2, 37.5% poly",
          4: "fp32x2, 50% poly", 5: "fp32x2 chain, MUFU turn handed over at 12/16", 6: "fp32x2 chain, handed over at 8/16",
-         7: "scalar chain, handed over at 12/16", 8: "scalar chain, handed over at 8/16"}
+         7: "scalar chain, handed over at 12/16", 8: "scalar chain, handed over at 8/16",
+         9: "fp32x2 chain, handed over at 14/16", 10: "fp32x2 chain, handed over at 10/16",
+         11: "fp32x2, 25% poly, handed over at 12/16"}
 VARIANTS = [int(v) for v in os.environ.get("ATTN_VARIANTS", "0,1,2,3,4").split(",")]
 PPS = [int(v) for v in os.environ.get("ATTN_PINGPONG", "1,0").split(",")]
 

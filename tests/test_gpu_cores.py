@@ -223,7 +223,7 @@ def test_attention(backend, n, tol):
     assert relerr(out, ref) < tol
 
 
-@pytest.mark.parametrize("expv,pingpong", [(0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (6, 1), (7, 1), (8, 1), (0, 0), (2, 0), (5, 0)])
+@pytest.mark.parametrize("expv,pingpong", [(0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (6, 1), (7, 1), (8, 1), (9, 1), (10, 1), (11, 1), (0, 0), (2, 0), (5, 0)])
 def test_attention_exp2_variants(expv, pingpong):
     """Non-default variants of the tcgen05 kernel's exp2 chain (DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG, selected
     here through the backend bits): scalar / packed fp32x2 chain, 25 / 37.5 / 50 % of the exponentials as a degree-3
