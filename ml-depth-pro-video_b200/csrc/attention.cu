@@ -281,10 +281,9 @@ void attention_f32(const float* qkv, float* out, int nseq, cudaStream_t s) {
 
 void attention_bf16(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
   constexpr int SMEM = B_QT * 128 + 4 * B_KT * 128;  // 48 KB
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0};
+  if (first_use_on_device(configured)) {
     DP_CUDA(cudaFuncSetAttribute(attention_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
   }
   dim3 grid(nseq * NH, (SEQ + B_QT - 1) / B_QT);
   attention_bf16_kernel<<<grid, B_THREADS, SMEM, s>>>(qkv, out);

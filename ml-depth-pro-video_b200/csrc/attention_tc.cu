@@ -548,10 +548,9 @@ void attn_prof_read(unsigned long long* host10, bool reset) {
 
 template <int EXPV>
 static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int nseq, int ctas, int pingpong, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0};
+  if (first_use_on_device(configured)) {
     DP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<EXPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    configured = true;
   }
   launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM_BYTES, s, tm, tmo, nseq, pingpong);
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
 
@@ -72,6 +73,15 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   DP_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
+// cudaFuncSetAttribute (opt-in dynamic shared memory) applies to the CURRENT device only.  One process per GPU is the
+// intended deployment, but two engines on two GPUs in one process must work too: every launcher keeps a bit per device.
+inline bool first_use_on_device(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  DP_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (mask.fetch_or(bit) & bit) == 0;
 }
 
 #define DP_LAUNCH_CHECK()                \

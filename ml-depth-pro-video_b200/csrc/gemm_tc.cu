@@ -984,10 +984,9 @@ void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const W
             cudaStream_t stream) {
   using C = Cfg<BN, CL, EPI>;
   constexpr size_t SMEM = C::STAGES * C::STAGE + 1024 /*align*/ + 256 /*barriers*/ + 8 * C::STG_WARP;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0};
+  if (first_use_on_device(configured)) {
     DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    configured = true;
   }
   const int units = g.m_units * g.n_tiles;
   const int max_clusters = num_sms() / CL;
