@@ -125,3 +125,22 @@ def test_reference_call_sites_are_covered_by_the_drop_in_package():
     assert list(inspect.signature(depth_pro.create_model_and_transforms).parameters) == ["config", "device", "precision"]
     assert list(inspect.signature(depth_pro.DepthPro.infer).parameters) == ["self", "x", "f_px", "interpolation_mode"]
     assert list(inspect.signature(depth_pro.load_rgb).parameters) == ["path", "auto_rotate", "remove_alpha"]
+
+
+def test_environment_switches_are_documented():
+    """Every DEPTHPRO_* switch the sources read is listed in INTEGRATION.md §E / README.md, and every documented one
+    is read somewhere (documentation that names a switch the code no longer honours is worse than none)."""
+    import glob
+    import re
+
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read() + open(os.path.join(ROOT, "README.md")).read()
+    documented = set(re.findall(r"DEPTHPRO_[A-Z0-9_]+", doc))
+    pkg = os.path.join(ROOT, "ml-depth-pro-video_b200")
+    files = (glob.glob(os.path.join(pkg, "csrc", "*.cu")) + glob.glob(os.path.join(pkg, "csrc", "*.cuh"))
+             + glob.glob(os.path.join(pkg, "depth_pro", "*.py")) + [os.path.join(ROOT, "bench.py")])
+    src = "".join(open(f).read() for f in files)
+    used = set(re.findall(r'getenv\("(DEPTHPRO_[A-Z0-9_]+)"\)', src))
+    used |= set(re.findall(r'environ(?:\.get)?[\(\[]"(DEPTHPRO_[A-Z0-9_]+)"', src))
+    assert used, "no switches found: the patterns above no longer match the sources"
+    assert used - documented == set(), f"undocumented switches: {sorted(used - documented)}"
+    assert documented - used == set(), f"documented but unused switches: {sorted(documented - used)}"
