@@ -132,7 +132,7 @@ __device__ __forceinline__ void exp2_poly2(F2 x, float& p0, float& p1) {
 // which (8-key group, pair) slots go to the FMA pipe: 0 / 0 / 25 % / 37.5 % / 50 % of the exponentials
 template <int EXPV>
 __device__ __forceinline__ constexpr bool poly_pair(int g8, int w) {
-  return (EXPV == 2 || EXPV == 11) ? w == 3 : EXPV == 3 ? (w == 3 || (w == 1 && (g8 & 1))) : EXPV == 4 ? (w & 1) != 0 : false;
+  return (EXPV == 2 || EXPV == 11 || EXPV == 13) ? w == 3 : EXPV == 3 ? (w == 3 || (w == 1 && (g8 & 1))) : EXPV == 4 ? (w & 1) != 0 : false;
 }
 
 // Variants 5-8 keep every exponential on the MUFU but hand the MUFU turn to the other stream EARLY, after 12 or 8
@@ -141,9 +141,15 @@ __device__ __forceinline__ constexpr bool poly_pair(int g8, int w) {
 // 25 % polynomial share with the hand-over after 12).
 template <int EXPV>
 __device__ __forceinline__ constexpr bool packed_chain() { return (EXPV >= 1 && EXPV <= 6) || EXPV >= 9; }
+// Variants 12 / 13 (= 5 / 11 otherwise) keep P out of shared memory: the softmax threads write the packed bf16 pairs
+// to 64 TMEM columns of their stream with tcgen05.st and the P V MMA takes its A operand from there (no 16 STS.128 +
+// generic->async proxy fence per block, half the shared-memory operand reads of P V).  NOT YET RUN ON A GPU: written in
+// the round's last, GPU-less hours; ptxas accepts the instruction forms, parity and timing are round-2 work.
+template <int EXPV>
+__device__ __forceinline__ constexpr bool p_in_tmem() { return EXPV == 12 || EXPV == 13; }
 template <int EXPV>
 __device__ __forceinline__ constexpr int arrive_at() {
-  return (EXPV == 5 || EXPV == 7 || EXPV == 11) ? 12 : (EXPV == 6 || EXPV == 8) ? 8 : EXPV == 9 ? 14 : EXPV == 10 ? 10 : 16;
+  return (EXPV == 5 || EXPV == 7 || EXPV >= 11) ? 12 : (EXPV == 6 || EXPV == 8) ? 8 : EXPV == 9 ? 14 : EXPV == 10 ? 10 : 16;
 }
 
 template <int EXPV>
@@ -268,7 +274,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 // A = P: 64-key half (ks >> 2), +32 B per K=16 step; B = V (MN-major): +16 keys = 2048 B
                 const uint64_t da = desc(p_lo + (ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2);
                 const uint64_t db = desc(v_lo + st * (TILE_BYTES >> 4) + ks * (2048 >> 4));
-                ptx::umma_bf16(tO, da, db, IDESC_PV, (jj | ks) != 0);
+                if constexpr (p_in_tmem<EXPV>()) ptx::umma_bf16_ts(tO, tmem_base + 192 + ks * 8, db, IDESC_PV, (jj | ks) != 0);
+                else ptx::umma_bf16(tO, da, db, IDESC_PV, (jj | ks) != 0);
               }
               ptx::umma_commit(pv_done);
               ptx::umma_commit(&v_empty[st]);
@@ -320,7 +327,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const int q = warp & 3;             // TMEM lane quadrant
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr, tO = tmem_base + 128 + lane_addr;
+    const uint32_t tS = tmem_base + lane_addr, tO = tmem_base + 128 + lane_addr, tP = tmem_base + 192 + lane_addr;
     const uint32_t prow = ptx::smem_u32(sP) + row * 128;
     const float c = 0.125f * 1.4426950408889634f;  // softmax scale * log2(e)
     // MUFU ping-pong.  The softmax warps of quadrant q of both streams sit on the same SM sub-partition
@@ -404,6 +411,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           if constexpr (packed_chain<EXPV>()) {
             const F2 c2 = pack_f2(c, c), nmc2 = pack_f2(-mc, -mc);
             F2 rs2[2] = {pack_f2(0.f, 0.f), pack_f2(0.f, 0.f)};
+            [[maybe_unused]] uint32_t pacc[32];  // p_in_tmem: the packed pairs of 64 keys, stored with one tcgen05.st
 #pragma unroll
             for (int g8 = 0; g8 < NG; ++g8) {
               if (ARR < 16 && g8 == ARR && pp_arrive) asm volatile("bar.arrive %0, 64;" ::"r"(bar_peer) : "memory");
@@ -427,8 +435,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                   pk[w] = pack_bf16(p0, p1);
                 }
               }
-              ptx::sts_u4(prow + (g8 >> 3) * TILE_BYTES + (((g8 & 7) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+              if constexpr (p_in_tmem<EXPV>()) {
+                // column c of the stream's P region holds keys (2c, 2c + 1) of this thread's row
+#pragma unroll
+                for (int w = 0; w < 4; ++w) pacc[(g8 & 7) * 4 + w] = pk[w];
+                if ((g8 & 7) == 7) ptx::tmem_st32(tP + (g8 >> 3) * 32, pacc);
+                if (LAST && g8 == NG - 1) {  // 80-key tail: keys 64..79 -> columns 32..39
+                  uint32_t tail[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) tail[i] = pacc[i];
+                  ptx::tmem_st8(tP + 32, tail);
+                }
+              } else {
+                ptx::sts_u4(prow + (g8 >> 3) * TILE_BYTES + (((g8 & 7) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+              }
             }
+            if constexpr (p_in_tmem<EXPV>()) ptx::tmem_st_wait();
             float a0, a1, b0, b1;
             unpack_f2(rs2[0], a0, a1);
             unpack_f2(rs2[1], b0, b1);
@@ -455,7 +477,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           }
           PROF_T(6)  // exponentials + P stores
           if (ARR >= 16 && pp_arrive) asm volatile("bar.arrive %0, 64;" ::"r"(bar_peer) : "memory");
-          ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          if constexpr (!p_in_tmem<EXPV>()) ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
           ptx::tc_fence_before();
           ptx::mbar_arrive(p_full);
           PROF_T(7)  // hand-off
@@ -555,11 +577,12 @@ static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int 
   launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM_BYTES, s, tm, tmo, nseq, pingpong);
 }
 
-// Variants of the softmax exp2 chain, DEPTHPRO_ATTN_EXP = 0..11:
+// Variants of the softmax exp2 chain, DEPTHPRO_ATTN_EXP = 0..13:
 //   0 scalar chain, every exponential on the MUFU, strict MUFU ping-pong between the two streams (the round's v5 kernel)
 //   1 packed fp32x2 chain;  2 / 3 / 4 packed chain with 25 / 37.5 / 50 % of the exponentials as a polynomial on the FMA pipe
 //   5 / 6 packed chain, the MUFU turn handed to the other stream after 12 / 8 of a block's 16 eight-key groups
 //   7 / 8 the same hand-over with the scalar chain;  9 / 10 packed chain, hand-over after 14 / 10;  11 = 2 + hand-over after 12
+//   12 / 13 = 5 / 11 with P handed to the P V MMA through TMEM instead of shared memory (EXPERIMENTAL: not yet run on a GPU)
 // Default 5.  DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams' exp phases overlap freely (slower).
 static int g_expv = -1, g_pingpong = 1;
 
@@ -570,7 +593,7 @@ void attention_tc_set_variant(int expv, int pingpong) {
     g_expv = -1;
     return;
   }
-  if (expv > 11) throw std::runtime_error("attention variant must be 0..11");
+  if (expv > 13) throw std::runtime_error("attention variant must be 0..13");
   g_expv = expv, g_pingpong = pingpong != 0;
 }
 
@@ -607,6 +630,8 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
     case 9: launch_attention<9>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 10: launch_attention<10>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 11: launch_attention<11>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 12: launch_attention<12>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 13: launch_attention<13>(tm, tmo, nseq, ctas, pingpong, s); break;
     default: throw std::runtime_error("attention variant not compiled in");
   }
   DP_LAUNCH_CHECK();

@@ -32,7 +32,8 @@ NAMES = {0: "scalar, all MUFU (default)", 1: "fp32x2 chain, all MUFU", 2: "fp32x
          4: "fp32x2, 50% poly", 5: "fp32x2 chain, MUFU turn handed over at 12/16", 6: "fp32x2 chain, handed over at 8/16",
          7: "scalar chain, handed over at 12/16", 8: "scalar chain, handed over at 8/16",
          9: "fp32x2 chain, handed over at 14/16", 10: "fp32x2 chain, handed over at 10/16",
-         11: "fp32x2, 25% poly, handed over at 12/16"}
+         11: "fp32x2, 25% poly, handed over at 12/16", 12: "variant 5 with P through TMEM (experimental)",
+         13: "variant 11 with P through TMEM (experimental)"}
 VARIANTS = [int(v) for v in os.environ.get("ATTN_VARIANTS", "0,1,2,3,4").split(",")]
 PPS = [int(v) for v in os.environ.get("ATTN_PINGPONG", "1,0").split(",")]
 
