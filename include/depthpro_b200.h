@@ -149,7 +149,7 @@ int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float*
 /* Attention core: qkv fp32 (n,577,3072) -> out fp32 (n,577,1024), 16 heads x 64.  `backend` low byte: 0 fp32
  * CUDA-core, 1 bf16 tcgen05, 2 bf16 mma.sync.  For backend 1, bits 8-11 = 1 + variant of the softmax exp2 chain
  * (0 scalar chain + strict MUFU ping-pong, 1 packed fp32x2 chain, 2 / 3 / 4 = 25 / 37.5 / 50 % of the exponentials
- * on the FMA pipe, 5-11 early hand-over of the MUFU turn, 12 / 13 experimental P-through-TMEM forms; 5 is the default), 0xF = back to the default, and
+ * on the FMA pipe, 5-11 early hand-over of the MUFU turn, 12-14 experimental P-through-TMEM forms (14 only through DEPTHPRO_ATTN_EXP / dp_kernel_bench); 5 is the default), 0xF = back to the default, and
  * bit 12 = no MUFU ping-pong; the choice is process-wide and sticky (same switch as DEPTHPRO_ATTN_EXP /
  * DEPTHPRO_ATTN_PINGPONG). */
 int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, int n,

@@ -146,7 +146,14 @@ __device__ __forceinline__ constexpr bool packed_chain() { return (EXPV >= 1 && 
 // generic->async proxy fence per block, half the shared-memory operand reads of P V).  NOT YET RUN ON A GPU: written in
 // the round's last, GPU-less hours; ptxas accepts the instruction forms, parity and timing are round-2 work.
 template <int EXPV>
-__device__ __forceinline__ constexpr bool p_in_tmem() { return EXPV == 12 || EXPV == 13; }
+__device__ __forceinline__ constexpr bool p_in_tmem() { return EXPV >= 12 && EXPV <= 14; }
+// Variant 14 (= 12 otherwise): with P in TMEM the high P tile is idle, so it becomes a SECOND Q BUFFER: the next query
+// tile's Q (and its first K block) are loaded while the current tile is still being worked on, and the MMA warp walks
+// the stream's blocks as one sequence -- Q K^T of block G, then P V of block G - 1, across tile boundaries -- so the
+// first S of a tile is computed under the previous tile's last softmax block instead of after it (phase profile:
+// 1340 cycles waiting for S at a tile's first block against 500-690 elsewhere).  EXPERIMENTAL like 12 / 13.
+template <int EXPV>
+__device__ __forceinline__ constexpr bool q_double() { return EXPV == 14; }
 template <int EXPV>
 __device__ __forceinline__ constexpr int arrive_at() {
   return (EXPV == 5 || EXPV == 7 || EXPV >= 11) ? 12 : (EXPV == 6 || EXPV == 8) ? 8 : EXPV == 9 ? 14 : EXPV == 10 ? 10 : 16;
@@ -179,6 +186,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint64_t* v_full = k_empty + RING;        // RING
   uint64_t* v_empty = v_full + RING;        // RING
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_all + 2 * NBAR);
+  uint64_t* q2_full = bars_all + 2 * NBAR + 1 + 2 * sidx;  // q_double: barriers of the second Q buffer (the high P tile)
+  uint64_t* q2_empty = q2_full + 1;
 
   const int n_units = nseq * NH;
   const int slot = blockIdx.x + sidx * gridDim.x, n_slots = 2 * gridDim.x;
@@ -192,6 +201,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     ptx::mbar_init(p_full, 128);
     ptx::mbar_init(pv_done, 1);
     ptx::mbar_init(o_empty, 128);
+    if constexpr (q_double<EXPV>()) ptx::mbar_init(q2_full, 1), ptx::mbar_init(q2_empty, 1);
     for (int i = 0; i < RING; ++i) {
       ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1);
       ptx::mbar_init(&v_full[i], 1), ptx::mbar_init(&v_empty[i], 1);
@@ -219,10 +229,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       for (int u = slot; u < n_units; u += n_slots) {
         const int h = u % NH, row0 = (u / NH) * SEQ;
         for (int qt = 0; qt < NQT; ++qt, ++T) {
-          ptx::mbar_wait(q_empty, (T & 1) ^ 1);
-          if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(q_full, TILE_BYTES);
-            ptx::tma_load_2d(sQ, &tmQKV, q_full, h * HD, row0 + qt * QT);
+          if constexpr (q_double<EXPV>()) {
+            uint64_t* qe = (T & 1) ? q2_empty : q_empty;
+            uint64_t* qf = (T & 1) ? q2_full : q_full;
+            ptx::mbar_wait(qe, ((T >> 1) & 1) ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(qf, TILE_BYTES);
+              ptx::tma_load_2d((T & 1) ? sP + TILE_BYTES : sQ, &tmQKV, qf, h * HD, row0 + qt * QT);
+            }
+          } else {
+            ptx::mbar_wait(q_empty, (T & 1) ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(q_full, TILE_BYTES);
+              ptx::tma_load_2d(sQ, &tmQKV, q_full, h * HD, row0 + qt * QT);
+            }
           }
           __syncwarp();
           for (int j = 0; j < NB; ++j) {
@@ -285,6 +305,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       };
       // (Issuing the last P V of tile T after the first Q K^T of tile T+1 was measured and changed nothing: the
       // single-buffered Q tile and the first K block of the next tile arrive too late for it to matter.)
+      if constexpr (q_double<EXPV>()) {
+        // one flat sequence of blocks: Q K^T (G), then P V (G - 1), across tile boundaries
+        const uint32_t q2_lo = desc_lo(ptx::smem_u32(sP + TILE_BYTES));
+        const int my_units = slot < n_units ? (n_units - slot + n_slots - 1) / n_slots : 0;
+        const int n_blocks = my_units * NQT * NB;
+        for (int G = 0; G < n_blocks; ++G) {
+          const int Tt = G / NB, j = G - Tt * NB, st = G % RING;
+          if (j == 0) ptx::mbar_wait((Tt & 1) ? q2_full : q_full, (Tt >> 1) & 1);
+          ptx::mbar_wait(&k_full[st], (G / RING) & 1);
+          ptx::mbar_wait(s_empty, (G & 1) ^ 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t ql = (Tt & 1) ? q2_lo : q_lo;
+#pragma unroll
+            for (int ks = 0; ks < HD / 16; ++ks)
+              ptx::umma_bf16(tS, desc(ql + ks * 2), desc(k_lo + st * (TILE_BYTES >> 4) + ks * 2),
+                             j == NB - 1 ? IDESC_QK_LAST : IDESC_QK, ks != 0);
+            ptx::umma_commit(s_full);
+            ptx::umma_commit(&k_empty[st]);
+            if (j == NB - 1) ptx::umma_commit((Tt & 1) ? q2_empty : q_empty);
+          }
+          __syncwarp();
+          if (G > 0) issue_pv((G - 1) / NB, (G - 1) % NB);
+        }
+        if (n_blocks > 0) issue_pv((n_blocks - 1) / NB, (n_blocks - 1) % NB);
+      } else {
       int T = 0;
       for (int u = slot; u < n_units; u += n_slots) {
         for (int qt = 0; qt < NQT; ++qt, ++T) {
@@ -315,6 +361,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           }
           issue_pv(T, NB - 1);
         }
+      }
       }
 #ifdef ATTN_PROFILE
       if (lane == 0)
@@ -570,19 +617,22 @@ void attn_prof_read(unsigned long long* host10, bool reset) {
 
 template <int EXPV>
 static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int nseq, int ctas, int pingpong, cudaStream_t s) {
+  constexpr uint32_t SMEM = SMEM_BYTES + (q_double<EXPV>() ? 64 : 0);  // + the second Q buffer's four mbarriers
+  static_assert(SMEM <= 232448, "more than 227 KB of shared memory");
   static std::atomic<unsigned long long> configured{0};
   if (first_use_on_device(configured)) {
-    DP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<EXPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    DP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<EXPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   }
-  launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM_BYTES, s, tm, tmo, nseq, pingpong);
+  launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM, s, tm, tmo, nseq, pingpong);
 }
 
-// Variants of the softmax exp2 chain, DEPTHPRO_ATTN_EXP = 0..13:
+// Variants of the softmax exp2 chain, DEPTHPRO_ATTN_EXP = 0..14:
 //   0 scalar chain, every exponential on the MUFU, strict MUFU ping-pong between the two streams (the round's v5 kernel)
 //   1 packed fp32x2 chain;  2 / 3 / 4 packed chain with 25 / 37.5 / 50 % of the exponentials as a polynomial on the FMA pipe
 //   5 / 6 packed chain, the MUFU turn handed to the other stream after 12 / 8 of a block's 16 eight-key groups
 //   7 / 8 the same hand-over with the scalar chain;  9 / 10 packed chain, hand-over after 14 / 10;  11 = 2 + hand-over after 12
 //   12 / 13 = 5 / 11 with P handed to the P V MMA through TMEM instead of shared memory (EXPERIMENTAL: not yet run on a GPU)
+//   14 = 12 + second Q buffer in the idle P tile + Q K^T of a tile's first block issued under the previous tile's last block
 // Default 5.  DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams' exp phases overlap freely (slower).
 static int g_expv = -1, g_pingpong = 1;
 
@@ -593,7 +643,7 @@ void attention_tc_set_variant(int expv, int pingpong) {
     g_expv = -1;
     return;
   }
-  if (expv > 13) throw std::runtime_error("attention variant must be 0..13");
+  if (expv > 14) throw std::runtime_error("attention variant must be 0..14");
   g_expv = expv, g_pingpong = pingpong != 0;
 }
 
@@ -632,6 +682,7 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
     case 11: launch_attention<11>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 12: launch_attention<12>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 13: launch_attention<13>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 14: launch_attention<14>(tm, tmo, nseq, ctas, pingpong, s); break;
     default: throw std::runtime_error("attention variant not compiled in");
   }
   DP_LAUNCH_CHECK();
