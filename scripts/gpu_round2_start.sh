@@ -9,7 +9,11 @@ run t_gpu 900 python -m pytest tests -q -m gpu -p no:cacheprovider
 ( timeout 300 python bench.py --workload clip1080p --no-cpu-baseline ) > gpurun_out/bench_clip1080p.json 2> gpurun_out/bench_clip1080p.err; echo "clip1080p exit $?" >> gpurun_out/summary.txt
 ( timeout 300 python bench.py --workload stream4k --no-cpu-baseline ) > gpurun_out/bench_stream4k.json 2> gpurun_out/bench_stream4k.err; echo "stream4k exit $?" >> gpurun_out/summary.txt
 ( timeout 300 python bench.py --batch 16 --steps 5 --warmup 3 --no-cpu-baseline ) > gpurun_out/bench_batch16.json 2> gpurun_out/bench_batch16.err; echo "batch16 exit $?" >> gpurun_out/summary.txt
-( ATTN_VARIANTS=5,11,12,13,14 ATTN_PINGPONG=1 timeout 300 python scripts/attn_variants.py ) > gpurun_out/attn_variants.json 2> gpurun_out/attn_variants.err; echo "attn_variants exit $?" >> gpurun_out/summary.txt
+# experimental variants one process each (a wrong barrier protocol traps after ~5 s and poisons the CUDA context)
+for v in 12 13 14; do
+  ( ATTN_VARIANTS=$v ATTN_PINGPONG=1 timeout 120 python scripts/attn_variants.py --no-model ) > gpurun_out/attn_variant_$v.json 2> gpurun_out/attn_variant_$v.err; echo "attn_variant_$v exit $?" >> gpurun_out/summary.txt
+done
+( ATTN_VARIANTS=5,11 ATTN_PINGPONG=1 timeout 300 python scripts/attn_variants.py ) > gpurun_out/attn_variants.json 2> gpurun_out/attn_variants.err; echo "attn_variants exit $?" >> gpurun_out/summary.txt
 ( timeout 300 python scripts/kernel_bench.py ) > gpurun_out/kernel_bench.log 2>&1; echo "kernel_bench exit $?" >> gpurun_out/summary.txt
-cat gpurun_out/summary.txt; tail -3 gpurun_out/t_gpu.log; tail -8 gpurun_out/attn_variants.err | cut -c1-200
+cat gpurun_out/summary.txt; tail -3 gpurun_out/t_gpu.log; tail -8 gpurun_out/attn_variants.err | cut -c1-200; tail -n 2 gpurun_out/attn_variant_1?.err | cut -c1-200
 bash scripts/gpu_ncu_final.sh
