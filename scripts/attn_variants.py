@@ -73,10 +73,10 @@ for pp in PPS:
         print(row, file=sys.stderr, flush=True)
 
 ok = [r for r in res["variants"] if r["relerr_n3"] < 1.5e-2 and (r["relerr_n37"] is None or r["relerr_n37"] < 1.5e-2)]
-best = min(ok, key=lambda r: r["us_37seq"])
+best = min(ok, key=lambda r: r["us_37seq"]) if ok else None
 res["best"] = best
 
-if "--no-model" not in sys.argv:
+if "--no-model" not in sys.argv and best is not None:
     model = depth_pro.DepthPro(device=dev, precision=torch.bfloat16).init_weights("stress", 1234)
     x = synthetic.synthetic_image_1536(1).to(dev)
     gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs.npz"))
