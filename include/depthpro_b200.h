@@ -162,7 +162,9 @@ int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, i
  * every launch: 6 uint8 HWC -> fused transform + resize -> fp32 3x1536^2, 7 pyramid + 35-patch split +
  * im2col of one 1536^2 frame, 8 depth epilogue 1536^2 -> M x N, 9 unprojection + colours, 10 colourise.
  * Kinds 11 / 12 / 13: kinds 0 / 1 / 2 in their LayerNorm-folded forms.  A/B bits (process-wide, sticky):
- * kind | 0x100 / 0x200 switches the fp32-residual forms' L2 prefetch on / off (DEPTHPRO_RES_PREFETCH); for kind 4,
+ * kind | 0x100 / 0x200 switches the fp32-residual forms' L2 prefetch on / off (DEPTHPRO_RES_PREFETCH), kind | 0x400 /
+ * 0x800 their persisting-L2 window on (set-aside = `iters >> 16` MB, 0 = 96; `iters` is taken modulo 65536) / off
+ * (DEPTHPRO_L2_PERSIST_MB); for kind 4,
  * N = 1 + exp2 variant + 16 * (no ping-pong) selects the attention variant (0 leaves it unchanged). */
 int dp_kernel_bench(dp_engine* e, int kind, int M, int N, int K, int iters, float* ms_out);
 
