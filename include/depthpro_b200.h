@@ -164,7 +164,8 @@ int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, i
  * Kinds 11 / 12 / 13: kinds 0 / 1 / 2 in their LayerNorm-folded forms.  A/B bits (process-wide, sticky):
  * kind | 0x100 / 0x200 switches the fp32-residual forms' L2 prefetch on / off (DEPTHPRO_RES_PREFETCH), kind | 0x400 /
  * 0x800 their persisting-L2 window on (set-aside = `iters >> 16` MB, 0 = 96; `iters` is taken modulo 65536) / off
- * (DEPTHPRO_L2_PERSIST_MB); for kind 4,
+ * (DEPTHPRO_L2_PERSIST_MB), kind | 0x1000 / 0x2000 the opt-in second-generation HBM kernels on / off
+ * (DEPTHPRO_HBM_V2); for kind 4,
  * N = 1 + exp2 variant + 16 * (no ping-pong) selects the attention variant (0 leaves it unchanged). */
 int dp_kernel_bench(dp_engine* e, int kind, int M, int N, int K, int iters, float* ms_out);
 

@@ -1058,6 +1058,8 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   // 0x400: L2 persistence of the fp32 residual stream on, set-aside = `iters >> 16` MB (0 -> 96); 0x800: off
   if (kind & 0x400) gemm_tc_set_l2_persist((iters >> 16) ? (iters >> 16) : 96);
   if (kind & 0x800) gemm_tc_set_l2_persist(0);
+  if (kind & 0x1000) hbm_v2_set(1);  // 0x1000 / 0x2000: opt-in second-generation HBM kernels on / off
+  if (kind & 0x2000) hbm_v2_set(0);
   iters &= 0xFFFF;
   kind &= 0xFF;
   cudaStream_t s = nullptr;

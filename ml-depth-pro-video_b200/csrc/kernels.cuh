@@ -80,6 +80,7 @@ void ln_apply_from_stats(const bf16* xb, const float* stats, float* y, long long
 void compute_fpx(const float* fov_deg, const float* f_px_in, int W, float* f_px, int B, cudaStream_t s);
 // depth[b,y,x] = 1 / clamp(resize(canon * (W / f_px[b]))[y,x], 1e-4, 1e4)    (depth_pro.py:285-293)
 void depth_epilogue(const float* canon, const float* f_px, int B, int H, int W, float* depth, cudaStream_t s);
+void hbm_v2_set(int on);  // A/B switch of the opt-in second-generation HBM kernels (DEPTHPRO_HBM_V2)
 
 // ---- video add-on ---------------------------------------------------------------------------
 void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float* f_px, float* xyz,
