@@ -137,7 +137,8 @@ def test_environment_switches_are_documented():
     documented = set(re.findall(r"DEPTHPRO_[A-Z0-9_]+", doc))
     pkg = os.path.join(ROOT, "ml-depth-pro-video_b200")
     files = (glob.glob(os.path.join(pkg, "csrc", "*.cu")) + glob.glob(os.path.join(pkg, "csrc", "*.cuh"))
-             + glob.glob(os.path.join(pkg, "depth_pro", "*.py")) + [os.path.join(ROOT, "bench.py")])
+             + glob.glob(os.path.join(pkg, "depth_pro", "*.py")) + [os.path.join(ROOT, "bench.py")]
+             + glob.glob(os.path.join(ROOT, "tests", "test_gpu_*.py")))
     src = "".join(open(f).read() for f in files)
     used = set(re.findall(r'getenv\("(DEPTHPRO_[A-Z0-9_]+)"\)', src))
     used |= set(re.findall(r'environ(?:\.get)?[\(\[]"(DEPTHPRO_[A-Z0-9_]+)"', src))
