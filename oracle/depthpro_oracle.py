@@ -14,7 +14,7 @@ reference lines it follows.  Unlike the reference it travels to the GPU box
 Pinning: the reference ships no tests, golden vectors or KATs for this path (SURVEY.md §4,
 §8c) — *parity is unpinned by the reference's own tests*.  This restatement is pinned
 instead against the reference ITSELF, executed in the build container through
-``oracle/reference_loader.py`` (``tests/test_oracle_vs_reference.py``), and against the
+``oracle/reference_loader.py`` (``tests/test_oracle.py::test_oracle_vs_live_reference``), and against the
 fixtures that run produced (``tests/golden/*.npz``, made by ``oracle/make_golden.py``).
 """
 
