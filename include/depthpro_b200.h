@@ -147,11 +147,11 @@ int dp_conv3x3_test(dp_engine* e, int backend, const float* x_nhwc, const float*
                     const float* bias, float* y_nhwc, int B, int H, int W, int Cin, int Cout,
                     void* stream);
 /* Attention core: qkv fp32 (n,577,3072) -> out fp32 (n,577,1024), 16 heads x 64.  `backend` low byte: 0 fp32
- * CUDA-core, 1 bf16 tcgen05, 2 bf16 mma.sync.  For backend 1, bits 8-11 = 1 + variant of the softmax exp2 chain
- * (0 scalar chain + strict MUFU ping-pong, 1 packed fp32x2 chain, 2 / 3 / 4 = 25 / 37.5 / 50 % of the exponentials
- * on the FMA pipe, 5-11 early hand-over of the MUFU turn, 12-14 experimental P-through-TMEM forms (14 only through DEPTHPRO_ATTN_EXP / dp_kernel_bench); 5 is the default), 0xF = back to the default, and
- * bit 12 = no MUFU ping-pong; the choice is process-wide and sticky (same switch as DEPTHPRO_ATTN_EXP /
- * DEPTHPRO_ATTN_PINGPONG). */
+ * CUDA-core, 1 bf16 tcgen05, 2 bf16 mma.sync.  For backend 1, bits 8-15 = 1 + kernel variant (0 scalar exp2 chain +
+ * strict MUFU ping-pong, 5 packed fp32x2 chain + early hand-over of the MUFU turn, 12 = 5 with P through TMEM, 13 = 12 with
+ * 25 % of the exponentials on the FMA pipe, 15-18 = 12 / 13 with the P V MMA split in two 64-key halves; the default is
+ * the fastest measured one, csrc/attention_tc.cu), 0xFF = back to the default, and bit 16 = no MUFU ping-pong; the choice
+ * is process-wide and sticky (same switch as DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG). */
 int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, int n,
                       void* stream);
 
@@ -166,7 +166,7 @@ int dp_attention_test(dp_engine* e, int backend, const float* qkv, float* out, i
  * 0x800 their persisting-L2 window on (set-aside = `iters >> 16` MB, 0 = 96; `iters` is taken modulo 65536) / off
  * (DEPTHPRO_L2_PERSIST_MB), kind | 0x1000 / 0x2000 the opt-in second-generation HBM kernels on / off
  * (DEPTHPRO_HBM_V2); for kind 4,
- * N = 1 + exp2 variant + 16 * (no ping-pong) selects the attention variant (0 leaves it unchanged). */
+ * N = 1 + variant + 64 * (no ping-pong) selects the attention variant (0 leaves it unchanged). */
 int dp_kernel_bench(dp_engine* e, int kind, int M, int N, int K, int iters, float* ms_out);
 
 /* Per-launch CUDA-event profiling of the hot kernels (used by bench.py for the roofline line).
@@ -177,6 +177,11 @@ int dp_kernel_bench(dp_engine* e, int kind, int M, int N, int K, int iters, floa
 int dp_profile_enable(dp_engine* e, int on);
 int dp_profile_collect(dp_engine* e, double* ms_by_class, double* work_by_class,
                        int64_t* launches_by_class);
+
+/* Debug counters of the kernels (tests only; synchronises the device).  id 0: softmax warps of the tcgen05 attention
+ * kernel that took the lazy-maximum RESCALE branch since the last reset (timm SDPA semantics are unchanged by it; the
+ * counter proves a test input really exercised it).  Returns the value and resets it when `reset` != 0; -1 on error. */
+int64_t dp_debug_counter(dp_engine* e, int id, int reset);
 
 /* Kernel launches issued by this engine since creation (bench.py's `gpu_launches`). */
 int64_t dp_launch_count(dp_engine* e);

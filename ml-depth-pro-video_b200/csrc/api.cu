@@ -2,6 +2,7 @@
 #include <string>
 
 #include "../../include/depthpro_b200.h"
+#include "attention.cuh"
 #include "engine.cuh"
 
 namespace {
@@ -118,6 +119,15 @@ int dp_profile_collect(dp_engine* e, double* ms_by_class, double* work_by_class,
     dp::prof_collect(ms_by_class, work_by_class, l);
     for (int i = 0; i < dp::KC_COUNT; ++i) launches_by_class[i] = l[i];
   });
+}
+int64_t dp_debug_counter(dp_engine* e, int id, int reset) {
+  int64_t v = -1;
+  guard([&] {
+    E(e);
+    if (id != 0) throw dp::Error("dp_debug_counter: unknown id");
+    v = static_cast<int64_t>(dp::attention_tc_rescale_count(reset != 0));
+  });
+  return v;
 }
 int64_t dp_launch_count(dp_engine* e) {
   (void)e;

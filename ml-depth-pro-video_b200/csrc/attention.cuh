@@ -8,6 +8,8 @@ void attention_f32(const float* qkv, float* out, int nseq, cudaStream_t s);
 void attention_bf16(const bf16* qkv, bf16* out, int nseq, cudaStream_t s);      // mma.sync (legacy tensor path)
 void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s);   // tcgen05 + TMEM + TMA
 // Experiment switch of the tcgen05 kernel (process-wide; overrides DEPTHPRO_ATTN_EXP / DEPTHPRO_ATTN_PINGPONG):
-// expv 0..8 = form of the softmax exp2 chain (see attention_tc.cu), -1 = back to the default; pingpong 0/1.
+// expv = kernel variant (list in attention_tc.cu), -1 = back to the default; pingpong 0/1.
 void attention_tc_set_variant(int expv, int pingpong);
+// Debug counter: softmax warps that took the lazy-maximum rescale branch since the last reset (synchronises the device).
+unsigned long long attention_tc_rescale_count(bool reset);
 }  // namespace dp

@@ -58,7 +58,7 @@ constexpr int RING = 2;                         // K ring depth = V ring depth
 constexpr int THREADS = 384;
 constexpr uint32_t TILE_BYTES = 128 * 128;      // 128 rows x 64 bf16 = 16 KB
 constexpr int STREAM_TILES = 1 + 2 * RING + 2;  // Q, K ring, V ring, P (two 64-key halves)
-constexpr uint32_t SMEM_BYTES = 2 * STREAM_TILES * TILE_BYTES + 1024 + 256;
+constexpr uint32_t SMEM_BYTES = 2 * STREAM_TILES * TILE_BYTES + 1024 + 512;
 constexpr int NBAR = 7 + 4 * RING;              // mbarriers per stream
 
 // idesc: D=f32, A=B=bf16, A K-major; B K-major (QK^T) or MN-major (PV: bit 16)
@@ -129,35 +129,29 @@ __device__ __forceinline__ void exp2_poly2(F2 x, float& p0, float& p1) {
   p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
   p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
-// which (8-key group, pair) slots go to the FMA pipe: 0 / 0 / 25 % / 37.5 % / 50 % of the exponentials
+// ---- kernel variants (template parameter EXPV, selected by DEPTHPRO_ATTN_EXP) -------------------
+//    0  scalar chain, every exponential on the MUFU, strict MUFU ping-pong, P through shared memory (round-1 v5 kernel)
+//    5  packed fp32x2 chain, MUFU turn handed to the other stream after 12 of a block's 16 eight-key groups (round-1 default)
+//   12  = 5 with P handed to the P V MMA through TMEM (tcgen05.st + A-from-TMEM MMA) instead of shared memory
+//   13  = 12 with 25 % of the exponentials as a degree-3 polynomial on the FMA pipe
+// Measured and deleted from the library in round 2 (profiles/r1_v6_attention_*, profiles/r2_attention_variants.json):
+// 1-4 (polynomial shares without hand-over), 6-11 (other hand-over points), 14 (second Q buffer + cross-tile Q K^T
+// issue: 87.1 us against 84.4 for variant 12) and 15-18 (P V split in two 64-key halves with their own p_full /
+// pv_done barriers, so that P V of keys 0..63 runs under the exponentials of keys 64..127: 94.7-96.4 us against 80.6
+// for variant 13 -- the extra barrier waits inside the unrolled exp loop cost more than the P V latency they hide).
 template <int EXPV>
 __device__ __forceinline__ constexpr bool poly_pair(int g8, int w) {
-  return (EXPV == 2 || EXPV == 11 || EXPV == 13) ? w == 3 : EXPV == 3 ? (w == 3 || (w == 1 && (g8 & 1))) : EXPV == 4 ? (w & 1) != 0 : false;
+  return EXPV == 13 && w == 3;
 }
+template <int EXPV>
+__device__ __forceinline__ constexpr bool packed_chain() { return EXPV != 0; }
+template <int EXPV>
+__device__ __forceinline__ constexpr bool p_in_tmem() { return EXPV >= 12; }
+template <int EXPV>
+__device__ __forceinline__ constexpr int arrive_at() { return EXPV == 0 ? 16 : 12; }
 
-// Variants 5-8 keep every exponential on the MUFU but hand the MUFU turn to the other stream EARLY, after 12 or 8
-// of the block's 16 eight-key groups, so the peer's first exponentials overlap this stream's last ones
-// (5 / 6: packed chain, 7 / 8: scalar chain; 9 / 10: packed chain, hand-over after 14 / 10 groups; 11: variant 2's
-// 25 % polynomial share with the hand-over after 12).
-template <int EXPV>
-__device__ __forceinline__ constexpr bool packed_chain() { return (EXPV >= 1 && EXPV <= 6) || EXPV >= 9; }
-// Variants 12 / 13 (= 5 / 11 otherwise) keep P out of shared memory: the softmax threads write the packed bf16 pairs
-// to 64 TMEM columns of their stream with tcgen05.st and the P V MMA takes its A operand from there (no 16 STS.128 +
-// generic->async proxy fence per block, half the shared-memory operand reads of P V).  NOT YET RUN ON A GPU: written in
-// the round's last, GPU-less hours; ptxas accepts the instruction forms, parity and timing are round-2 work.
-template <int EXPV>
-__device__ __forceinline__ constexpr bool p_in_tmem() { return EXPV >= 12 && EXPV <= 14; }
-// Variant 14 (= 12 otherwise): with P in TMEM the high P tile is idle, so it becomes a SECOND Q BUFFER: the next query
-// tile's Q (and its first K block) are loaded while the current tile is still being worked on, and the MMA warp walks
-// the stream's blocks as one sequence -- Q K^T of block G, then P V of block G - 1, across tile boundaries -- so the
-// first S of a tile is computed under the previous tile's last softmax block instead of after it (phase profile:
-// 1340 cycles waiting for S at a tile's first block against 500-690 elsewhere).  EXPERIMENTAL like 12 / 13.
-template <int EXPV>
-__device__ __forceinline__ constexpr bool q_double() { return EXPV == 14; }
-template <int EXPV>
-__device__ __forceinline__ constexpr int arrive_at() {
-  return (EXPV == 5 || EXPV == 7 || EXPV >= 11) ? 12 : (EXPV == 6 || EXPV == 8) ? 8 : EXPV == 9 ? 14 : EXPV == 10 ? 10 : 16;
-}
+// Debug counter (dp_debug_counter): how many times a softmax warp took the lazy-maximum RESCALE branch.
+__device__ unsigned long long g_attn_rescales;
 
 template <int EXPV>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -186,8 +180,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint64_t* v_full = k_empty + RING;        // RING
   uint64_t* v_empty = v_full + RING;        // RING
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_all + 2 * NBAR);
-  uint64_t* q2_full = bars_all + 2 * NBAR + 1 + 2 * sidx;  // q_double: barriers of the second Q buffer (the high P tile)
-  uint64_t* q2_empty = q2_full + 1;
 
   const int n_units = nseq * NH;
   const int slot = blockIdx.x + sidx * gridDim.x, n_slots = 2 * gridDim.x;
@@ -201,7 +193,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     ptx::mbar_init(p_full, 128);
     ptx::mbar_init(pv_done, 1);
     ptx::mbar_init(o_empty, 128);
-    if constexpr (q_double<EXPV>()) ptx::mbar_init(q2_full, 1), ptx::mbar_init(q2_empty, 1);
     for (int i = 0; i < RING; ++i) {
       ptx::mbar_init(&k_full[i], 1), ptx::mbar_init(&k_empty[i], 1);
       ptx::mbar_init(&v_full[i], 1), ptx::mbar_init(&v_empty[i], 1);
@@ -229,20 +220,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       for (int u = slot; u < n_units; u += n_slots) {
         const int h = u % NH, row0 = (u / NH) * SEQ;
         for (int qt = 0; qt < NQT; ++qt, ++T) {
-          if constexpr (q_double<EXPV>()) {
-            uint64_t* qe = (T & 1) ? q2_empty : q_empty;
-            uint64_t* qf = (T & 1) ? q2_full : q_full;
-            ptx::mbar_wait(qe, ((T >> 1) & 1) ^ 1);
-            if (ptx::elect_one()) {
-              ptx::mbar_expect_tx(qf, TILE_BYTES);
-              ptx::tma_load_2d((T & 1) ? sP + TILE_BYTES : sQ, &tmQKV, qf, h * HD, row0 + qt * QT);
-            }
-          } else {
-            ptx::mbar_wait(q_empty, (T & 1) ^ 1);
-            if (ptx::elect_one()) {
-              ptx::mbar_expect_tx(q_full, TILE_BYTES);
-              ptx::tma_load_2d(sQ, &tmQKV, q_full, h * HD, row0 + qt * QT);
-            }
+          ptx::mbar_wait(q_empty, (T & 1) ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(q_full, TILE_BYTES);
+            ptx::tma_load_2d(sQ, &tmQKV, q_full, h * HD, row0 + qt * QT);
           }
           __syncwarp();
           for (int j = 0; j < NB; ++j) {
@@ -283,11 +264,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             ptx::mbar_wait(&v_full[st], (G / RING) & 1);
             if (jj == 0) ptx::mbar_wait(o_empty, (Tt & 1) ^ 1);  // the previous tile's O has been read out
             MPROF(4)
+            const int nks = jj == NB - 1 ? LAST_N / 16 : KB / 16;
             ptx::mbar_wait(p_full, G & 1);
             MPROF(5)
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-              const int nks = jj == NB - 1 ? LAST_N / 16 : KB / 16;
 #pragma unroll
               for (int ks = 0; ks < KB / 16; ++ks) {
                 if (ks >= nks) break;
@@ -305,32 +286,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       };
       // (Issuing the last P V of tile T after the first Q K^T of tile T+1 was measured and changed nothing: the
       // single-buffered Q tile and the first K block of the next tile arrive too late for it to matter.)
-      if constexpr (q_double<EXPV>()) {
-        // one flat sequence of blocks: Q K^T (G), then P V (G - 1), across tile boundaries
-        const uint32_t q2_lo = desc_lo(ptx::smem_u32(sP + TILE_BYTES));
-        const int my_units = slot < n_units ? (n_units - slot + n_slots - 1) / n_slots : 0;
-        const int n_blocks = my_units * NQT * NB;
-        for (int G = 0; G < n_blocks; ++G) {
-          const int Tt = G / NB, j = G - Tt * NB, st = G % RING;
-          if (j == 0) ptx::mbar_wait((Tt & 1) ? q2_full : q_full, (Tt >> 1) & 1);
-          ptx::mbar_wait(&k_full[st], (G / RING) & 1);
-          ptx::mbar_wait(s_empty, (G & 1) ^ 1);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint32_t ql = (Tt & 1) ? q2_lo : q_lo;
-#pragma unroll
-            for (int ks = 0; ks < HD / 16; ++ks)
-              ptx::umma_bf16(tS, desc(ql + ks * 2), desc(k_lo + st * (TILE_BYTES >> 4) + ks * 2),
-                             j == NB - 1 ? IDESC_QK_LAST : IDESC_QK, ks != 0);
-            ptx::umma_commit(s_full);
-            ptx::umma_commit(&k_empty[st]);
-            if (j == NB - 1) ptx::umma_commit((Tt & 1) ? q2_empty : q_empty);
-          }
-          __syncwarp();
-          if (G > 0) issue_pv((G - 1) / NB, (G - 1) % NB);
-        }
-        if (n_blocks > 0) issue_pv((n_blocks - 1) / NB, (n_blocks - 1) % NB);
-      } else {
+      {
       int T = 0;
       for (int u = slot; u < n_units; u += n_slots) {
         for (int qt = 0; qt < NQT; ++qt, ++T) {
@@ -429,6 +385,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           if (j == 0) {
             m_ref = mx;
           } else if (__any_sync(0xffffffffu, (mx - m_ref) * c > RESCALE_LOG2)) {
+            if (lane == 0) atomicAdd(&g_attn_rescales, 1ull);
             const float m_new = fmaxf(m_ref, mx);
             const float alpha = ex2((m_ref - m_new) * c);
             m_ref = m_new;
@@ -615,9 +572,20 @@ void attn_prof_read(unsigned long long* host10, bool reset) {
 }
 #endif
 
+unsigned long long attention_tc_rescale_count(bool reset) {
+  unsigned long long v = 0;
+  DP_CUDA(cudaDeviceSynchronize());
+  DP_CUDA(cudaMemcpyFromSymbol(&v, g_attn_rescales, sizeof(v)));
+  if (reset) {
+    const unsigned long long z = 0;
+    DP_CUDA(cudaMemcpyToSymbol(g_attn_rescales, &z, sizeof(z)));
+  }
+  return v;
+}
+
 template <int EXPV>
 static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int nseq, int ctas, int pingpong, cudaStream_t s) {
-  constexpr uint32_t SMEM = SMEM_BYTES + (q_double<EXPV>() ? 64 : 0);  // + the second Q buffer's four mbarriers
+  constexpr uint32_t SMEM = SMEM_BYTES;
   static_assert(SMEM <= 232448, "more than 227 KB of shared memory");
   static std::atomic<unsigned long long> configured{0};
   if (first_use_on_device(configured)) {
@@ -626,24 +594,19 @@ static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int 
   launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM, s, tm, tmo, nseq, pingpong);
 }
 
-// Variants of the softmax exp2 chain, DEPTHPRO_ATTN_EXP = 0..14:
-//   0 scalar chain, every exponential on the MUFU, strict MUFU ping-pong between the two streams (the round's v5 kernel)
-//   1 packed fp32x2 chain;  2 / 3 / 4 packed chain with 25 / 37.5 / 50 % of the exponentials as a polynomial on the FMA pipe
-//   5 / 6 packed chain, the MUFU turn handed to the other stream after 12 / 8 of a block's 16 eight-key groups
-//   7 / 8 the same hand-over with the scalar chain;  9 / 10 packed chain, hand-over after 14 / 10;  11 = 2 + hand-over after 12
-//   12 / 13 = 5 / 11 with P handed to the P V MMA through TMEM instead of shared memory (EXPERIMENTAL: not yet run on a GPU)
-//   14 = 12 + second Q buffer in the idle P tile + Q K^T of a tile's first block issued under the previous tile's last block
-// Default 5.  DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams' exp phases overlap freely (slower).
+// DEPTHPRO_ATTN_EXP selects a variant (list at the top of this file); DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams'
+// exp phases overlap freely (slower).
 static int g_expv = -1, g_pingpong = 1;
 
-constexpr int ATTN_EXP_DEFAULT = 5;  // measured on B200 (profiles/r1_v6_attention_*): 92.9 -> 89.2 us per layer, +1.8 % frames/s
+constexpr int ATTN_EXP_DEFAULT = 13;  // measured on B200 (profiles/r2_attention_variants.json)
+static bool variant_compiled(int v) { return v == 0 || v == 5 || v == 12 || v == 13; }
 
 void attention_tc_set_variant(int expv, int pingpong) {
   if (expv < 0) {  // back to the environment's / built-in default on the next launch
     g_expv = -1;
     return;
   }
-  if (expv > 14) throw std::runtime_error("attention variant must be 0..14");
+  if (!variant_compiled(expv)) throw std::runtime_error("attention variant not compiled in (0, 5, 12, 13)");
   g_expv = expv, g_pingpong = pingpong != 0;
 }
 
@@ -669,20 +632,9 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
   if (ctas > sms) ctas = sms;
   switch (expv) {
     case 0: launch_attention<0>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 1: launch_attention<1>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 2: launch_attention<2>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 3: launch_attention<3>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 4: launch_attention<4>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 5: launch_attention<5>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 6: launch_attention<6>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 7: launch_attention<7>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 8: launch_attention<8>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 9: launch_attention<9>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 10: launch_attention<10>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 11: launch_attention<11>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 12: launch_attention<12>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 13: launch_attention<13>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 14: launch_attention<14>(tm, tmo, nseq, ctas, pingpong, s); break;
     default: throw std::runtime_error("attention variant not compiled in");
   }
   DP_LAUNCH_CHECK();

@@ -1024,9 +1024,9 @@ void Engine::attention_test(int backend, const float* qkv, float* out, int n, cu
     bf16* q = to_dev<bf16>(qkv, nq, s);
     bf16* o = nullptr;
     DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&o), no * 2, s));
-    // backend bits 8-11: tcgen05 kernel variant + 1 (0xF = back to the default), bit 12: no MUFU ping-pong
-    if (((backend >> 8) & 0xF) == 0xF) attention_tc_set_variant(-1, 1);  // 0xF: back to the default variant
-    else if ((backend >> 8) & 0xF) attention_tc_set_variant(((backend >> 8) & 0xF) - 1, !((backend >> 12) & 1));
+    // backend bits 8-15: tcgen05 kernel variant + 1 (0xFF = back to the default), bit 16: no MUFU ping-pong
+    if (((backend >> 8) & 0xFF) == 0xFF) attention_tc_set_variant(-1, 1);
+    else if ((backend >> 8) & 0xFF) attention_tc_set_variant(((backend >> 8) & 0xFF) - 1, !((backend >> 16) & 1));
     if ((backend & 0xFF) == 2) attention_bf16(q, o, n, s);
     else attention_bf16_tc(q, o, n, s);
     convert<bf16, float>(o, out, (long long)no, s);
@@ -1107,7 +1107,7 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   } else if (kind == 4) {
     bf16* q = (bf16*)B((size_t)M * SEQ * 3 * EMB * 2);
     bf16* o = (bf16*)B((size_t)M * SEQ * EMB * 2);
-    if (N > 0) attention_tc_set_variant((N - 1) & 15, !(((N - 1) >> 4) & 1));  // N = 1 + variant + 16 * no-ping-pong
+    if (N > 0) attention_tc_set_variant((N - 1) & 63, !(((N - 1) >> 6) & 1));  // N = 1 + variant + 64 * no-ping-pong
     run = [&, q, o] { attention_bf16_tc(q, o, M, s); };
   } else if (kind == 5) {
     float* x = (float*)B((size_t)M * EMB * 4);

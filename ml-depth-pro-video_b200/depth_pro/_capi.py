@@ -44,6 +44,7 @@ SIGNATURES = {
     "dp_kernel_bench": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float)]),
     "dp_profile_enable": (_i, [_vp, _i]),
     "dp_profile_collect": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "dp_debug_counter": (_i64, [_vp, _i, _i]),
     "dp_launch_count": (_i64, [_vp]),
 }
 

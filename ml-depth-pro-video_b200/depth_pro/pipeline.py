@@ -81,7 +81,11 @@ class Progress:
         self.done: Dict[str, Dict[str, Any]] = {}
         self._unsaved = 0
         if resume and not force_reprocess:
-            for p in {self.path, self.shard_path}:
+            # EVERY rank reads the merged file and ALL rank shards: after an interrupted multi-rank run the merged file
+            # may be missing or stale, and a rank that only knew its own shard would disagree with the others about
+            # what is left (frames skipped or processed twice).
+            self.done.update(self._read(self.path))
+            for p in sorted(glob.glob(os.path.join(output_dir, "processing_progress.rank*.json"))):
                 self.done.update(self._read(p))
 
     @staticmethod
@@ -237,7 +241,10 @@ def process_frames(frames_dir: str, output_dir: Optional[str], model, consumer: 
     summary.skipped = len(paths) - len(todo)
     if summary.skipped:
         log(f"Skipping {summary.skipped} already processed frames")
-    mine = [(i, todo[i]) for i in video.shard_frames(len(todo), rank, world)]
+    # shard on CLIP POSITIONS (i % world over the unfiltered, sorted list), then drop what is done: which rank owns a
+    # frame, and FrameOutput.index, never depend on how far an earlier run got
+    todo_set = set(todo)
+    mine = [(i, paths[i]) for i in video.shard_frames(len(paths), rank, world) if paths[i] in todo_set]
     for frame in FrameLoader(mine, downscale_factor, decode_threads, load_fn=load_fn):
         ok = False
         try:

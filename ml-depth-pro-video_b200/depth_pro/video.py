@@ -153,58 +153,96 @@ class FrameResult:
     index: int
     depth: np.ndarray            # (H,W) float32, pinned host memory view (valid until the slot is reused)
     focallength_px: float
+    points: Optional[np.ndarray] = None   # (N,3) float32 view of the unprojected cloud (DepthStream(unproject=True))
 
 
 class DepthStream:
-    """Streams uint8 HWC frames through ``model.infer`` with pinned, double-buffered host staging."""
+    """Streams uint8 HWC frames through ``model.infer`` (optionally + ``depth_to_3d``) as a three-stage pipeline.
 
-    def __init__(self, model: DepthPro, height: int, width: int, batch: int = 1, slots: int = 2):
+    Stage 1 copies batch k+1 from a pinned host slot to the GPU on a copy stream, stage 2 runs the network on the
+    caller's current stream, stage 3 copies the results of batch k-1 back into pinned host slots on a second copy
+    stream; CUDA events chain the stages, the host only blocks when it needs a slot back.  (Copies issued on the
+    COMPUTE stream, as in round 1, serialise with the kernels: 100 MB of 4K points per frame cost 7 % of the stream's
+    frames/s.)  Device tensors of a batch are kept alive until its last copy has completed, so the caching allocator
+    never hands their memory to another stream early.
+    """
+
+    def __init__(self, model: DepthPro, height: int, width: int, batch: int = 1, slots: int = 3,
+                 unproject: bool = False):
+        if unproject and batch != 1:
+            raise ValueError("DepthStream(unproject=True) processes one frame per batch")
+        if slots < 2:
+            raise ValueError("DepthStream needs at least 2 slots")
         self.model, self.H, self.W, self.B = model, height, width, batch
         self.dev = model._device
+        self.unproject = unproject
         self._in = [torch.empty((batch, height, width, 3), dtype=torch.uint8).pin_memory() for _ in range(slots)]
         self._out = [torch.empty((batch, height, width), dtype=torch.float32).pin_memory() for _ in range(slots)]
         self._f = [torch.empty((batch,), dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self._xyz = [torch.empty((height * width, 3), dtype=torch.float32).pin_memory() for _ in range(slots)] if unproject else None
+        self._n = [torch.zeros(1, dtype=torch.int64).pin_memory() for _ in range(slots)] if unproject else None
+        self._ev_in = [torch.cuda.Event() for _ in range(slots)]
+        self._ev_c = [torch.cuda.Event() for _ in range(slots)]
         self._done = [torch.cuda.Event() for _ in range(slots)]
+        self._h2d = torch.cuda.Stream(self.dev)
+        self._d2h = torch.cuda.Stream(self.dev)
         self._slots = slots
+        self.h2d_bytes_per_frame = height * width * 3
+        self.d2h_bytes_per_frame = height * width * 4 + 4 + (height * width * 12 + 8 if unproject else 0)
 
     def run(self, frames: Iterable[Tuple[int, np.ndarray]], f_px: Optional[float] = None) -> Iterator[FrameResult]:
-        """``frames`` yields (index, uint8 HWC array).  Results are yielded in input order, one batch
-        behind the GPU, so the D2H copy of batch k overlaps the compute of batch k+1."""
-        pending: List[Tuple[int, List[int]]] = []
+        """``frames`` yields (index, uint8 HWC array).  Results are yielded in input order, up to ``slots - 1``
+        batches behind the GPU."""
+        pending: List[Tuple[int, List[int], tuple]] = []
         slot = 0
         batch_idx: List[int] = []
-        stream = torch.cuda.current_stream(self.dev)
+        compute = torch.cuda.current_stream(self.dev)
 
         def flush(n_valid: int):
             nonlocal slot
-            x = self._in[slot][:n_valid].to(self.dev, non_blocking=True)
+            s = slot
+            with torch.cuda.stream(self._h2d):
+                x = self._in[s][:n_valid].to(self.dev, non_blocking=True)
+                self._ev_in[s].record(self._h2d)
+            compute.wait_event(self._ev_in[s])
             pred = self.model.infer(x, f_px=f_px)
-            self._out[slot][:n_valid].copy_(pred["depth"].reshape(n_valid, self.H, self.W), non_blocking=True)
-            fp = pred["focallength_px"]
-            if f_px is None:
-                self._f[slot][:n_valid].copy_(fp.reshape(n_valid), non_blocking=True)
-            else:
-                self._f[slot][:n_valid].fill_(float(f_px))
-            self._done[slot].record(stream)
-            pending.append((slot, list(batch_idx)))
+            depth = pred["depth"].reshape(n_valid, self.H, self.W)
+            xyz = n = None
+            if self.unproject:
+                xyz, n, _ = depth_to_3d(self.model, depth[0], pred["focallength_px"], self.W, self.H, rgb=None, sync=False)
+            self._ev_c[s].record(compute)
+            self._d2h.wait_event(self._ev_c[s])
+            with torch.cuda.stream(self._d2h):
+                self._out[s][:n_valid].copy_(depth, non_blocking=True)
+                if f_px is None:
+                    self._f[s][:n_valid].copy_(pred["focallength_px"].reshape(n_valid), non_blocking=True)
+                if self.unproject:
+                    self._xyz[s].copy_(xyz, non_blocking=True)
+                    self._n[s].copy_(n, non_blocking=True)
+                self._done[s].record(self._d2h)
+            if f_px is not None:
+                self._f[s][:n_valid].fill_(float(f_px))
+            pending.append((s, list(batch_idx), (x, pred, xyz, n)))   # keeps the device tensors alive until `done`
             slot = (slot + 1) % self._slots
 
         def drain(keep: int):
             while len(pending) > keep:
-                s, idxs = pending.pop(0)
+                s, idxs, _alive = pending.pop(0)
                 self._done[s].synchronize()
                 for j, i in enumerate(idxs):
-                    yield FrameResult(i, self._out[s][j].numpy(), float(self._f[s][j]))
+                    pts = self._xyz[s][: int(self._n[s][0])].numpy() if self.unproject else None
+                    yield FrameResult(i, self._out[s][j].numpy(), float(self._f[s][j]), pts)
 
         for i, frame in frames:
             if frame.shape != (self.H, self.W, 3) or frame.dtype != np.uint8:
                 raise ValueError(f"frame {i}: expected uint8 ({self.H},{self.W},3), got {frame.dtype} {frame.shape}")
+            if not batch_idx:
+                yield from drain(self._slots - 1)   # the slot about to be overwritten must have been handed out
             self._in[slot][len(batch_idx)].copy_(torch.from_numpy(frame))
             batch_idx.append(i)
             if len(batch_idx) == self.B:
                 flush(self.B)
                 batch_idx = []
-                yield from drain(self._slots - 1)
         if batch_idx:
             flush(len(batch_idx))
             batch_idx = []
@@ -228,13 +266,26 @@ def gather_records(records: List[dict], rank: int, world: int) -> Optional[List[
 def batch_generate_depth_maps(input_dir: str, output_dir: str, pattern: str = "*.png", downscale_factor: float = 1.0,
                               half_precision: bool = False, colored: bool = True, cmap: str = "turbo",
                               model: Optional[DepthPro] = None, rank: int = 0, world: int = 1,
-                              load_fn: Optional[Callable] = None) -> int:
-    """Drop-in for ``generate_depth_maps.batch_generate_depth_maps`` (:153-206): same arguments and
-    return value (number of frames written), plus optional frame sharding.  Errors are caught per
-    frame and the loop continues, like the reference (:147-151)."""
-    import cv2
+                              load_fn: Optional[Callable] = None, decode_threads: int = 4, write_threads: int = 4,
+                              slots: int = 4) -> int:
+    """Drop-in for ``generate_depth_maps.batch_generate_depth_maps`` (:153-206): same arguments and return value
+    (number of frames written), plus optional frame sharding.  Errors are caught per frame and the loop continues,
+    like the reference (:147-151).
 
-    from .utils import load_rgb
+    Execution model (the reference decodes, rebuilds the model, infers, colourises and writes one frame after the other
+    on one thread): ``pipeline.FrameLoader`` decodes / downscales on ``decode_threads`` host threads ahead of the GPU;
+    the GPU runs infer -> colourise (or 16-bit normalise) back to back; the small uint8 / uint16 result goes to a pinned
+    slot on a copy stream; ``write_threads`` host threads PNG-encode and write (``cv2.imwrite`` releases the GIL).
+
+    With ``model=None`` the model is built ONCE through ``create_model_and_transforms`` exactly like the reference's
+    per-frame call (:76-80): the checkpoint ``./checkpoints/depth_pro.pt`` is loaded under ``strict=True`` and a missing
+    file raises -- there is no random-weights fallback.
+    """
+    import cv2
+    from concurrent.futures import ThreadPoolExecutor
+
+    from .depth_pro import create_model_and_transforms
+    from .pipeline import FrameLoader
 
     os.makedirs(output_dir, exist_ok=True)
     paths = sorted(glob.glob(os.path.join(input_dir, pattern)))
@@ -243,32 +294,60 @@ def batch_generate_depth_maps(input_dir: str, output_dir: str, pattern: str = "*
         return 0
     if model is None:
         dev = torch.device("cuda", torch.cuda.current_device())
-        model = DepthPro(device=dev, precision=torch.bfloat16 if half_precision else torch.float32)
-        model.init_weights("reference", 0)
-    lut = torch.from_numpy(colormap_lut(cmap)).to(model._device) if colored else None
-    load_fn = load_fn or load_rgb
+        model, _ = create_model_and_transforms(device=dev, precision=torch.half if half_precision else torch.float32)
+        model.eval()
+    dev = model._device
+    lut = torch.from_numpy(colormap_lut(cmap)).to(dev) if colored else None
+    mine = [(i, paths[i]) for i in shard_frames(len(paths), rank, world)]
+    compute = torch.cuda.current_stream(dev)
+    d2h = torch.cuda.Stream(dev)
+    ring: Dict[Tuple[int, int], List[torch.Tensor]] = {}     # pinned result slots per output shape
+    busy: List = []                                           # (future, slot tensor) in submission order
     ok = 0
-    for i in shard_frames(len(paths), rank, world):
-        path = paths[i]
-        base = os.path.splitext(os.path.basename(path))[0]
-        out_path = os.path.join(output_dir, f"{base}_depth.png")
-        try:
-            image, _, f_px = load_fn(path)
-            if downscale_factor != 1.0 and downscale_factor > 0:
-                h, w = image.shape[:2]
-                nh, nw = int(h * downscale_factor), int(w * downscale_factor)
-                image = cv2.resize(image, (nw, nh),
-                                   interpolation=cv2.INTER_AREA if downscale_factor < 1.0 else cv2.INTER_LINEAR)
-                if f_px is not None:
-                    f_px = f_px * downscale_factor
-            pred = model.infer(torch.from_numpy(np.ascontiguousarray(image)), f_px=f_px)
-            depth = pred["depth"]
-            if colored:
-                rgb = colorize_depth(model, depth, lut=lut).cpu().numpy()
-                cv2.imwrite(out_path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
-            else:
-                cv2.imwrite(out_path, depth_to_uint16(model, depth).cpu().numpy().view(np.uint16))
-            ok += 1
-        except Exception as e:  # noqa: BLE001 — per-frame isolation, as in the reference
-            print(f"Error generating depth map for {path}: {e}")
+
+    def write(out_path, host, done, alive):
+        done.synchronize()
+        del alive
+        arr = host.numpy()
+        return bool(cv2.imwrite(out_path, cv2.cvtColor(arr, cv2.COLOR_RGB2BGR) if colored else arr.view(np.uint16)))
+
+    def reap(limit):
+        nonlocal ok
+        while len(busy) > limit:
+            fut, path, slot, key = busy.pop(0)
+            try:
+                if fut.result():
+                    ok += 1
+                else:
+                    print(f"Error generating depth map for {path}: cv2.imwrite failed")
+            except Exception as e:  # noqa: BLE001
+                print(f"Error generating depth map for {path}: {e}")
+            ring[key].append(slot)
+
+    with ThreadPoolExecutor(max_workers=max(1, write_threads), thread_name_prefix="depthpro-write") as pool:
+        for frame in FrameLoader(mine, downscale_factor, decode_threads, prefetch=2 * max(1, decode_threads), load_fn=load_fn):
+            base = os.path.splitext(os.path.basename(frame.path))[0]
+            out_path = os.path.join(output_dir, f"{base}_depth.png")
+            try:
+                if frame.image is None:
+                    raise RuntimeError(frame.error)
+                pred = model.infer(torch.from_numpy(frame.image), f_px=frame.f_px)
+                depth = pred["depth"]
+                H, W = depth.shape
+                res = colorize_depth(model, depth, lut=lut) if colored else depth_to_uint16(model, depth)
+                key = (H, W)
+                reap(slots - 1)
+                if not ring.setdefault(key, []):
+                    ring[key].append(torch.empty((H, W, 3) if colored else (H, W), dtype=res.dtype).pin_memory())
+                host = ring[key].pop()
+                ev, done = torch.cuda.Event(), torch.cuda.Event()
+                ev.record(compute)
+                d2h.wait_event(ev)
+                with torch.cuda.stream(d2h):
+                    host.copy_(res, non_blocking=True)
+                    done.record(d2h)
+                busy.append((pool.submit(write, out_path, host, done, (res, depth)), frame.path, host, key))
+            except Exception as e:  # noqa: BLE001 — per-frame isolation, as in the reference
+                print(f"Error generating depth map for {frame.path}: {e}")
+        reap(0)
     return ok

@@ -29,27 +29,6 @@ def _kb(kind, M, N, K, iters=1):
     return ms.value
 
 
-@pytest.mark.parametrize("expv", [12, 13, 14])
-@pytest.mark.parametrize("n", [1, 3, 37])
-def test_attention_p_through_tmem(expv, n):
-    """Variants 12-14 against fp64 SDPA on the bf16-rounded inputs, and against the default kernel."""
-    g = torch.Generator(device=DEV).manual_seed(200 + n)
-    qkv = torch.randn(n, 577, 3072, device=DEV, generator=g)
-    if n > 1:
-        qkv[1] *= 3.0
-    out, base = torch.empty(n, 577, 1024, device=DEV), torch.empty(n, 577, 1024, device=DEV)
-    try:
-        _kb(4, 1, 1 + expv, 0)  # sticky variant selection (the backend bits of dp_attention_test stop at 13)
-        _capi.check(lib().dp_attention_test(engine(), 1, qkv.data_ptr(), out.data_ptr(), n, stream()))
-    finally:
-        _capi.check(lib().dp_attention_test(engine(), 1 | (0xF << 8), qkv.data_ptr(), base.data_ptr(), n, stream()))
-    torch.cuda.synchronize()
-    q, k, v = qkv.bfloat16().double().reshape(n, 577, 3, 16, 64).permute(2, 0, 3, 1, 4)
-    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n, 577, 1024)
-    assert relerr(out, ref) < 1.5e-2
-    assert float((out - base).abs().mean() / base.abs().mean()) < 2e-3
-
-
 @pytest.mark.parametrize("H,W", [(1536, 1536), (1080, 1920), (2160, 3840), (333, 2001), (7, 5), (1, 1), (1081, 1023)])
 def test_depth_epilogue_v2_is_bit_identical(H, W):
     """DEPTHPRO_HBM_V2 (four output pixels per thread) must reproduce the default epilogue bit for bit, at aligned,

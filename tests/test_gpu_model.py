@@ -130,6 +130,144 @@ def test_bf16_vs_oracle(model_bf16, oracle_run):
     assert float(q[0]) <= 5e-3
     assert f_rel <= 1e-2
     assert float((~ok).float().mean()) <= 1e-3
+    # the tail is asserted too (VERDICT r1 weak #2): p99 and max over ALL 2.36 M un-clamped pixels
+    assert float(q[2]) <= 2e-2 and float(rel.max()) <= 5e-2
+    # border ring: the composed head (head.1 o head.2, border-aware bias) and every padded conv differ from the
+    # interior only on the outermost pixels -- same tolerance there as everywhere else
+    ring = torch.zeros(1536, 1536, dtype=torch.bool)
+    for i in (0, 1, 1534, 1535):
+        ring[i, :] = True
+        ring[:, i] = True
+    rr = _pix_rel(depth, ref["depth"])[ring & (ref["depth"] < 1e4 - 1) & (depth < 1e4 - 1)].float()
+    print(f"  border ring ({int(ring.sum())} px): median {float(rr.median()):.3e} p99 {float(torch.quantile(rr, 0.99)):.3e} "
+          f"max {float(rr.max()):.3e}")
+    assert float(rr.median()) <= 5e-3 and float(torch.quantile(rr, 0.99)) <= 2e-2 and float(rr.max()) <= 5e-2
+    corners = _pix_rel(depth, ref["depth"])[[0, 0, 1535, 1535], [0, 1535, 0, 1535]]
+    assert float(corners.max()) <= 5e-2
+
+
+def test_bf16_1080p_u8_vs_golden(model_bf16, golden_dir):
+    """The bf16 engine on the uint8 1080p video frame (fused transform + resize in, resize back out) against the
+    REFERENCE's recorded fp32 output for that frame (tests/golden: depth_1080p, generate_depth_maps.py:113-121)."""
+    gold = np.load(os.path.join(golden_dir, "reference_outputs.npz"))
+    pred = model_bf16.infer(torch.from_numpy(O.synthetic_frame_u8(0)))
+    assert pred["depth"].shape == (1080, 1920)
+    g = torch.from_numpy(gold["depth_1080p"])
+    d = pred["depth"].cpu()[::16, ::16]
+    ok = (g < 1e4 - 1) & (d < 1e4 - 1)
+    rel = _pix_rel(d, g)[ok].float()
+    f_rel = abs(float(pred["focallength_px"]) - float(gold["f_px_1080p"])) / float(gold["f_px_1080p"])
+    print(f"bf16 1080p: depth abs-rel median {float(rel.median()):.3e} p99 {float(torch.quantile(rel, 0.99)):.3e} "
+          f"max {float(rel.max()):.3e}; f_px rel {f_rel:.3e}")
+    assert float(rel.median()) <= 5e-3 and float(torch.quantile(rel, 0.99)) <= 2e-2 and float(rel.max()) <= 5e-2
+    assert f_rel <= 1e-2 and float((~ok).float().mean()) <= 1e-3
+    # last row / last column of the 1080p output (never on a ::16 grid of 1080 rows): finite and inside the clamp
+    edge = torch.cat([pred["depth"][-1, :], pred["depth"][:, -1]])
+    assert bool(torch.isfinite(edge).all()) and float(edge.min()) >= 1e-4 - 1e-9 and float(edge.max()) <= 1e4 * (1 + 1e-6)
+
+
+def _oracle_vs_bf16(sd, seed_img):
+    torch.set_num_threads(os.cpu_count())
+    x = O.synthetic_image_1536(seed_img)
+    ref = O.infer(sd, x)
+    m = _model(sd, torch.bfloat16)
+    pred = m.infer(x.to(DEV))
+    canon, _ = m.forward(x[None].to(DEV))
+    del m
+    torch.cuda.empty_cache()
+    return x, ref, pred, canon[0, 0].cpu()
+
+
+def test_bf16_second_seed():
+    """A second weight seed AND a second input: the bf16 claim must not rest on one draw (VERDICT r1 weak #2)."""
+    sd = weights.stress_init(4321)
+    _, ref, pred, _ = _oracle_vs_bf16(sd, 2)
+    depth = pred["depth"].cpu()
+    ok = (ref["depth"] < 1e4 - 1) & (depth < 1e4 - 1)
+    rel = _pix_rel(depth, ref["depth"])[ok].float()
+    q = torch.quantile(rel[:: max(1, rel.numel() // 1_000_000)], torch.tensor([0.5, 0.99]))
+    f_rel = abs(float(pred["focallength_px"]) - float(ref["focallength_px"])) / float(ref["focallength_px"])
+    # This draw has pixels whose inverse depth comes close to the final ReLU's kink (seed 1234 has none: min 0.74), where
+    # a RELATIVE error is unbounded (measured max 0.22 on an inverse depth of 0.05).  The max is therefore asserted as
+    # (a) relative error on pixels whose reference inverse depth is at least a quarter of the median, and (b) absolute
+    # error of the inverse depth, in units of the median inverse depth, everywhere.
+    inv_ref, inv = 1.0 / ref["depth"].double(), 1.0 / depth.double()
+    scale = float(inv_ref[ok].median())
+    solid = ok & (inv_ref >= 0.25 * scale)
+    rel_solid = _pix_rel(depth, ref["depth"])[solid].float()
+    abs_inv = ((inv - inv_ref).abs() / scale)[ok].float()
+    print(f"bf16 seed 4321 / image 2: median {float(q[0]):.3e} p99 {float(q[1]):.3e} max {float(rel.max()):.3e} "
+          f"(inverse depth >= median/4: {float(solid.float().mean()):.4f} of pixels, max {float(rel_solid.max()):.3e}); "
+          f"|d inv| / median inv max {float(abs_inv.max()):.3e}; f_px {f_rel:.3e}")
+    assert float(q[0]) <= 5e-3 and float(q[1]) <= 2e-2
+    assert float(rel_solid.max()) <= 5e-2 and float(abs_inv.max()) <= 2e-2
+    assert f_rel <= 1e-2 and float((~ok).float().mean()) <= 1e-3
+
+
+def test_bf16_adversarial_zeros_init():
+    """SURVEY.md §7 hard-part 1: an init whose final pre-ReLU map straddles zero (head.4 bias 0, weight x4), so a large
+    share of the canonical inverse depth is EXACTLY 0 (depth clamped at 1e4) and the rest comes arbitrarily close to the
+    ReLU kink.  Relative error is unbounded at the kink, so the grading is: (1) the zero masks agree except where the
+    reference value itself is within bf16 noise of 0; (2) absolute error of the canonical inverse depth, relative to its
+    scale, over ALL pixels; (3) abs-rel of depth on pixels comfortably above the kink."""
+    sd = weights.stress_init(1234)
+    sd["head.4.bias"] = torch.zeros(1)
+    sd["head.4.weight"] = sd["head.4.weight"] * 4.0
+    x = O.synthetic_image_1536(1)
+    torch.set_num_threads(os.cpu_count())
+    canon_ref, _ = O.forward(sd, x[None])
+    canon_ref = canon_ref[0, 0]
+    m = _model(sd, torch.bfloat16)
+    canon, _ = m.forward(x[None].to(DEV))
+    canon = canon[0, 0].cpu()
+    del m
+    zero_frac = float((canon_ref == 0).float().mean())
+    scale = float(canon_ref[canon_ref > 0].median())
+    abs_err = (canon - canon_ref).abs() / scale
+    flips = (canon == 0) != (canon_ref == 0)
+    flip_mag = torch.maximum(canon, canon_ref)[flips] / scale            # how far from the kink the disagreeing pixels are
+    far = canon_ref > 0.5 * scale
+    rel_far = ((canon - canon_ref).abs() / canon_ref)[far]
+    print(f"adversarial: zeros {zero_frac:.2%}, scale {scale:.3f}; |err|/scale median {float(abs_err.median()):.3e} "
+          f"max {float(abs_err.max()):.3e}; mask flips {float(flips.float().mean()):.2e} (largest {float(flip_mag.max()) if flips.any() else 0:.3e}); "
+          f"rel on far pixels median {float(rel_far.median()):.3e} max {float(rel_far.max()):.3e}")
+    assert 0.05 <= zero_frac <= 0.95, "the init is meant to put a large share of the map on the ReLU kink"
+    # head.4's weight x4 with no bias makes the output a zero-mean sum: the same absolute bf16 noise of the 32 head
+    # channels is 4x larger relative to the output than in recipe B (measured: median 5.3e-3, max 5.8e-2 of the scale).
+    # These are robustness guards for the kink, not the BASELINE.md tolerance (that one is asserted on recipe B above).
+    assert float(abs_err.max()) <= 1e-1 and float(abs_err.median()) <= 1e-2
+    assert float(flips.float().mean()) <= 2e-2 and (not flips.any() or float(flip_mag.max()) <= 1e-1)
+    assert float(rel_far.median()) <= 1e-2 and float(rel_far.max()) <= 2e-1
+
+
+def test_bf16_layernorm_fold_with_outlier_channels(monkeypatch):
+    """ADVICE r1: real DINOv2-L checkpoints carry a few residual-stream channels with activations two orders of
+    magnitude above the rest.  The folded LayerNorm subtracts rstd*mean*colsum AFTER the GEMM on the bf16-rounded raw
+    x, which is where such channels could cost accuracy: plant them (pos_embed + 40 in three channels of every encoder,
+    ~100x the typical |x|), and require the folded path to stay as close to the fp32 oracle as the stand-alone one."""
+    sd = weights.stress_init(1234)
+    for p in weights.VIT_PREFIXES:
+        pe = sd[p + "pos_embed"].clone()
+        pe[..., [5, 300, 911]] += torch.tensor([40.0, -55.0, 70.0])
+        sd[p + "pos_embed"] = pe
+    x = O.synthetic_image_1536(1)
+    torch.set_num_threads(os.cpu_count())
+    ref = O.infer(sd, x)["depth"]
+    folded_m = _model(sd, torch.bfloat16)
+    folded = folded_m.infer(x.to(DEV))["depth"].cpu()
+    del folded_m
+    monkeypatch.setenv("DEPTHPRO_LN_FUSE", "0")
+    plain_m = _model(sd, torch.bfloat16)
+    plain = plain_m.infer(x.to(DEV))["depth"].cpu()     # the engine (and its LN mode) is created by the first call
+    monkeypatch.delenv("DEPTHPRO_LN_FUSE")
+    del plain_m
+    assert not torch.equal(plain, folded), "DEPTHPRO_LN_FUSE=0 did not select the stand-alone LayerNorm path"
+    ok = (ref < 1e4 - 1) & (folded < 1e4 - 1) & (plain < 1e4 - 1)
+    e_f, e_p = _pix_rel(folded, ref)[ok].float(), _pix_rel(plain, ref)[ok].float()
+    print(f"outlier channels: folded median {float(e_f.median()):.3e} p99 {float(torch.quantile(e_f[::4], 0.99)):.3e}; "
+          f"stand-alone median {float(e_p.median()):.3e} p99 {float(torch.quantile(e_p[::4], 0.99)):.3e}")
+    assert float(e_f.median()) <= 5e-3
+    assert float(e_f.median()) <= 1.5 * float(e_p.median()) + 5e-4
 
 
 def test_bf16_layernorm_fold_matches_standalone_layernorm(model_bf16, oracle_run, monkeypatch):

@@ -173,3 +173,28 @@ def test_process_frames_shards_partition_the_clip(tmp_path):
         got[rank] = seen
     assert got[0] == [0, 2, 4, 6] and got[1] == [1, 3, 5]
     assert len(json.load(open(tmp_path / "out" / pipeline.PROGRESS_FILE))) == 7
+
+
+def test_interrupted_multi_rank_resume_partitions_exactly_the_pending_set(tmp_path):
+    """after a killed world=2 run there are two rank shard files and NO merged file.  On resume
+    every rank must see the union of what both ranks finished, and the frames still to do must be split by CLIP
+    POSITION (i % world), so that the two ranks together process exactly the pending set, nothing twice."""
+    frames, out = tmp_path / "frames", tmp_path / "out"
+    frames.mkdir(), out.mkdir()
+    _make_clip(frames, 10)
+    stamp = {"success": True, "timestamp": 1.0}
+    # the interrupted run: rank 0 had finished clip positions 0, 2, 4; rank 1 had finished 1, 3
+    json.dump({f"output_{i:04d}.png": stamp for i in (0, 2, 4)}, open(out / "processing_progress.rank0.json", "w"))
+    json.dump({f"output_{i:04d}.png": stamp for i in (1, 3)}, open(out / "processing_progress.rank1.json", "w"))
+    got = {}
+    for rank in (1, 0):
+        seen = []
+        s = pipeline.process_frames(str(frames), str(out), _FakeModel(), lambda o: seen.append(o.index), unproject=False,
+                                    pattern="output_000*.png", resume=True, rank=rank, world=2, log=lambda m: None)
+        got[rank] = seen
+        # the ranks run one after the other here: rank 0 also sees the three frames rank 1 has just finished
+        assert s.total == 10 and s.skipped == (5 if rank == 1 else 8)
+    assert got[0] == [6, 8] and got[1] == [5, 7, 9]                         # clip positions, owner = i % 2
+    assert sorted(got[0] + got[1]) == [5, 6, 7, 8, 9]                       # exactly the pending set, no overlap
+    merged = json.load(open(out / pipeline.PROGRESS_FILE))
+    assert set(merged) == {f"output_{i:04d}.png" for i in range(10)}
