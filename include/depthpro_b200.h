@@ -44,6 +44,14 @@ int dp_version(void);
 
 /* src/depth_pro/depth_pro.py:72-123  create_model_and_transforms (model construction). */
 int dp_engine_create(int device, int precision, int max_batch, dp_engine** out);
+/* Non-default configurations of src/depth_pro/depth_pro.py:26-36, 100-108 (DepthProConfig.use_fov_head /
+ * fov_encoder_preset) and src/depth_pro/network/fov.py:29-56.  fov_mode 2 = the default (FOV head with its own ViT-L
+ * encoder; dp_engine_create), 1 = FOV head WITHOUT encoder (fov_encoder_preset=None: state_dict keys fov.head.{0,2,4,6},
+ * four convs on the low-resolution decoder feature), 0 = use_fov_head=False (no fov.* keys; dp_forward leaves fov_deg
+ * untouched -- it may be NULL -- and dp_infer fails unless f_px_host is given, where the reference fails on
+ * fov_deg=None, depth_pro.py:282-283). */
+enum { DP_FOV_NONE = 0, DP_FOV_HEAD_ONLY = 1, DP_FOV_ENCODER = 2 };
+int dp_engine_create_ex(int device, int precision, int max_batch, int fov_mode, dp_engine** out);
 int dp_engine_destroy(dp_engine* e);
 
 /* src/depth_pro/depth_pro.py:134-149  (load_state_dict): hand over ONE tensor of the
@@ -64,6 +72,13 @@ int dp_engine_finalize(dp_engine* e);
  * bilinear, align_corners=False).  img -> x_1536 float32 (B,3,1536,1536). */
 int dp_preprocess(dp_engine* e, const void* img, int B, int H, int W, int src_fmt,
                   float* x_1536, void* stream);
+
+/* The same with DepthPro.infer's `interpolation_mode` (depth_pro.py:247, 273-279): DP_INTERP_BILINEAR or
+ * DP_INTERP_BICUBIC (ATen upsample_bicubic2d, align_corners=False, A = -0.75) -- the only two modes F.interpolate accepts
+ * with align_corners=False on 4-D input; the reference raises ValueError for every other mode, and so does the shim. */
+enum { DP_INTERP_BILINEAR = 0, DP_INTERP_BICUBIC = 1 };
+int dp_preprocess_ex(dp_engine* e, const void* img, int B, int H, int W, int src_fmt, int interp_mode,
+                     float* x_1536, void* stream);
 
 /* src/depth_pro/network/encoder.py:151-188, 253-263  (_create_pyramid + split + cat):
  * x_1536 (B,3,1536,1536) -> patches float32 (35*B,3,384,384) in the REFERENCE order
@@ -87,6 +102,10 @@ int dp_forward(dp_engine* e, const float* x_1536, int B, float* canon_inv_depth,
 int dp_infer(dp_engine* e, const void* img, int B, int H, int W, int src_fmt,
              const float* f_px_host, float* depth_out, float* f_px_out, void* stream);
 
+/* dp_infer with `interpolation_mode` for BOTH resizes (depth_pro.py:273-279 and :288-291). */
+int dp_infer_ex(dp_engine* e, const void* img, int B, int H, int W, int src_fmt, int interp_mode,
+                const float* f_px_host, float* depth_out, float* f_px_out, void* stream);
+
 /* Same call with HOST buffers: H2D copy, dp_infer, D2H copy, stream sync.  This is the
  * call generate_depth_maps.py:113-121 (transform -> infer -> .cpu().numpy()) amounts to. */
 int dp_infer_host(dp_engine* e, const void* img_host, int B, int H, int W, int src_fmt,
@@ -105,6 +124,10 @@ int dp_unproject(dp_engine* e, const float* depth, const uint8_t* rgb, int H, in
  * normalised depth to `out` instead. */
 int dp_colorize(dp_engine* e, const float* depth, int H, int W, const uint8_t* lut,
                 void* out, void* stream);
+/* colorize_depth(depth, min_depth, max_depth, cmap) with caller-supplied range ends (generate_depth_maps.py:15-31):
+ * NaN = "None" = the image's own nanmin / nanmax.  With both ends given the reduction pass is skipped (one launch). */
+int dp_colorize_range(dp_engine* e, const float* depth, int H, int W, const uint8_t* lut,
+                      void* out, float min_depth, float max_depth, void* stream);
 
 /* img_to_normalized_pointcloud.py:880-975  normalize_point_cloud_to_ground, on the points dp_unproject
  * produced: xyz float32 (n,3) on the device, updated IN PLACE.  `normal3` (host, 3 doubles) and `d` are the

@@ -1,4 +1,5 @@
 // extern "C" boundary of the engine (include/depthpro_b200.h).  No C++ or torch types cross it.
+#include <cmath>
 #include <string>
 
 #include "../../include/depthpro_b200.h"
@@ -39,6 +40,12 @@ int dp_engine_create(int device, int precision, int max_batch, dp_engine** out) 
     *out = reinterpret_cast<dp_engine*>(new dp::Engine(device, precision, max_batch));
   });
 }
+int dp_engine_create_ex(int device, int precision, int max_batch, int fov_mode, dp_engine** out) {
+  return guard([&] {
+    if (!out) throw dp::Error("null out pointer");
+    *out = reinterpret_cast<dp_engine*>(new dp::Engine(device, precision, max_batch, fov_mode));
+  });
+}
 int dp_engine_destroy(dp_engine* e) {
   return guard([&] { delete reinterpret_cast<dp::Engine*>(e); });
 }
@@ -54,7 +61,11 @@ int dp_engine_finalize(dp_engine* e) {
   return guard([&] { E(e)->finalize(); });
 }
 int dp_preprocess(dp_engine* e, const void* img, int B, int H, int W, int src_fmt, float* x_1536, void* stream) {
-  return guard([&] { E(e)->preprocess(img, B, H, W, src_fmt, x_1536, S(stream)); });
+  return guard([&] { E(e)->preprocess(img, B, H, W, src_fmt, x_1536, 0, S(stream)); });
+}
+int dp_preprocess_ex(dp_engine* e, const void* img, int B, int H, int W, int src_fmt, int interp_mode, float* x_1536,
+                     void* stream) {
+  return guard([&] { E(e)->preprocess(img, B, H, W, src_fmt, x_1536, interp_mode, S(stream)); });
 }
 int dp_split(dp_engine* e, const float* x_1536, int B, float* patches, void* stream) {
   return guard([&] { E(e)->split(x_1536, B, patches, S(stream)); });
@@ -67,7 +78,11 @@ int dp_forward(dp_engine* e, const float* x_1536, int B, float* canon_inv_depth,
 }
 int dp_infer(dp_engine* e, const void* img, int B, int H, int W, int src_fmt, const float* f_px_host, float* depth_out,
              float* f_px_out, void* stream) {
-  return guard([&] { E(e)->infer(img, B, H, W, src_fmt, f_px_host, depth_out, f_px_out, S(stream)); });
+  return guard([&] { E(e)->infer(img, B, H, W, src_fmt, f_px_host, depth_out, f_px_out, 0, S(stream)); });
+}
+int dp_infer_ex(dp_engine* e, const void* img, int B, int H, int W, int src_fmt, int interp_mode, const float* f_px_host,
+                float* depth_out, float* f_px_out, void* stream) {
+  return guard([&] { E(e)->infer(img, B, H, W, src_fmt, f_px_host, depth_out, f_px_out, interp_mode, S(stream)); });
 }
 int dp_infer_host(dp_engine* e, const void* img_host, int B, int H, int W, int src_fmt, const float* f_px_host,
                   float* depth_out_host, float* f_px_out_host) {
@@ -78,7 +93,11 @@ int dp_unproject(dp_engine* e, const float* depth, const uint8_t* rgb, int H, in
   return guard([&] { E(e)->unproject(depth, rgb, H, W, f_px_dev, xyz, rgb_out, valid_mask, n_valid, S(stream)); });
 }
 int dp_colorize(dp_engine* e, const float* depth, int H, int W, const uint8_t* lut, void* out, void* stream) {
-  return guard([&] { E(e)->colorize(depth, H, W, lut, out, S(stream)); });
+  return guard([&] { E(e)->colorize(depth, H, W, lut, out, NAN, NAN, S(stream)); });
+}
+int dp_colorize_range(dp_engine* e, const float* depth, int H, int W, const uint8_t* lut, void* out, float min_depth,
+                      float max_depth, void* stream) {
+  return guard([&] { E(e)->colorize(depth, H, W, lut, out, min_depth, max_depth, S(stream)); });
 }
 int dp_ground_normalize(dp_engine* e, float* xyz, int64_t n, const double* normal3, double d, uint64_t* counters,
                         void* stream) {

@@ -107,11 +107,11 @@ void add_vit(std::map<std::string, std::vector<int64_t>>& m, const std::string& 
 }
 
 // name -> shape of the reference state_dict (pinned by tests/golden/state_dict_manifest.json)
-std::map<std::string, std::vector<int64_t>> build_manifest() {
+std::map<std::string, std::vector<int64_t>> build_manifest(int fov_mode) {
   std::map<std::string, std::vector<int64_t>> m;
   add_vit(m, "encoder.patch_encoder.");
   add_vit(m, "encoder.image_encoder.");
-  add_vit(m, "fov.encoder.0.");
+  if (fov_mode == 2) add_vit(m, "fov.encoder.0.");
   m["encoder.upsample_latent0.0.weight"] = {256, EMB, 1, 1};
   for (int i = 1; i <= 3; ++i) m["encoder.upsample_latent0." + std::to_string(i) + ".weight"] = {256, 256, 2, 2};
   m["encoder.upsample_latent1.0.weight"] = {256, EMB, 1, 1};
@@ -147,16 +147,27 @@ std::map<std::string, std::vector<int64_t>> build_manifest() {
   m["head.2.bias"] = {32};
   m["head.4.weight"] = {1, 32, 1, 1};
   m["head.4.bias"] = {1};
-  m["fov.encoder.1.weight"] = {128, EMB};
-  m["fov.encoder.1.bias"] = {128};
-  m["fov.downsample.0.weight"] = {128, 256, 3, 3};
-  m["fov.downsample.0.bias"] = {128};
-  m["fov.head.0.weight"] = {64, 128, 3, 3};
-  m["fov.head.0.bias"] = {64};
-  m["fov.head.2.weight"] = {32, 64, 3, 3};
-  m["fov.head.2.bias"] = {32};
-  m["fov.head.4.weight"] = {1, 32, 6, 6};
-  m["fov.head.4.bias"] = {1};
+  if (fov_mode == 2) {  // fov.py:47-54: encoder + Linear, downsample = fov_head0, head = the remaining three convs
+    m["fov.encoder.1.weight"] = {128, EMB};
+    m["fov.encoder.1.bias"] = {128};
+    m["fov.downsample.0.weight"] = {128, 256, 3, 3};
+    m["fov.downsample.0.bias"] = {128};
+    m["fov.head.0.weight"] = {64, 128, 3, 3};
+    m["fov.head.0.bias"] = {64};
+    m["fov.head.2.weight"] = {32, 64, 3, 3};
+    m["fov.head.2.bias"] = {32};
+    m["fov.head.4.weight"] = {1, 32, 6, 6};
+    m["fov.head.4.bias"] = {1};
+  } else if (fov_mode == 1) {  // fov.py:55-56: head = fov_head0 + fov_head (Sequential indices 0, 2, 4, 6)
+    m["fov.head.0.weight"] = {128, 256, 3, 3};
+    m["fov.head.0.bias"] = {128};
+    m["fov.head.2.weight"] = {64, 128, 3, 3};
+    m["fov.head.2.bias"] = {64};
+    m["fov.head.4.weight"] = {32, 64, 3, 3};
+    m["fov.head.4.bias"] = {32};
+    m["fov.head.6.weight"] = {1, 32, 6, 6};
+    m["fov.head.6.bias"] = {1};
+  }
   return m;
 }
 
@@ -181,8 +192,10 @@ bool is_convT(const std::string& n) {
 }  // namespace
 
 // ============================================================================ lifecycle
-Engine::Engine(int device, int prec, int max_batch) : device_(device), prec_(prec), max_batch_(max_batch) {
+Engine::Engine(int device, int prec, int max_batch, int fov_mode)
+    : device_(device), prec_(prec), max_batch_(max_batch), fov_mode_(fov_mode), n_enc_(fov_mode == 2 ? 3 : 2) {
   DP_CHECK(prec == FP32 || prec == BF16, "precision must be 0 (fp32) or 1 (bf16)");
+  DP_CHECK(fov_mode >= 0 && fov_mode <= 2, "fov_mode must be 0 (no FOV head), 1 (head without encoder) or 2 (default)");
   DP_CHECK(max_batch >= 1 && max_batch <= 64, "max_batch out of range");
   int count = 0;
   DP_CUDA(cudaGetDeviceCount(&count));
@@ -192,7 +205,7 @@ Engine::Engine(int device, int prec, int max_batch) : device_(device), prec_(pre
   DP_CUDA(cudaGetDeviceProperties(&prop, device));
   DP_CHECK(prop.major == 10, "depthpro_b200 is built for sm_100a (Blackwell B200) only; found sm_" +
                                  std::to_string(prop.major) + std::to_string(prop.minor));
-  manifest_ = build_manifest();
+  manifest_ = build_manifest(fov_mode_);
   const char* a = getenv("DEPTHPRO_ATTN");  // debugging switch: "mma" selects the mma.sync kernel
   attn_legacy_ = a != nullptr && std::string(a) == "mma";
   const char* lf = getenv("DEPTHPRO_LN_FUSE");  // debugging switch: "0" keeps the stand-alone LayerNorm launches
@@ -224,6 +237,7 @@ void Engine::set_weight(const std::string& name, const void* data, const int64_t
   DP_CUDA(cudaSetDevice(device_));
   auto it = manifest_.find(name);
   if (it == manifest_.end()) throw Error("unexpected key in state_dict: " + name);
+  weights_changed_ = true;
   const auto& ms = it->second;
   DP_CHECK(static_cast<int>(ms.size()) == ndim, "rank mismatch for " + name);
   size_t n = 1;
@@ -266,7 +280,8 @@ void Engine::set_weight(const std::string& name, const void* data, const int64_t
       pk.bytes = bytes;
     }
   };
-  const bool fov_conv = name == "fov.head.4.weight";  // 6x6 valid conv, reduced by fov_final (fp32 HWIO)
+  // the 6x6 valid conv that ends the FOV head, reduced by fov_final (fp32 HWIO)
+  const bool fov_conv = name == (fov_mode_ == 1 ? "fov.head.6.weight" : "fov.head.4.weight") && fov_mode_ != 0;
   if (ndim == 4 && is_convT(name)) {
     ensure(n * esz());
     if (bf) pack_convT_iohw<bf16>(src, reinterpret_cast<bf16*>(pk.ptr), (int)shape[0], (int)shape[1], s);
@@ -333,6 +348,7 @@ VitWeights Engine::vit_weights(const std::string& p) const {
 
 void Engine::finalize() {
   DP_CUDA(cudaSetDevice(device_));
+  if (finalized_ && !weights_changed_) return;  // nothing was handed over since the last finalize: no-op
   if (missing_weights() != 0) {
     for (auto& kv : manifest_)
       if (!packed_.count(kv.first)) throw Error("missing key in state_dict: " + kv.first);
@@ -350,6 +366,7 @@ void Engine::finalize() {
       return pk.ptr;
     };
     for (const char* enc : {"encoder.patch_encoder.", "encoder.image_encoder.", "fov.encoder.0."}) {
+      if (fov_mode_ != 2 && std::string(enc) == "fov.encoder.0.") continue;
       for (int i = 0; i < 24; ++i) {
         const std::string b = std::string(enc) + "blocks." + std::to_string(i) + ".";
         const std::pair<const char*, const char*> pairs[2] = {{"attn.qkv", "norm1"}, {"mlp.fc1", "norm2"}};
@@ -379,7 +396,7 @@ void Engine::finalize() {
   }
   vit_patch_ = vit_weights("encoder.patch_encoder.");
   vit_image_ = vit_weights("encoder.image_encoder.");
-  vit_fov_ = vit_weights("fov.encoder.0.");
+  if (fov_mode_ == 2) vit_fov_ = vit_weights("fov.encoder.0.");
   if (prec_ == BF16) {
     // exact-linear fusion head.1 o head.2 (no nonlinearity in between, depth_pro.py:182-201),
     // composed in fp32 from the fp32 originals, then rounded to bf16 once
@@ -399,11 +416,12 @@ void Engine::finalize() {
     }
     DP_CUDA(cudaStreamSynchronize(nullptr));
   }
+  weights_changed_ = false;
   if (finalized_) return;  // workspace already allocated; weights re-bound above
 
   const size_t e = esz();
   const size_t MB = static_cast<size_t>(max_batch_);
-  const size_t T = MB * 37 * SEQ;  // 35 patch + 1 image + 1 fov sequence per frame
+  const size_t T = MB * seqs_per_frame() * SEQ;  // 35 patch + 1 image (+ 1 fov) sequences per frame
   xbuf_ = (float*)alloc(MB * 3 * IMG * IMG * 4);
   canon_ = (float*)alloc(MB * IMG * IMG * 4);
   fov_ = (float*)alloc(MB * 4);
@@ -441,15 +459,16 @@ void Engine::finalize() {
   fovcol_ = alloc(P24 * 2304 * e);
   fovlin_ = alloc(P24 * 128 * e), fov_a_ = alloc(P24 * 128 * e), fov_b_ = alloc(12 * 12 * 64 * e),
   fov_c_ = alloc(6 * 6 * 32 * e);
-  colorize_mm_ = (float*)alloc(64);
+  colorize_mm_ = (float*)alloc(colorize_scratch_bytes());
   finalized_ = true;
 }
 
 // ============================================================================ small entry points
-void Engine::preprocess(const void* img, int B, int H, int W, int src_fmt, float* x, cudaStream_t s) {
+void Engine::preprocess(const void* img, int B, int H, int W, int src_fmt, float* x, int interp, cudaStream_t s) {
   DP_CHECK(B >= 1 && H >= 1 && W >= 1, "bad image shape");
   DP_CHECK(src_fmt == 0 || src_fmt == 1, "bad src_fmt");
-  resize_to_1536(img, src_fmt, B, H, W, x, s);
+  DP_CHECK(interp == INTERP_BILINEAR || interp == INTERP_BICUBIC, "interpolation mode must be 0 (bilinear) or 1 (bicubic)");
+  resize_to_1536(img, src_fmt, B, H, W, x, interp, s);
 }
 
 void Engine::split(const float* x, int B, float* patches, cudaStream_t s) {
@@ -485,8 +504,9 @@ void Engine::merge(const float* tokens, int B, int steps, int padding, int C, fl
 template <typename T>
 void Engine::run_vits(int B, cudaStream_t s) {
   const VitWeights* vw[3] = {&vit_patch_, &vit_image_, &vit_fov_};
+  const int NG = n_enc_;  // 3 encoders, or 2 without the fov encoder
   const int nseq_g[3] = {35 * B, B, B};
-  const int nseq = 37 * B;
+  const int nseq = seqs_per_frame() * B;
   const long long M = static_cast<long long>(nseq) * SEQ;
   T* xn = (T*)xn_;
   T* qkv = (T*)qkv_;
@@ -495,9 +515,9 @@ void Engine::run_vits(int B, cudaStream_t s) {
   float* resid = resid_;
 
   auto grouped = [&](GemmOp& op, int rows_per_seq, bool a_shared_small) {
-    op.ngroups = 3;
+    op.ngroups = NG;
     long long off = 0, aoff = 0;
-    for (int g = 0; g < 3; ++g) {
+    for (int g = 0; g < NG; ++g) {
       op.grp[g].M = nseq_g[g] * rows_per_seq;
       op.grp[g].o_row_off = off;
       op.grp[g].a_row_off = aoff;
@@ -514,16 +534,16 @@ void Engine::run_vits(int B, cudaStream_t s) {
     op.N = EMB, op.K = 768, op.A = A35_, op.lda = 768;
     op.out = resid, op.out_f32 = 1, op.out_mode = O_PATCH_EMBED, op.ldo = EMB;
     grouped(op, 576, true);
-    for (int g = 0; g < 3; ++g) op.grp[g].Wt = vw[g]->pe_w, op.grp[g].bias = vw[g]->pe_b, op.grp[g].pos = vw[g]->pos;
+    for (int g = 0; g < NG; ++g) op.grp[g].Wt = vw[g]->pe_w, op.grp[g].bias = vw[g]->pe_b, op.grp[g].pos = vw[g]->pos;
     gemm(prec_, op, s);
     int seq0 = 0;
-    for (int g = 0; g < 3; ++g) {
+    for (int g = 0; g < NG; ++g) {
       write_cls_rows(resid + static_cast<long long>(seq0) * SEQ * EMB, vw[g]->cls, vw[g]->pos, nseq_g[g], s);
       seq0 += nseq_g[g];
     }
   }
   LnGroups lg;
-  lg.n = 3;
+  lg.n = NG;
   lg.end[0] = 35LL * B * SEQ, lg.end[1] = 36LL * B * SEQ, lg.end[2] = M;
   // bf16 mode: norm1 / norm2 are folded into qkv / fc1 (common.cuh GemmOp::ln_stats); xn holds the RAW
   // bf16 residual stream, written with its row statistics by this one launch for layer 0 and by the
@@ -533,17 +553,17 @@ void Engine::run_vits(int B, cudaStream_t s) {
   for (int i = 0; i < 24; ++i) {
     if (!fuse) {
       ProfScope ps(s, KC_LAYERNORM, static_cast<double>(M) * EMB * (4 + sizeof(T)));
-      for (int g = 0; g < 3; ++g) lg.w[g] = vw[g]->blk[i].n1w, lg.b[g] = vw[g]->blk[i].n1b;
+      for (int g = 0; g < NG; ++g) lg.w[g] = vw[g]->blk[i].n1w, lg.b[g] = vw[g]->blk[i].n1b;
       layernorm_rows_grouped<T>(resid, xn, lg, M, s);
     }
     {
       GemmOp op;
       op.N = 3 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.out = qkv, op.ldo = 3 * EMB;
       grouped(op, SEQ, false);
-      for (int g = 0; g < 3; ++g) op.grp[g].Wt = vw[g]->blk[i].qkv_w, op.grp[g].bias = vw[g]->blk[i].qkv_b;
+      for (int g = 0; g < NG; ++g) op.grp[g].Wt = vw[g]->blk[i].qkv_w, op.grp[g].bias = vw[g]->blk[i].qkv_b;
       if (fuse) {
         op.ln_stats = ln_stats_;
-        for (int g = 0; g < 3; ++g) op.grp[g].ln_c = vw[g]->blk[i].qkv_c;
+        for (int g = 0; g < NG; ++g) op.grp[g].ln_c = vw[g]->blk[i].qkv_c;
       }
       gemm(prec_, op, s);
     }
@@ -561,24 +581,24 @@ void Engine::run_vits(int B, cudaStream_t s) {
       op.N = EMB, op.K = EMB, op.A = attn, op.lda = EMB;
       op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
       grouped(op, SEQ, false);
-      for (int g = 0; g < 3; ++g)
+      for (int g = 0; g < NG; ++g)
         op.grp[g].Wt = vw[g]->blk[i].proj_w, op.grp[g].bias = vw[g]->blk[i].proj_b, op.grp[g].gamma = vw[g]->blk[i].g1;
       if (fuse) op.ln_xb = xn, op.ln_stats_out = ln_stats_;
       gemm(prec_, op, s);
     }
     if (!fuse) {
       ProfScope ps(s, KC_LAYERNORM, static_cast<double>(M) * EMB * (4 + sizeof(T)));
-      for (int g = 0; g < 3; ++g) lg.w[g] = vw[g]->blk[i].n2w, lg.b[g] = vw[g]->blk[i].n2b;
+      for (int g = 0; g < NG; ++g) lg.w[g] = vw[g]->blk[i].n2w, lg.b[g] = vw[g]->blk[i].n2b;
       layernorm_rows_grouped<T>(resid, xn, lg, M, s);
     }
     {
       GemmOp op;
       op.N = 4 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.act = ACT_GELU, op.out = hid, op.ldo = 4 * EMB;
       grouped(op, SEQ, false);
-      for (int g = 0; g < 3; ++g) op.grp[g].Wt = vw[g]->blk[i].fc1_w, op.grp[g].bias = vw[g]->blk[i].fc1_b;
+      for (int g = 0; g < NG; ++g) op.grp[g].Wt = vw[g]->blk[i].fc1_w, op.grp[g].bias = vw[g]->blk[i].fc1_b;
       if (fuse) {
         op.ln_stats = ln_stats_;
-        for (int g = 0; g < 3; ++g) op.grp[g].ln_c = vw[g]->blk[i].fc1_c;
+        for (int g = 0; g < NG; ++g) op.grp[g].ln_c = vw[g]->blk[i].fc1_c;
       }
       gemm(prec_, op, s);
     }
@@ -587,7 +607,7 @@ void Engine::run_vits(int B, cudaStream_t s) {
       op.N = EMB, op.K = 4 * EMB, op.A = hid, op.lda = 4 * EMB;
       op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
       grouped(op, SEQ, false);
-      for (int g = 0; g < 3; ++g)
+      for (int g = 0; g < NG; ++g)
         op.grp[g].Wt = vw[g]->blk[i].fc2_w, op.grp[g].bias = vw[g]->blk[i].fc2_b, op.grp[g].gamma = vw[g]->blk[i].g2;
       if (fuse && i < 23) op.ln_xb = xn, op.ln_stats_out = ln_stats_;
       gemm(prec_, op, s);
@@ -620,10 +640,13 @@ void Engine::forward_impl(const float* x, int B, float* canon, float* fov_deg, c
     ms.mode = 1, ms.S = 24, ms.steps = 1, ms.pad = 0, ms.patch_base = 0, ms.sb = 1, ms.sp = 1;
     ms.seq_off = 35 * B;
     layernorm_rows<T>(resid_, (T*)globm_, vit_image_.norm_w, vit_image_.norm_b, (long long)B * 24 * 24, ms, 1, s);
-    ms.seq_off = 36 * B;
-    layernorm_rows<T>(resid_, (T*)fovtok_, vit_fov_.norm_w, vit_fov_.norm_b, (long long)B * 24 * 24, ms, 1, s);
+    if (fov_mode_ == 2) {
+      ms.seq_off = 36 * B;
+      layernorm_rows<T>(resid_, (T*)fovtok_, vit_fov_.norm_w, vit_fov_.norm_b, (long long)B * 24 * 24, ms, 1, s);
+    }
   }
-  for (int f = 0; f < B; ++f) decode_frame<T>(f, canon + static_cast<size_t>(f) * IMG * IMG, fov_deg + f, s);
+  for (int f = 0; f < B; ++f)
+    decode_frame<T>(f, canon + static_cast<size_t>(f) * IMG * IMG, fov_deg ? fov_deg + f : nullptr, s);
   last_B_ = B;
 }
 
@@ -745,7 +768,8 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
   }
 
   // ---- FOV head (fov.py:56-82)
-  {
+  if (fov_mode_ == 0) return;  // use_fov_head=False (depth_pro.py:236-239: fov_deg stays None)
+  if (fov_mode_ == 2) {
     GemmOp op;  // Linear 1024 -> 128 on the 576 non-cls tokens (cls is dropped at fov.py:77)
     op.M = 576, op.N = 128, op.K = EMB, op.A = fovtok, op.lda = EMB, op.Wt = W("fov.encoder.1.weight");
     op.bias = F("fov.encoder.1.bias"), op.out = fovlin_, op.ldo = 128;
@@ -759,10 +783,17 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
     op.bias = F(name + ".bias"), op.act = ACT_RELU, op.res = addend, op.ldres = Cout, op.out = out, op.ldo = Cout;
     gemm(prec_, op, s);
   };
-  conv_s2(lowres_, 48, 256, "fov.downsample.0", 128, fovlin_, fov_a_);  // relu(conv) + tokens (fov.py:78-79)
-  conv_s2(fov_a_, 24, 128, "fov.head.0", 64, nullptr, fov_b_);
-  conv_s2(fov_b_, 12, 64, "fov.head.2", 32, nullptr, fov_c_);
-  fov_final<T>((const T*)fov_c_, F("fov.head.4.weight"), F("fov.head.4.bias"), fov_deg, 1, s);
+  if (fov_mode_ == 2) {
+    conv_s2(lowres_, 48, 256, "fov.downsample.0", 128, fovlin_, fov_a_);  // relu(conv) + tokens (fov.py:78-79)
+    conv_s2(fov_a_, 24, 128, "fov.head.0", 64, nullptr, fov_b_);
+    conv_s2(fov_b_, 12, 64, "fov.head.2", 32, nullptr, fov_c_);
+    fov_final<T>((const T*)fov_c_, F("fov.head.4.weight"), F("fov.head.4.bias"), fov_deg, 1, s);
+  } else {  // fov_encoder_preset=None: head(lowres_feature) with head = fov_head0 + fov_head (fov.py:55-56, 80-82)
+    conv_s2(lowres_, 48, 256, "fov.head.0", 128, nullptr, fov_a_);
+    conv_s2(fov_a_, 24, 128, "fov.head.2", 64, nullptr, fov_b_);
+    conv_s2(fov_b_, 12, 64, "fov.head.4", 32, nullptr, fov_c_);
+    fov_final<T>((const T*)fov_c_, F("fov.head.6.weight"), F("fov.head.6.bias"), fov_deg, 1, s);
+  }
 }
 
 void Engine::forward(const float* x, int B, float* canon, float* fov_deg, cudaStream_t s) {
@@ -774,13 +805,15 @@ void Engine::forward(const float* x, int B, float* canon, float* fov_deg, cudaSt
 }
 
 void Engine::infer(const void* img, int B, int H, int W, int src_fmt, const float* f_px_host, float* depth,
-                   float* f_px_out, cudaStream_t s) {
+                   float* f_px_out, int interp, cudaStream_t s) {
   DP_CHECK(finalized_, "dp_engine_finalize has not been called");
   DP_CHECK(B >= 1 && B <= max_batch_, "batch exceeds max_batch");
+  DP_CHECK(fov_mode_ != 0 || f_px_host != nullptr,
+           "this model has no FOV head (use_fov_head=False): infer needs f_px (the reference fails on fov_deg=None here)");
   DP_CUDA(cudaSetDevice(device_));
   const float* x = xbuf_;
   if (src_fmt == 0 && H == IMG && W == IMG) x = reinterpret_cast<const float*>(img);  // already at network resolution
-  else preprocess(img, B, H, W, src_fmt, xbuf_, s);
+  else preprocess(img, B, H, W, src_fmt, xbuf_, interp, s);
   forward(x, B, canon_, fov_, s);
   const float* fin = nullptr;
   if (f_px_host) {
@@ -788,7 +821,7 @@ void Engine::infer(const void* img, int B, int H, int W, int src_fmt, const floa
     fin = fpx_in_;
   }
   compute_fpx(fov_, fin, W, f_px_out ? f_px_out : fpx_, B, s);
-  depth_epilogue(canon_, f_px_out ? f_px_out : fpx_, B, H, W, depth, s);
+  depth_epilogue(canon_, f_px_out ? f_px_out : fpx_, B, H, W, depth, interp, s);
 }
 
 void Engine::infer_host(const void* img_host, int B, int H, int W, int src_fmt, const float* f_px_host, float* depth_host,
@@ -808,7 +841,7 @@ void Engine::infer_host(const void* img_host, int B, int H, int W, int src_fmt, 
   }
   cudaStream_t s = host_stream_;
   DP_CUDA(cudaMemcpyAsync(himg_, img_host, in_bytes, cudaMemcpyHostToDevice, s));
-  infer(himg_, B, H, W, src_fmt, f_px_host, hdepth_, fpx_, s);
+  infer(himg_, B, H, W, src_fmt, f_px_host, hdepth_, fpx_, INTERP_BILINEAR, s);
   DP_CUDA(cudaMemcpyAsync(depth_host, hdepth_, out_bytes, cudaMemcpyDeviceToHost, s));
   if (f_px_out_host) DP_CUDA(cudaMemcpyAsync(f_px_out_host, fpx_, B * 4, cudaMemcpyDeviceToHost, s));
   DP_CUDA(cudaStreamSynchronize(s));
@@ -848,10 +881,11 @@ void Engine::ground_grid_adjust(float* xyz, int64_t n, int grid_size, double per
                          reinterpret_cast<unsigned long long*>(counters), s);
 }
 
-void Engine::colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, cudaStream_t s) {
+void Engine::colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, float min_depth, float max_depth,
+                      cudaStream_t s) {
   DP_CUDA(cudaSetDevice(device_));
-  if (!colorize_mm_) colorize_mm_ = (float*)alloc(64);
-  dp::colorize(depth, H, W, lut, out, colorize_mm_, s);
+  if (!colorize_mm_) colorize_mm_ = (float*)alloc(colorize_scratch_bytes());
+  dp::colorize(depth, H, W, lut, out, colorize_mm_, min_depth, max_depth, s);
 }
 
 // ============================================================================ taps
@@ -1117,7 +1151,7 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   } else if (kind == 6) {  // uint8 HWC (M x N) -> fused transform + bilinear resize -> fp32 3x1536^2
     uint8_t* src = (uint8_t*)B((size_t)M * N * 3);
     float* x = (float*)B((size_t)3 * IMG * IMG * 4);
-    run = [&, src, x] { resize_to_1536(src, 1, 1, M, N, x, s); };
+    run = [&, src, x] { resize_to_1536(src, 1, 1, M, N, x, INTERP_BILINEAR, s); };
   } else if (kind == 7) {  // pyramid + 35-patch split + 16x16 im2col, fp32 frame -> bf16 A operands
     float* x = (float*)B((size_t)3 * IMG * IMG * 4);
     bf16* a35 = (bf16*)B((size_t)35 * 576 * 768 * 2);
@@ -1135,7 +1169,7 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
     const float fpx = 1000.f;
     DP_CUDA(cudaMemcpy(f, &fpx, 4, cudaMemcpyHostToDevice));
     if (kind == 8) {
-      run = [&, canon, f, depth] { depth_epilogue(canon, f, 1, M, N, depth, s); };
+      run = [&, canon, f, depth] { depth_epilogue(canon, f, 1, M, N, depth, INTERP_BILINEAR, s); };
     } else if (kind == 9) {
       uint8_t* rgb = (uint8_t*)B((size_t)M * N * 3);
       float* xyz = (float*)B((size_t)M * N * 12);
@@ -1146,8 +1180,8 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
     } else {
       uint8_t* lut = (uint8_t*)B(768);
       uint8_t* out = (uint8_t*)B((size_t)M * N * 3);
-      float* mm = (float*)B(8);
-      run = [&, depth, lut, out, mm] { dp::colorize(depth, M, N, lut, out, mm, s); };
+      float* mm = (float*)B(colorize_scratch_bytes());
+      run = [&, depth, lut, out, mm] { dp::colorize(depth, M, N, lut, out, mm, NAN, NAN, s); };
     }
   } else {
     DP_CHECK(false, "kernel_bench: unknown kind");

@@ -29,24 +29,28 @@ struct Packed {
 
 class Engine {
  public:
-  Engine(int device, int prec, int max_batch);
+  // fov_mode (depth_pro.py:100-108, fov.py:29-55): 0 = use_fov_head=False (no FOV network: forward yields no fov_deg and
+  // infer needs a caller-supplied f_px), 1 = FOV head without its own encoder (fov_encoder_preset=None: four convs on the
+  // low-resolution decoder feature), 2 = the default (ViT-L fov encoder + Linear + downsample + head)
+  Engine(int device, int prec, int max_batch, int fov_mode = 2);
   ~Engine();
 
   void set_weight(const std::string& name, const void* data, const int64_t* shape, int ndim, bool on_device);
   int missing_weights() const;
   void finalize();
 
-  void preprocess(const void* img, int B, int H, int W, int src_fmt, float* x, cudaStream_t s);
+  void preprocess(const void* img, int B, int H, int W, int src_fmt, float* x, int interp, cudaStream_t s);
   void split(const float* x, int B, float* patches, cudaStream_t s);
   void merge(const float* tokens, int B, int steps, int padding, int C, float* merged, cudaStream_t s);
   void forward(const float* x, int B, float* canon, float* fov_deg, cudaStream_t s);
   void infer(const void* img, int B, int H, int W, int src_fmt, const float* f_px_host, float* depth, float* f_px_out,
-             cudaStream_t s);
+             int interp, cudaStream_t s);
   void infer_host(const void* img_host, int B, int H, int W, int src_fmt, const float* f_px_host, float* depth_host,
                   float* f_px_out_host);
   void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float* f_px_dev, float* xyz, float* rgb_out,
                  uint8_t* valid_mask, int64_t* n_valid, cudaStream_t s);
-  void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, cudaStream_t s);
+  void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, float min_depth, float max_depth,
+                cudaStream_t s);
   // img_to_normalized_pointcloud.py:880-1118 on the GPU (ground.cu); `counters` = 6 x uint64 on the device or null
   void ground_normalize(float* xyz, int64_t n, const double* normal3, double d, uint64_t* counters, cudaStream_t s);
   void ground_grid_adjust(float* xyz, int64_t n, int grid_size, double percentile, uint64_t* counters, cudaStream_t s);
@@ -79,7 +83,11 @@ class Engine {
   size_t esz() const { return prec_ == BF16 ? 2 : 4; }
 
   int device_, prec_, max_batch_;
+  int fov_mode_ = 2;
+  int n_enc_ = 3;   // ViT encoders run as one grouped batch: patch, image (+ fov when fov_mode_ == 2)
+  int seqs_per_frame() const { return 35 + n_enc_ - 1; }
   bool finalized_ = false;
+  bool weights_changed_ = false;  // a set_weight since the last finalize
   bool attn_legacy_ = false;
   std::map<std::string, std::vector<int64_t>> manifest_;
   std::unordered_map<std::string, Packed> packed_;

@@ -2,6 +2,7 @@
 // kernel; paths are relative to the reference repo root.
 #include "kernels.cuh"
 
+#include <cmath>
 #include <cstdlib>
 
 namespace dp {
@@ -79,6 +80,94 @@ __global__ void __launch_bounds__(256) resize_kernel(const void* __restrict__ sr
     }
     dst[static_cast<size_t>(c) * IMG * IMG] = v;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// interpolation_mode = "bicubic" (depth_pro.py:247, 273-279, 288-291 pass the mode to F.interpolate): ATen's
+// upsample_bicubic2d with align_corners=False -- source index scale * (dst + 0.5) - 0.5 WITHOUT the clamp at 0 the
+// linear modes have, floor, lambda clamped to [0, 1], cubic-convolution coefficients with A = -0.75, the four taps per
+// axis clamped to the image, rows first.  ("bilinear" and "bicubic" are the only modes F.interpolate accepts together
+// with align_corners=False on 4-D input; every other mode raises ValueError in the reference and in the Python shim.)
+// ------------------------------------------------------------------------------------------
+struct CubicTaps {
+  int i[4];
+  float w[4];
+};
+__device__ __forceinline__ CubicTaps cubic_taps(float scale, int dst, int size) {
+  constexpr float A = -0.75f;
+  const float real = fmaf(scale, dst + 0.5f, -0.5f);
+  int idx = static_cast<int>(floorf(real));
+  idx = idx > size - 1 ? size - 1 : idx;
+  const float t = fminf(fmaxf(real - idx, 0.f), 1.f);
+  CubicTaps c;
+  const float x0 = t + 1.f, x3 = (1.f - t) + 1.f, x2 = 1.f - t;
+  c.w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c.w[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+  c.w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  c.w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int k = idx + j - 1;
+    c.i[j] = k < 0 ? 0 : (k > size - 1 ? size - 1 : k);
+  }
+  return c;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) resize_bicubic_kernel(const void* __restrict__ src, int H, int W, float* __restrict__ x) {
+  __shared__ float lut[256];
+  if (FMT == 1) {
+    const float t = __fdiv_rn(static_cast<float>(threadIdx.x), 255.f);
+    lut[threadIdx.x] = __fmul_rn(__fsub_rn(t, 0.5f), 2.f);
+    __syncthreads();
+  }
+  const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y, b = blockIdx.z;
+  const CubicTaps ty = cubic_taps(static_cast<float>(H) / IMG, oy, H), tx = cubic_taps(static_cast<float>(W) / IMG, ox, W);
+  float* dst = x + (static_cast<size_t>(b) * 3 * IMG + oy) * IMG + ox;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float row = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float p;
+        if (FMT == 1) {
+          const uint8_t* im = reinterpret_cast<const uint8_t*>(src) + static_cast<size_t>(b) * H * W * 3 + c;
+          p = lut[im[(static_cast<size_t>(ty.i[j]) * W + tx.i[i]) * 3]];
+        } else {
+          const float* im = reinterpret_cast<const float*>(src) + (static_cast<size_t>(b) * 3 + c) * H * W;
+          p = im[static_cast<size_t>(ty.i[j]) * W + tx.i[i]];
+        }
+        row = i == 0 ? __fmul_rn(tx.w[0], p) : __fadd_rn(row, __fmul_rn(tx.w[i], p));
+      }
+      acc = j == 0 ? __fmul_rn(ty.w[0], row) : __fadd_rn(acc, __fmul_rn(ty.w[j], row));
+    }
+    dst[static_cast<size_t>(c) * IMG * IMG] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) depth_epilogue_bicubic_kernel(const float* __restrict__ canon,
+                                                                     const float* __restrict__ f_px, int H, int W,
+                                                                     float* __restrict__ depth) {
+  const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y, b = blockIdx.z;
+  if (ox >= W) return;
+  const float scale = static_cast<float>(W) / f_px[b];
+  const float* src = canon + static_cast<size_t>(b) * IMG * IMG;
+  const CubicTaps ty = cubic_taps(static_cast<float>(IMG) / H, oy, IMG), tx = cubic_taps(static_cast<float>(IMG) / W, ox, IMG);
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float row = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float p = src[ty.i[j] * IMG + tx.i[i]] * scale;
+      row = i == 0 ? __fmul_rn(tx.w[0], p) : __fadd_rn(row, __fmul_rn(tx.w[i], p));
+    }
+    acc = j == 0 ? __fmul_rn(ty.w[0], row) : __fadd_rn(acc, __fmul_rn(ty.w[j], row));
+  }
+  depth[(static_cast<size_t>(b) * H + oy) * W + ox] = 1.0f / fminf(fmaxf(acc, 1e-4f), 1e4f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -621,11 +710,11 @@ __device__ __forceinline__ unsigned f2ord(float f) {
 __device__ __forceinline__ float ord2f(unsigned o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
-__global__ void minmax_init_kernel(unsigned* mm) {
-  mm[0] = 0xffffffffu;
-  mm[1] = 0u;
-}
+// Pass 1 of 2: every block leaves ITS nan-min / nan-max (order-preserving keys) in mm[2 * block], no atomics and no
+// initialisation launch; pass 2 (colorize_kernel) reduces the MINMAX_BLOCKS pairs in its prologue.
+constexpr int MINMAX_BLOCKS = 592;  // 148 SMs x 4
 __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ d, long long n, unsigned* mm) {
+  __shared__ unsigned slo[8], shi[8];
   unsigned lo = 0xffffffffu, hi = 0u;
   auto take = [&](float v) {
     if (!isnan(v)) {
@@ -646,23 +735,44 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ d
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&mm[0], lo);
-    atomicMax(&mm[1], hi);
+  if ((threadIdx.x & 31) == 0) slo[threadIdx.x >> 5] = lo, shi[threadIdx.x >> 5] = hi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) lo = min(lo, slo[w]), hi = max(hi, shi[w]);
+    mm[2 * blockIdx.x] = lo, mm[2 * blockIdx.x + 1] = hi;
   }
 }
 // one thread = 4 consecutive pixels: one 16-byte load, 12 bytes (three 32-bit words) or four uint16 out
+// `lo_fix` / `hi_fix`: caller-supplied min_depth / max_depth (generate_depth_maps.py:15-31), NaN = take the image's own.
 __global__ void __launch_bounds__(256) colorize_kernel(const float* __restrict__ d, long long n,
                                                        const unsigned* __restrict__ mm, const uint8_t* __restrict__ lut,
-                                                       void* __restrict__ out, int vec) {
+                                                       void* __restrict__ out, int vec, float lo_fix, float hi_fix) {
   __shared__ uint8_t slut[768];
-  if (lut) {
+  __shared__ unsigned slo[8], shi[8];
+  __shared__ float s_lo, s_hi;
+  if (lut)
     for (int i = threadIdx.x; i < 768; i += 256) slut[i] = lut[i];
+  {
+    unsigned lo = 0xffffffffu, hi = 0u;
+    if (mm)
+      for (int i = threadIdx.x; i < MINMAX_BLOCKS; i += 256) lo = min(lo, mm[2 * i]), hi = max(hi, mm[2 * i + 1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) slo[threadIdx.x >> 5] = lo, shi[threadIdx.x >> 5] = hi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) lo = min(lo, slo[w]), hi = max(hi, shi[w]);
+      s_lo = isnan(lo_fix) ? ord2f(lo) : lo_fix;
+      s_hi = isnan(hi_fix) ? ord2f(hi) : hi_fix;
+    }
     __syncthreads();
   }
   const long long i0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4;
   if (i0 >= n) return;
-  const float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
+  const float lo = s_lo, hi = s_hi;
   const float span = __fsub_rn(hi, lo);
   const int cnt = n - i0 < 4 ? static_cast<int>(n - i0) : 4;
   float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -818,11 +928,16 @@ void compose_head(const float* w1, const float* b1, const float* w2, const float
   DP_LAUNCH_CHECK();
 }
 
-void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x, cudaStream_t s) {
+void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x, int interp, cudaStream_t s) {
   static_assert(IMG % 256 == 0, "one block = 256 pixels of a row");
   const dim3 grid(IMG / 256, IMG, B);
-  if (src_fmt == 1) resize_kernel<1><<<grid, 256, 0, s>>>(src, H, W, x);
-  else resize_kernel<0><<<grid, 256, 0, s>>>(src, H, W, x);
+  if (interp == INTERP_BICUBIC && !(H == IMG && W == IMG)) {
+    if (src_fmt == 1) resize_bicubic_kernel<1><<<grid, 256, 0, s>>>(src, H, W, x);
+    else resize_bicubic_kernel<0><<<grid, 256, 0, s>>>(src, H, W, x);
+  } else {
+    if (src_fmt == 1) resize_kernel<1><<<grid, 256, 0, s>>>(src, H, W, x);
+    else resize_kernel<0><<<grid, 256, 0, s>>>(src, H, W, x);
+  }
   DP_LAUNCH_CHECK();
 }
 
@@ -943,14 +1058,16 @@ void hbm_v2_set(int on) { g_hbm_v2 = on != 0; }
 static bool hbm_v2() {
   if (g_hbm_v2 < 0) {
     const char* e = getenv("DEPTHPRO_HBM_V2");
-    g_hbm_v2 = e ? (atoi(e) != 0) : 0;
+    g_hbm_v2 = e ? (atoi(e) != 0) : 1;  // default since round 2: bit-identical to v1 on B200 (test_depth_epilogue_v2_is_bit_identical)
   }
   return g_hbm_v2 != 0;
 }
 
-void depth_epilogue(const float* canon, const float* f_px, int B, int H, int W, float* depth, cudaStream_t s) {
+void depth_epilogue(const float* canon, const float* f_px, int B, int H, int W, float* depth, int interp, cudaStream_t s) {
   DP_CHECK(H <= 65535 && B <= 65535, "depth epilogue: image too tall");
-  if (hbm_v2()) depth_epilogue_kernel_v2<<<dim3((W + 1023) / 1024, H, B), 256, 0, s>>>(canon, f_px, H, W, depth);
+  if (interp == INTERP_BICUBIC && !(H == IMG && W == IMG))
+    depth_epilogue_bicubic_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, s>>>(canon, f_px, H, W, depth);
+  else if (hbm_v2()) depth_epilogue_kernel_v2<<<dim3((W + 1023) / 1024, H, B), 256, 0, s>>>(canon, f_px, H, W, depth);
   else depth_epilogue_kernel<<<dim3((W + 255) / 256, H, B), 256, 0, s>>>(canon, f_px, H, W, depth);
   DP_LAUNCH_CHECK();
 }
@@ -975,16 +1092,20 @@ void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float
   DP_LAUNCH_CHECK();
 }
 
-void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, float* minmax, cudaStream_t s) {
+size_t colorize_scratch_bytes() { return MINMAX_BLOCKS * 2 * sizeof(unsigned); }
+void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, float* minmax, float min_depth,
+              float max_depth, cudaStream_t s) {
   const long long n = static_cast<long long>(H) * W;
   unsigned* mm = reinterpret_cast<unsigned*>(minmax);
-  minmax_init_kernel<<<1, 1, 0, s>>>(mm);
-  DP_LAUNCH_CHECK();
-  minmax_kernel<<<592, 256, 0, s>>>(depth, n, mm);
-  DP_LAUNCH_CHECK();
+  const bool need_scan = std::isnan(min_depth) || std::isnan(max_depth);   // both given: no reduction pass at all
+  if (need_scan) {
+    minmax_kernel<<<MINMAX_BLOCKS, 256, 0, s>>>(depth, n, mm);
+    DP_LAUNCH_CHECK();
+  }
   // 4 pixels per thread; the packed 32-bit stores need 16-byte aligned buffers (4 pixels = 12 output bytes)
   const int vec = reinterpret_cast<uintptr_t>(depth) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0;
-  colorize_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(depth, n, mm, lut, out, vec);
+  colorize_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(depth, n, need_scan ? mm : nullptr, lut, out, vec, min_depth,
+                                                                max_depth);
   DP_LAUNCH_CHECK();
 }
 

@@ -8,7 +8,9 @@ namespace dp {
 
 // ---- preprocessing ------------------------------------------------------------------
 // src (u8 HWC or f32 CHW, B images of HxW) -> x (B,3,1536,1536) f32, bilinear align_corners=False.
-void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x, cudaStream_t s);
+// `interp`: INTERP_BILINEAR or INTERP_BICUBIC (the two modes F.interpolate accepts with align_corners=False).
+enum { INTERP_BILINEAR = 0, INTERP_BICUBIC = 1 };
+void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x, int interp, cudaStream_t s);
 
 // x (B,3,1536,1536) f32 -> patch-embed im2col rows.  Frame-major order: row =
 // ((b*35 + patch)*576 + ty*24 + tx), col = c*256 + ky*16 + kx.  patch 0..24 = 5x5 windows of the
@@ -79,14 +81,17 @@ void ln_apply_from_stats(const bf16* xb, const float* stats, float* y, long long
 // f_px[b] = f_px_in ? f_px_in[b] : 0.5*W / tan(0.5*deg2rad(fov_deg[b]))   (depth_pro.py:282-283)
 void compute_fpx(const float* fov_deg, const float* f_px_in, int W, float* f_px, int B, cudaStream_t s);
 // depth[b,y,x] = 1 / clamp(resize(canon * (W / f_px[b]))[y,x], 1e-4, 1e4)    (depth_pro.py:285-293)
-void depth_epilogue(const float* canon, const float* f_px, int B, int H, int W, float* depth, cudaStream_t s);
+void depth_epilogue(const float* canon, const float* f_px, int B, int H, int W, float* depth, int interp, cudaStream_t s);
 void hbm_v2_set(int on);  // A/B switch of the opt-in second-generation HBM kernels (DEPTHPRO_HBM_V2)
 
 // ---- video add-on ---------------------------------------------------------------------------
 void unproject(const float* depth, const uint8_t* rgb, int H, int W, const float* f_px, float* xyz,
                float* rgb_out, uint8_t* valid_mask, int64_t* n_valid, int* scratch, cudaStream_t s);
 size_t unproject_scratch_ints(int H, int W);
-void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, float* minmax, cudaStream_t s);
+// `minmax`: >= colorize_scratch_bytes() of device scratch; min_depth / max_depth: NaN = the image's own nan-min / nan-max
+size_t colorize_scratch_bytes();
+void colorize(const float* depth, int H, int W, const uint8_t* lut, void* out, float* minmax, float min_depth,
+              float max_depth, cudaStream_t s);
 
 // ---- ground normalisation of a point cloud (ground.cu; img_to_normalized_pointcloud.py:880-1118) -------
 // xyz float32 (n,3) in place; `scratch` >= ground_scratch_bytes(n, grid_size) bytes; `counters` (device, 6 x

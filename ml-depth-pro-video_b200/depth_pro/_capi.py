@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libdepthpro_b200.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
 SRC_F32_CHW, SRC_U8_HWC = 0, 1
+FOV_NONE, FOV_HEAD_ONLY, FOV_ENCODER = 0, 1, 2
+INTERP = {"bilinear": 0, "bicubic": 1}
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
@@ -23,18 +25,22 @@ SIGNATURES = {
     "dp_last_error": (C.c_char_p, []),
     "dp_version": (_i, []),
     "dp_engine_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),
+    "dp_engine_create_ex": (_i, [_i, _i, _i, _i, C.POINTER(_vp)]),
     "dp_engine_destroy": (_i, [_vp]),
     "dp_engine_set_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _i]),
     "dp_engine_missing_weights": (_i, [_vp]),
     "dp_engine_finalize": (_i, [_vp]),
     "dp_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "dp_preprocess_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "dp_split": (_i, [_vp, _vp, _i, _vp, _vp]),
     "dp_merge": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "dp_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "dp_infer": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dp_infer_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dp_infer_host": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dp_unproject": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dp_colorize": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "dp_colorize_range": (_i, [_vp, _vp, _i, _i, _vp, _vp, C.c_float, C.c_float, _vp]),
     "dp_ground_normalize": (_i, [_vp, _vp, _i64, C.POINTER(C.c_double), C.c_double, _vp, _vp]),
     "dp_ground_grid_adjust": (_i, [_vp, _vp, _i64, _i, C.c_double, _vp, _vp]),
     "dp_tap": (_i, [_vp, C.c_char_p, _vp, _i64, C.POINTER(_i64), _vp]),

@@ -70,7 +70,11 @@ def _precision_code(precision: torch.dtype) -> int:
 class DepthPro(nn.Module):
     """Depth Pro network backed by the B200 engine."""
 
-    def __init__(self, device: torch.device, precision: torch.dtype = torch.float32, max_batch: int = 1):
+    def __init__(self, device: torch.device, precision: torch.dtype = torch.float32, max_batch: int = 1,
+                 use_fov_head: bool = True, fov_encoder: bool = True):
+        """``use_fov_head`` / ``fov_encoder`` mirror the reference constructor (depth_pro.py:153-211): without the head
+        ``forward`` returns ``fov_deg=None`` and ``infer`` needs ``f_px``; ``fov_encoder=False`` is the head without
+        its own ViT (``DepthProConfig.fov_encoder_preset=None``)."""
         super().__init__()
         device = torch.device(device)
         if device.type != "cuda":
@@ -84,7 +88,8 @@ class DepthPro(nn.Module):
         self._max_batch = int(max_batch)
         self._engine = None
         self._dirty = True
-        for name, shape in weights.manifest().items():
+        self._fov = None if not use_fov_head else ("encoder" if fov_encoder else "head")
+        for name, shape in weights.manifest(self._fov).items():
             node: nn.Module = self
             parts = name.split(".")
             for p in parts[:-1]:
@@ -99,6 +104,19 @@ class DepthPro(nn.Module):
     # ------------------------------------------------------------------ weights / engine
     def _mark_dirty(self):
         self._dirty = True
+
+    def refresh_weights(self) -> "DepthPro":
+        """Re-upload every parameter to the engine before the next call.  ``load_state_dict``, ``init_weights`` and
+        module-level conversions (``.to()``, ``.half()``, ``.float()``) are tracked automatically; IN-PLACE edits of a
+        parameter (``p.data.copy_(...)``, ``p.mul_(...)``) are not -- call this after them, otherwise the engine keeps
+        computing with its packed copy of the old values."""
+        self._dirty = True
+        return self
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._dirty = True
+        return out
 
     def init_weights(self, recipe: str = "stress", seed: int = 1234) -> "DepthPro":
         """Seeded random init (no checkpoint offline): 'stress' = recipe B, 'reference' = the
@@ -118,7 +136,9 @@ class DepthPro(nn.Module):
         if self._engine is None:
             self._max_batch = max(self._max_batch, batch)
             h = ctypes.c_void_p()
-            _capi.check(lib.dp_engine_create(self._device.index, self._prec_code, self._max_batch, ctypes.byref(h)))
+            fov_mode = {None: _capi.FOV_NONE, "head": _capi.FOV_HEAD_ONLY, "encoder": _capi.FOV_ENCODER}[self._fov]
+            _capi.check(lib.dp_engine_create_ex(self._device.index, self._prec_code, self._max_batch, fov_mode,
+                                                ctypes.byref(h)))
             self._engine = h
             self._dirty = True
         if self._dirty:
@@ -159,10 +179,10 @@ class DepthPro(nn.Module):
         B = x.shape[0]
         lib = self._ensure_engine(B)
         canon = torch.empty((B, 1, IMG_SIZE, IMG_SIZE), dtype=torch.float32, device=self._device)
-        fov = torch.empty((B, 1, 1, 1), dtype=torch.float32, device=self._device)
+        fov = torch.empty((B, 1, 1, 1), dtype=torch.float32, device=self._device) if self._fov is not None else None
         with torch.cuda.device(self._device):
-            _capi.check(lib.dp_forward(self._engine, x.data_ptr(), B, canon.data_ptr(), fov.data_ptr(), self._stream()))
-        return canon, fov
+            _capi.check(lib.dp_forward(self._engine, x.data_ptr(), B, canon.data_ptr(), _capi.ptr(fov), self._stream()))
+        return canon, fov   # fov is None without the FOV head, like depth_pro.py:236-241
 
     @torch.no_grad()
     def infer(self, x: torch.Tensor, f_px: Optional[Union[float, torch.Tensor]] = None,
@@ -173,8 +193,14 @@ class DepthPro(nn.Module):
         uint8 HWC / BHWC tensor or ndarray straight from ``load_rgb`` is accepted, in which case
         ToTensor + Normalize are fused into the resize kernel.
         """
-        if interpolation_mode != "bilinear":
-            raise NotImplementedError("the B200 engine implements interpolation_mode='bilinear' only")
+        if interpolation_mode not in _capi.INTERP:
+            # F.interpolate(..., mode=m, align_corners=False) on a 4-D tensor accepts "bilinear" and "bicubic" only; the
+            # reference raises this ValueError for every other mode ("nearest", "area", "nearest-exact", ...)
+            raise ValueError("align_corners option can only be set with the interpolating modes: "
+                             "linear | bilinear | bicubic | trilinear")
+        if f_px is None and self._fov is None:
+            # depth_pro.py:282-283 dereferences fov_deg=None here
+            raise AttributeError("'NoneType' object has no attribute 'to' (this model has no FOV head: pass f_px)")
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(np.ascontiguousarray(x))
         u8 = x.dtype == torch.uint8
@@ -201,9 +227,9 @@ class DepthPro(nn.Module):
             assert f_t.numel() == B, "f_px must be a scalar or one value per image"
             f_host = f_t.contiguous()
         with torch.cuda.device(self._device):
-            _capi.check(lib.dp_infer(self._engine, x.data_ptr(), B, H, W, fmt,
-                                     None if f_host is None else f_host.data_ptr(),
-                                     depth.data_ptr(), f_out.data_ptr(), self._stream()))
+            _capi.check(lib.dp_infer_ex(self._engine, x.data_ptr(), B, H, W, fmt, _capi.INTERP[interpolation_mode],
+                                        None if f_host is None else f_host.data_ptr(),
+                                        depth.data_ptr(), f_out.data_ptr(), self._stream()))
         if f_px is None:
             focal = f_out.squeeze()
         else:
@@ -246,13 +272,15 @@ def create_model_and_transforms(
 
     for preset in (config.patch_encoder_preset, config.image_encoder_preset):
         create_backbone_model(preset)
-    if not (config.use_fov_head and config.fov_encoder_preset is not None):
-        raise NotImplementedError("the B200 engine implements the default config (FOV head with its own encoder)")
-    create_backbone_model(config.fov_encoder_preset)
+    fov_encoder = config.use_fov_head and config.fov_encoder_preset is not None     # depth_pro.py:100-102
+    if fov_encoder:
+        create_backbone_model(config.fov_encoder_preset)
     if config.decoder_features != 256:
+        # every tensor-core tile shape, the composed head and the workspace plan are built for dim_decoder = 256 (the only
+        # value a published checkpoint has); rejected loudly rather than run on a silent slow path
         raise NotImplementedError("the B200 engine implements decoder_features=256")
 
-    model = DepthPro(device=device, precision=precision)
+    model = DepthPro(device=device, precision=precision, use_fov_head=config.use_fov_head, fov_encoder=fov_encoder)
     transform = Compose([
         ToTensor(),
         Lambda(lambda x: x.to(device)),
@@ -271,3 +299,7 @@ def create_model_and_transforms(
     else:
         model.init_weights("reference", seed=0)
     return model, transform
+
+
+__all__ = ["DepthPro", "DepthProConfig", "DEFAULT_MONODEPTH_CONFIG_DICT", "create_model_and_transforms",
+           "create_backbone_model"]

@@ -80,16 +80,22 @@ def depth_to_3d(model: DepthPro, depth: torch.Tensor, focallength_px, width: int
     return xyz[:k], mask.bool(), (cols[:k] if cols is not None else None)
 
 
-def colorize_depth(model: DepthPro, depth: torch.Tensor, cmap: str = "turbo", lut: Optional[torch.Tensor] = None
+def colorize_depth(model: DepthPro, depth: torch.Tensor, min_depth: Optional[float] = None,
+                   max_depth: Optional[float] = None, cmap: str = "turbo", lut: Optional[torch.Tensor] = None
                    ) -> torch.Tensor:
-    """GPU ``colorize_depth`` (generate_depth_maps.py:15-44): (H,W) float32 -> (H,W,3) uint8 RGB."""
+    """GPU ``colorize_depth(depth, min_depth, max_depth, cmap)`` (generate_depth_maps.py:15-44): (H,W) float32 ->
+    (H,W,3) uint8 RGB.  ``min_depth`` / ``max_depth`` default to the image's nanmin / nanmax like the reference; values
+    outside the range are clipped; NaN pixels come out black (matplotlib's "bad" colour)."""
     H, W = depth.shape
     if lut is None:
         lut = torch.from_numpy(colormap_lut(cmap)).to(depth.device)
     out = torch.empty((H, W, 3), dtype=torch.uint8, device=depth.device)
     lib = model._ensure_engine(1)
     depth = depth.contiguous()
-    _capi.check(lib.dp_colorize(model._engine, depth.data_ptr(), H, W, lut.data_ptr(), out.data_ptr(), model._stream()))
+    nan = float("nan")
+    _capi.check(lib.dp_colorize_range(model._engine, depth.data_ptr(), H, W, lut.data_ptr(), out.data_ptr(),
+                                      nan if min_depth is None else float(min_depth),
+                                      nan if max_depth is None else float(max_depth), model._stream()))
     return out
 
 

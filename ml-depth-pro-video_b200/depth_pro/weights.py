@@ -60,8 +60,12 @@ def _vit(prefix: str) -> Iterator[Tuple[str, Tuple[int, ...]]]:
     yield prefix + "norm.bias", (EMBED,)
 
 
-def manifest() -> "OrderedDict[str, Tuple[int, ...]]":
-    """name -> shape for all 1119 tensors, in the reference's state_dict order."""
+def manifest(fov: str = "encoder") -> "OrderedDict[str, Tuple[int, ...]]":
+    """name -> shape in the reference's state_dict order: all 1119 tensors of the default configuration
+    (``fov="encoder"``), or of ``fov="head"`` (``fov_encoder_preset=None``: FOV head without its own ViT, fov.py:55-56)
+    / ``fov=None`` (``use_fov_head=False``: no ``fov.*`` tensors, depth_pro.py:100-108)."""
+    if fov not in ("encoder", "head", None):
+        raise ValueError(f"fov must be 'encoder', 'head' or None, got {fov!r}")
     m: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
     for k, s in _vit("encoder.patch_encoder."):
         m[k] = s
@@ -103,6 +107,15 @@ def manifest() -> "OrderedDict[str, Tuple[int, ...]]":
     m["head.4.weight"] = (1, 32, 1, 1)
     m["head.4.bias"] = (1,)
     # fov.py:29-55
+    if fov is None:
+        return m
+    if fov == "head":
+        for i, (co, ci) in zip((0, 2, 4), ((128, 256), (64, 128), (32, 64))):
+            m[f"fov.head.{i}.weight"] = (co, ci, 3, 3)
+            m[f"fov.head.{i}.bias"] = (co,)
+        m["fov.head.6.weight"] = (1, 32, 6, 6)
+        m["fov.head.6.bias"] = (1,)
+        return m
     for k, s in _vit("fov.encoder.0."):
         m[k] = s
     m["fov.encoder.1.weight"] = (128, EMBED)
@@ -148,7 +161,7 @@ def stress_tensor(name: str, shape: Tuple[int, ...], seed: int) -> torch.Tensor:
     leaf = name.rsplit(".", 1)[-1]
     if name == "head.4.bias":
         return torch.full(shape, 2.0)
-    if name == "fov.head.4.bias":
+    if name in ("fov.head.4.bias", "fov.head.6.bias") and shape == (1,):   # the FOV head's last conv (6x6 -> 1)
         return torch.full(shape, 60.0)
     if name == "head.4.weight":
         return normal(0.25 / math.sqrt(32))
@@ -209,10 +222,10 @@ def _bias_fan_in(name: str) -> int:
     return s[1] * s[2] * s[3]
 
 
-def stress_init(seed: int = 1234) -> Dict[str, torch.Tensor]:
+def stress_init(seed: int = 1234, fov: str = "encoder") -> Dict[str, torch.Tensor]:
     """Full "recipe B" state_dict (fp32, CPU, ~3.8 GB)."""
-    return OrderedDict((k, stress_tensor(k, s, seed)) for k, s in manifest().items())
+    return OrderedDict((k, stress_tensor(k, s, seed)) for k, s in manifest(fov).items())
 
 
-def reference_like_init(seed: int = 0) -> Dict[str, torch.Tensor]:
-    return OrderedDict((k, reference_like_tensor(k, s, seed)) for k, s in manifest().items())
+def reference_like_init(seed: int = 0, fov: str = "encoder") -> Dict[str, torch.Tensor]:
+    return OrderedDict((k, reference_like_tensor(k, s, seed)) for k, s in manifest(fov).items())

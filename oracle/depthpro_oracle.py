@@ -237,8 +237,18 @@ def head_forward(sd, feat: torch.Tensor) -> torch.Tensor:
     return F.relu(F.conv2d(x, sd["head.4.weight"], sd["head.4.bias"]))
 
 
-def fov_forward(sd, x: torch.Tensor, lowres: torch.Tensor) -> torch.Tensor:
-    """fov.py:56-82."""
+def fov_forward(sd, x: torch.Tensor, lowres: torch.Tensor) -> Optional[torch.Tensor]:
+    """fov.py:56-82.  Three configurations, told apart by the state_dict keys like the reference's `hasattr` checks:
+    the default (own ViT encoder, fov.py:47-54), the head without encoder (`fov_encoder_preset=None`: `head =
+    fov_head0 + fov_head` applied to the low-resolution feature, fov.py:55-56, 80-82) and no FOV network at all
+    (`use_fov_head=False`, depth_pro.py:236-239: `fov_deg` stays None)."""
+    if not any(k.startswith("fov.") for k in sd):
+        return None
+    if "fov.encoder.0.cls_token" not in sd:
+        h = lowres
+        for i in (0, 2, 4):
+            h = F.relu(F.conv2d(h, sd[f"fov.head.{i}.weight"], sd[f"fov.head.{i}.bias"], stride=2, padding=1))
+        return F.conv2d(h, sd["fov.head.6.weight"], sd["fov.head.6.bias"])
     x = F.interpolate(x, size=None, scale_factor=0.25, mode="bilinear", align_corners=False)
     t, _ = vit_forward(sd, "fov.encoder.0.", x)
     t = F.linear(t, sd["fov.encoder.1.weight"], sd["fov.encoder.1.bias"])
@@ -266,14 +276,15 @@ def forward(sd, x: torch.Tensor, taps: Optional[dict] = None) -> Tuple[torch.Ten
 
 
 @torch.no_grad()
-def infer(sd, x: torch.Tensor, f_px=None, taps: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+def infer(sd, x: torch.Tensor, f_px=None, taps: Optional[dict] = None,
+          interpolation_mode: str = "bilinear") -> Dict[str, torch.Tensor]:
     """depth_pro.py:243-298."""
     if x.dim() == 3:
         x = x.unsqueeze(0)
     _, _, H, W = x.shape
     resize = H != IMG or W != IMG
     if resize:
-        x = F.interpolate(x, size=(IMG, IMG), mode="bilinear", align_corners=False)
+        x = F.interpolate(x, size=(IMG, IMG), mode=interpolation_mode, align_corners=False)
     canon, fov = forward(sd, x, taps)
     if f_px is None:
         f_px = 0.5 * W / torch.tan(0.5 * torch.deg2rad(fov.to(torch.float)))
@@ -282,7 +293,7 @@ def infer(sd, x: torch.Tensor, f_px=None, taps: Optional[dict] = None) -> Dict[s
     inv = canon * (W / f_px)
     f_px = f_px.squeeze()
     if resize:
-        inv = F.interpolate(inv, size=(H, W), mode="bilinear", align_corners=False)
+        inv = F.interpolate(inv, size=(H, W), mode=interpolation_mode, align_corners=False)
     depth = 1.0 / torch.clamp(inv, min=1e-4, max=1e4)
     return {"depth": depth.squeeze(), "focallength_px": f_px}
 
@@ -304,9 +315,10 @@ def depth_to_3d(depth_in, focallength_px, width, height):
     return np.column_stack((x, y, z)), valid
 
 
-def normalize_depth(depth: np.ndarray) -> np.ndarray:
-    """generate_depth_maps.py:28-35 — (d - nanmin) / (nanmax - nanmin), clipped to [0,1]."""
-    lo, hi = np.nanmin(depth), np.nanmax(depth)
+def normalize_depth(depth: np.ndarray, min_depth=None, max_depth=None) -> np.ndarray:
+    """generate_depth_maps.py:28-35 — (d - min) / (max - min), clipped to [0,1]; min / max default to nanmin / nanmax."""
+    lo = np.nanmin(depth) if min_depth is None else min_depth
+    hi = np.nanmax(depth) if max_depth is None else max_depth
     return np.clip((depth - lo) / (hi - lo), 0, 1)
 
 

@@ -52,6 +52,28 @@ def test_resize_u8_fused_transform():
     assert _ulp_err(got2, ref2) <= 2.0
 
 
+@pytest.mark.parametrize("H,W", [(1080, 1920), (2160, 3840), (384, 640), (1537, 1535), (5, 3), (1, 1)])
+def test_resize_bicubic(H, W):
+    """interpolation_mode="bicubic" (depth_pro.py:247, 273-279): ATen upsample_bicubic2d, align_corners=False.  The
+    cubic weights reach 1.27 in magnitude and four products are summed per axis -> 8 ulp of the operand range."""
+    g = torch.Generator().manual_seed(H * 7 + W)
+    x = torch.rand(1, 3, H, W, generator=g) * 2 - 1
+    ref = F.interpolate(x, size=(1536, 1536), mode="bicubic", align_corners=False)
+    got = torch.empty(1, 3, 1536, 1536, device=DEV)
+    _capi.check(lib().dp_preprocess_ex(engine(), x.to(DEV).data_ptr(), 1, H, W, _capi.SRC_F32_CHW, _capi.INTERP["bicubic"],
+                                       got.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    assert _ulp_err(got.cpu(), ref) <= 8.0
+    if (H, W) == (1080, 1920):       # and it is not the bilinear result
+        assert float((got.cpu() - F.interpolate(x, size=(1536, 1536), mode="bilinear", align_corners=False)).abs().max()) > 1e-2
+        frame = O.synthetic_frame_u8(3)
+        ref8 = F.interpolate(O.transform_u8(frame)[None], size=(1536, 1536), mode="bicubic", align_corners=False)
+        _capi.check(lib().dp_preprocess_ex(engine(), torch.from_numpy(frame).to(DEV).data_ptr(), 1, H, W, _capi.SRC_U8_HWC,
+                                           _capi.INTERP["bicubic"], got.data_ptr(), stream()))
+        torch.cuda.synchronize()
+        assert _ulp_err(got.cpu(), ref8) <= 8.0
+
+
 @pytest.mark.parametrize("B", [1, 2])
 def test_split_bit_exact(B, golden_dir):
     """pyramid + split + cat (encoder.py:151-188, 253-263): patches identical to the oracle's."""
@@ -242,3 +264,42 @@ def test_ground_edge_cases():
     # n = 0 is a no-op
     empty = torch.empty((0, 3), device=DEV)
     _capi.check(lib().dp_ground_grid_adjust(engine(), empty.data_ptr(), 0, 20, 5.0, None, stream()))
+
+
+def _kb(kind, M, N, K, iters=1):
+    ms = ctypes.c_float()
+    _capi.check(lib().dp_kernel_bench(engine(), kind, M, N, K, iters, ctypes.byref(ms)))
+    return ms.value
+
+
+@pytest.mark.parametrize("H,W", [(1536, 1536), (1080, 1920), (2160, 3840), (333, 2001), (7, 5), (1, 1), (1081, 1023)])
+def test_depth_epilogue_v2_is_bit_identical(H, W):
+    """The four-pixels-per-thread metric-depth epilogue (default since round 2) must reproduce the one-pixel-per-thread
+    round-1 kernel (DEPTHPRO_HBM_V2=0) bit for bit, at aligned, ragged and tiny output sizes.  Runs the whole bf16 frame
+    twice on the same input."""
+    import depth_pro
+
+    model = _epilogue_model()
+    g = torch.Generator(device=DEV).manual_seed(H * 10007 + W)
+    x = torch.rand(3, H, W, device=DEV, generator=g) * 2 - 1
+    try:
+        _kb(8 | 0x2000, 64, 64, 0)
+        a = model.infer(x)["depth"].clone()
+        _kb(8 | 0x1000, 64, 64, 0)
+        b = model.infer(x)["depth"].clone()
+    finally:
+        _kb(8 | 0x1000, 64, 64, 0)   # back to the default (v2)
+    assert a.shape == b.shape
+    assert torch.equal(a, b)
+
+
+_MODEL = None
+
+
+def _epilogue_model():
+    global _MODEL
+    if _MODEL is None:
+        import depth_pro
+
+        _MODEL = depth_pro.DepthPro(device=torch.device(DEV), precision=torch.bfloat16).init_weights("stress", 1234)
+    return _MODEL

@@ -298,6 +298,76 @@ def test_bf16_layernorm_fold_matches_standalone_layernorm(model_bf16, oracle_run
     del plain_model
 
 
+def test_interpolation_mode_bicubic(model_fp32, state_dict):
+    """VERDICT r1 missing #2: DepthPro.infer(interpolation_mode="bicubic") (depth_pro.py:247, 273-279, 288-291) against the
+    oracle in fp32, down- and up-sampling in one call (540x960 -> 1536^2 -> 540x960), tolerance of the fp32 mode."""
+    x = O.transform_u8(O.synthetic_frame_u8(2, 540, 960))
+    torch.set_num_threads(os.cpu_count())
+    ref = O.infer(state_dict, x, interpolation_mode="bicubic")
+    pred = model_fp32.infer(x.to(DEV), interpolation_mode="bicubic")
+    rel = _pix_rel(pred["depth"].cpu(), ref["depth"])
+    f_rel = abs(float(pred["focallength_px"]) - float(ref["focallength_px"])) / float(ref["focallength_px"])
+    print(f"fp32 bicubic 540x960: depth rel-err max {float(rel.max()):.3e}; f_px rel {f_rel:.3e}")
+    assert float(rel.max()) <= 1e-4 and f_rel <= 1e-4
+    bil = model_fp32.infer(x.to(DEV))["depth"].cpu()
+    assert float(_pix_rel(bil, ref["depth"]).max()) > 1e-3          # the mode really changes the result
+
+
+@pytest.mark.parametrize("fov", [None, "head"])
+def test_non_default_fov_configs(fov):
+    """VERDICT r1 missing #3: `use_fov_head=False` and `fov_encoder_preset=None` (depth_pro.py:100-108, 236-241;
+    fov.py:29-56) through create_model_and_transforms, against the oracle (whose conv-only head is pinned to the
+    reference's own FOVNetwork in tests/test_oracle.py)."""
+    import dataclasses
+
+    cfg = dataclasses.replace(depth_pro.depth_pro.DEFAULT_MONODEPTH_CONFIG_DICT, checkpoint_uri=None,
+                              use_fov_head=fov is not None, fov_encoder_preset=None)
+    model, _ = depth_pro.create_model_and_transforms(cfg, device=DEV, precision=torch.bfloat16)
+    sd = weights.stress_init(SEED, fov=fov)
+    assert set(model.state_dict()) == set(sd)
+    model.load_state_dict(sd, strict=True)
+    x = O.synthetic_image_1536(1)
+    torch.set_num_threads(os.cpu_count())
+    canon_ref, fov_ref = O.forward(sd, x[None])
+    canon, fov_deg = model.forward(x[None].to(DEV))
+    rel = _pix_rel(canon[0, 0].cpu(), canon_ref[0, 0]).float()
+    print(f"fov={fov}: canonical inverse depth abs-rel median {float(rel.median()):.3e} max {float(rel.max()):.3e}")
+    assert float(rel.median()) <= 5e-3 and float(rel.max()) <= 5e-2
+    if fov is None:
+        assert fov_deg is None and fov_ref is None                   # depth_pro.py:236-241
+        with pytest.raises(AttributeError):                          # depth_pro.py:282-283 on fov_deg=None
+            model.infer(x.to(DEV))
+    else:
+        assert fov_deg.shape == (1, 1, 1, 1)
+        assert abs(float(fov_deg) - float(fov_ref)) / abs(float(fov_ref)) <= 1e-2
+        est = model.infer(x.to(DEV))
+        ref = O.infer(sd, x)
+        assert abs(float(est["focallength_px"]) - float(ref["focallength_px"])) / float(ref["focallength_px"]) <= 1e-2
+    pred = model.infer(x.to(DEV), f_px=1500.0)                       # caller-supplied focal length works in every config
+    ref = O.infer(sd, x, f_px=1500.0)
+    r2 = _pix_rel(pred["depth"].cpu(), ref["depth"]).float()
+    assert float(r2.median()) <= 5e-3 and float(pred["focallength_px"]) == 1500.0
+    del model
+    torch.cuda.empty_cache()
+
+
+def test_weight_edits_reach_the_engine(state_dict):
+    """module-level conversions re-upload automatically, in-place edits need refresh_weights()."""
+    m = _model(state_dict, torch.bfloat16)
+    x = O.synthetic_image_1536(1)[:, :256, :256].contiguous().to(DEV)
+    a = m.infer(x)["depth"].clone()
+    with torch.no_grad():
+        m.head.get_parameter("4.bias").add_(0.5)
+    assert torch.equal(m.infer(x)["depth"], a)                       # documented: the packed copy is still in use
+    m.refresh_weights()
+    b = m.infer(x)["depth"].clone()
+    assert not torch.equal(b, a)
+    m.float()                                                        # nn.Module._apply marks the engine copy stale
+    assert m._dirty
+    assert torch.equal(m.infer(x)["depth"], b)
+    del m
+
+
 def test_batch_is_bit_identical(model_bf16):
     """Frames are independent units: a 2-frame batch must equal two single-frame calls bit for bit."""
     frames = np.stack([O.synthetic_frame_u8(i, 540, 960) for i in range(2)])
@@ -347,8 +417,11 @@ def test_infer_edge_shapes_and_argument_forms(model_bf16):
     far = model_bf16.infer(x, f_px=800.0)["depth"]
     ok = (one < 4e3) & (one > 1e-3)
     assert float(((far / one)[ok] - 2.0).abs().max()) < 1e-5
-    with pytest.raises(NotImplementedError):
-        model_bf16.infer(x, interpolation_mode="bicubic")
+    # interpolation_mode: F.interpolate(align_corners=False) accepts bilinear / bicubic only (reference: ValueError)
+    for bad in ("nearest", "area", "nearest-exact", "trilinear"):
+        with pytest.raises(ValueError):
+            model_bf16.infer(x, interpolation_mode=bad)
+    assert not torch.equal(model_bf16.infer(x, interpolation_mode="bicubic")["depth"], a)
     with pytest.raises(AssertionError):
         model_bf16.infer(torch.rand(4, 40, 56))               # not 3 channels
     with pytest.raises(AssertionError):

@@ -63,6 +63,22 @@ def test_colorize_and_u16(model):
     assert np.array_equal(u16, O.depth_to_u16(depth.cpu().numpy()))
 
 
+def test_colorize_with_explicit_range(model):
+    """colorize_depth(depth, min_depth, max_depth) (generate_depth_maps.py:15-35): either end may be given; values outside
+    are clipped; NaN stays black."""
+    g = torch.Generator(device=DEV).manual_seed(4)
+    depth = torch.rand(270, 481, device=DEV, generator=g) * 9 + 1
+    depth[5, 7] = float("nan")
+    lut = video.colormap_lut("turbo")
+    d = depth.cpu().numpy()
+    for lo, hi in ((2.0, 8.0), (None, 6.0), (3.0, None), (None, None)):
+        rgb = video.colorize_depth(model, depth, min_depth=lo, max_depth=hi).cpu().numpy()
+        norm = O.normalize_depth(d, lo, hi)
+        want = lut[np.minimum((np.nan_to_num(norm) * 256).astype(np.int64), 255)]
+        want[5, 7] = 0
+        assert np.array_equal(rgb, want), (lo, hi)
+
+
 def test_batch_generate_depth_maps(model, tmp_path):
     import cv2
 

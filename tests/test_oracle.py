@@ -123,3 +123,28 @@ def test_ground_normalisation_oracle_matches_reference_outputs(golden_dir):
     out = O.normalize_point_cloud_to_ground(far, np.array([0.0, 1.0, 0.0]), 0.0)
     assert np.array_equal(out, far)
     assert np.array_equal(O.grid_based_ground_adjustment(far, 20, 5), far)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not RL.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_fov_head_without_encoder_vs_live_reference():
+    """`fov_encoder_preset=None` (fov.py:55-56, 80-82): the oracle's conv-only FOV head against the reference's own
+    FOVNetwork(num_features=256, fov_encoder=None), same state_dict keys (fov.head.{0,2,4,6}), bit for bit."""
+    RL.load()
+    FOV = sys.modules["ref_depth_pro.network.fov"].FOVNetwork
+    net = FOV(num_features=256, fov_encoder=None).eval()
+    want = weights.manifest("head")
+    assert {"fov." + k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: s for k, s in want.items() if k.startswith("fov.")}
+    sd = {k: weights.stress_tensor(k, s, 3) for k, s in want.items() if k.startswith("fov.")}
+    net.load_state_dict({k[4:]: v for k, v in sd.items()}, strict=True)
+    g = torch.Generator().manual_seed(2)
+    lowres = torch.randn(2, 256, 48, 48, generator=g)
+    with torch.no_grad():
+        ref = net(torch.zeros(2, 3, 1536, 1536), lowres)
+    got = O.fov_forward(sd, torch.zeros(2, 3, 1536, 1536), lowres)
+    assert ref.shape == (2, 1, 1, 1) and torch.equal(ref, got)
+    assert O.fov_forward({"head.0.weight": torch.zeros(1)}, None, lowres) is None      # use_fov_head=False
+    # the three manifests: default 1119 tensors, head-only drops the fov ViT, none drops every fov.* key
+    assert len(weights.manifest()) == 1119
+    assert not any(k.startswith("fov.") for k in weights.manifest(None))
+    assert sum(k.startswith("fov.") for k in want) == 8
