@@ -23,6 +23,7 @@
 //                                 After the last block: O from TMEM, 1/l, bf16 store.
 // 296 stream slots x 2 units = 592 = 37 sequences x 16 heads: a frame's attention is perfectly balanced.
 // Register budget: the control warps drop to 40 registers, the softmax warps grow to 232 (setmaxnreg).
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 
@@ -552,10 +553,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 
 }  // namespace
 
-const CUtensorMap& get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                 const uint32_t* box);  // gemm_tc.cu
-const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
-                                    uint32_t box_rows);  // gemm_tc.cu
+CUtensorMap get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box);  // gemm_tc.cu (cached, thread-safe, returned by value)
+CUtensorMap get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                             uint32_t box_rows);  // gemm_tc.cu
 
 #ifdef ATTN_PROFILE
 void attn_prof_read(unsigned long long* host10, bool reset) {
@@ -596,7 +597,7 @@ static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int 
 
 // DEPTHPRO_ATTN_EXP selects a variant (list at the top of this file); DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams'
 // exp phases overlap freely (slower).
-static int g_expv = -1, g_pingpong = 1;
+static std::atomic<int> g_expv{-1}, g_pingpong{1};
 
 constexpr int ATTN_EXP_DEFAULT = 13;  // measured on B200 (profiles/r2_attention_variants.json)
 static bool variant_compiled(int v) { return v == 0 || v == 5 || v == 12 || v == 13; }
@@ -611,23 +612,23 @@ void attention_tc_set_variant(int expv, int pingpong) {
 }
 
 void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
-  static int sms = 0;
-  if (!sms) {
-    int dev;
+  static const int sms = [] {
+    int dev, v;
     DP_CUDA(cudaGetDevice(&dev));
-    DP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+    DP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    return v;
+  }();
   if (g_expv < 0) {  // first call and no explicit choice: the environment, else the default
     const char* e = getenv("DEPTHPRO_ATTN_EXP");
     const char* p = getenv("DEPTHPRO_ATTN_PINGPONG");
     attention_tc_set_variant(e && atoi(e) >= 0 ? atoi(e) : ATTN_EXP_DEFAULT, p ? atoi(p) : 1);
   }
   const int expv = g_expv, pingpong = g_pingpong;
-  const CUtensorMap& tm = get_tmap_2d_bf16(qkv, LDQ, static_cast<uint64_t>(nseq) * SEQ, LDQ, 64, 128);
+  const CUtensorMap tm = get_tmap_2d_bf16(qkv, LDQ, static_cast<uint64_t>(nseq) * SEQ, LDQ, 64, 128);
   const uint64_t od[3] = {(uint64_t)LDO, (uint64_t)SEQ, (uint64_t)nseq};
   const uint64_t os[2] = {(uint64_t)LDO * 2, (uint64_t)SEQ * LDO * 2};
   const uint32_t ob[3] = {64, 32, 1};
-  const CUtensorMap& tmo = get_tmap_bf16(out, 3, od, os, ob);
+  const CUtensorMap tmo = get_tmap_bf16(out, 3, od, os, ob);
   int ctas = (nseq * NH + 1) / 2;  // two streams per CTA, one (sequence, head) unit at a time each
   if (ctas > sms) ctas = sms;
   switch (expv) {

@@ -32,9 +32,17 @@ struct Error : std::runtime_error {
                         " in " #expr " at " __FILE__ ":" + std::to_string(__LINE__)); \
   } while (0)
 
-// Launch counter (reported by dp_launch_count, used for bench.py's gpu_launches).
-extern int64_t g_launches;
-inline void count_launch(int n = 1) { g_launches += n; }
+// Launch counter (reported by dp_launch_count, used for bench.py's gpu_launches): process-wide, atomic -- engines on
+// several host threads (one per GPU, or several per GPU) may launch concurrently.
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// NVTX ranges per stage of a frame (SURVEY.md §5 "tracing"): visible in Nsight Systems / ncu --nvtx, free when no tool
+// is attached (nvtx3 is header-only and resolves its injection library lazily).
+struct NvtxRange {
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+};
 
 // ---- optional per-launch profiling with CUDA events (bench.py roofline numbers) ----------
 enum KernelClass {

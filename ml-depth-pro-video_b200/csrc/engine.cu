@@ -11,7 +11,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <type_traits>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "attention.cuh"
 #include "gemm.cuh"
@@ -19,7 +22,10 @@
 
 namespace dp {
 
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 bool pdl_enabled() {
   static const bool on = [] {
@@ -35,8 +41,13 @@ struct ProfRec {
   cudaEvent_t a, b;
   int cls;
   double work;
+  cudaStream_t s = nullptr;
+  bool closed = false;
 };
-bool g_prof_on = false;
+// The per-launch profiler is process-wide (bench.py switches it on for a replay of the timed steps): one mutex guards
+// the records and the event pool, the on/off flag is atomic so the disabled fast path takes no lock.
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_event_pool;
 cudaEvent_t new_event() {
@@ -52,24 +63,36 @@ cudaEvent_t new_event() {
 }  // namespace
 
 void prof_enable(bool on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& r : g_prof) g_event_pool.push_back(r.a), g_event_pool.push_back(r.b);
   g_prof.clear();
   g_prof_on = on;
 }
 void prof_begin(cudaStream_t s, int cls, double work) {
   if (!g_prof_on) return;
-  ProfRec r{new_event(), new_event(), cls, work};
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{new_event(), new_event(), cls, work, s, false};
   DP_CUDA(cudaEventRecord(r.a, s));
   g_prof.push_back(r);
 }
 void prof_end(cudaStream_t s) {
   if (!g_prof_on) return;
-  DP_CUDA(cudaEventRecord(g_prof.back().b, s));
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  // the record this scope opened is the last one of ITS stream (scopes of one stream nest strictly; profiling several
+  // engines at once interleaves records, so match on the stream)
+  for (auto it = g_prof.rbegin(); it != g_prof.rend(); ++it)
+    if (it->s == s && !it->closed) {
+      DP_CUDA(cudaEventRecord(it->b, s));
+      it->closed = true;
+      return;
+    }
 }
 void prof_collect(double* ms, double* work, long long* launches) {
   DP_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (int i = 0; i < KC_COUNT; ++i) ms[i] = 0, work[i] = 0, launches[i] = 0;
   for (auto& r : g_prof) {
+    if (!r.closed) continue;
     float t = 0.f;
     DP_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
     ms[r.cls] += t, work[r.cls] += r.work, launches[r.cls] += 1;

@@ -23,6 +23,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include <mutex>
+
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -906,13 +908,21 @@ std::unordered_map<TmapKey, CUtensorMap, TmapHash>& tmap_cache() {
   static std::unordered_map<TmapKey, CUtensorMap, TmapHash> c;
   return c;
 }
+// The cache is process-wide (device pointers are unique across GPUs under UVA) and shared by every engine and host
+// thread: lookups and inserts take this mutex, and a descriptor is handed out BY VALUE, so a concurrent
+// tmap_cache_clear() (engine destruction, test entry points) can never pull it from under a launch in flight.
+std::mutex& tmap_mutex() {
+  static std::mutex m;
+  return m;
+}
 
-const CUtensorMap& get_tmap(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                            const uint32_t* box) {
+CUtensorMap get_tmap(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
   TmapKey key{ptr, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, rank > 4 ? dims[4] : 0,
               strides_bytes[0], rank > 2 ? strides_bytes[1] : 0, rank > 3 ? strides_bytes[2] : 0,
               rank > 4 ? strides_bytes[3] : 0, box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
               rank > 4 ? box[4] : 0};
+  std::lock_guard<std::mutex> lk(tmap_mutex());
   auto& cache = tmap_cache();
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -930,25 +940,28 @@ const CUtensorMap& get_tmap(const void* ptr, int rank, const uint64_t* dims, con
 }
 
 int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev;
+  static const int n = [] {   // every GPU of a B200 box has the same SM count
+    int dev, v;
     DP_CUDA(cudaGetDevice(&dev));
-    DP_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-  }
+    DP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    return v;
+  }();
   return n;
 }
 
 // L2 persistence of the fp32 residual stream (opt-in: DEPTHPRO_L2_PERSIST_MB=<MB>, or gemm_tc_set_l2_persist()).
 // The set-aside is device-wide (cudaLimitPersistingL2CacheSize) and comes out of every other kernel's L2.
-static long long g_l2_persist_req = -1;   // requested MB; -1 = read the environment on first use
-static size_t g_l2_carve = 0, g_l2_window = 0;
-static bool g_l2_applied = false;
+static std::atomic<long long> g_l2_persist_req{-1};   // requested MB; -1 = read the environment on first use
+static std::atomic<size_t> g_l2_carve{0}, g_l2_window{0};
+static std::atomic<bool> g_l2_applied{false};
+static std::mutex g_l2_mu;
 static void set_l2_persist_impl(int mb) {
   g_l2_persist_req = mb < 0 ? 0 : mb;
   g_l2_applied = false;
 }
 static void l2_apply() {
+  std::lock_guard<std::mutex> lk(g_l2_mu);
+  if (g_l2_applied) return;
   if (g_l2_persist_req < 0) {
     const char* e = getenv("DEPTHPRO_L2_PERSIST_MB");
     g_l2_persist_req = e ? atoll(e) : 0;
@@ -1034,17 +1047,20 @@ void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const W
 
 }  // namespace
 
-void tmap_cache_clear() { tmap_cache().clear(); }
+void tmap_cache_clear() {
+  std::lock_guard<std::mutex> lk(tmap_mutex());
+  tmap_cache().clear();
+}
 
 // cached bf16 tensor map of any rank <= 5 (128B swizzle) for the other translation units
-const CUtensorMap& get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                 const uint32_t* box) {
+CUtensorMap get_tmap_bf16(const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box) {
   return get_tmap(ptr, rank, dims, strides_bytes, box);
 }
 
 // 2D row-major bf16 matrix (rows x cols, leading dimension ld_elems), 128B-swizzled box.
-const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
-                                    uint32_t box_rows) {
+CUtensorMap get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                             uint32_t box_rows) {
   const uint64_t dims[2] = {cols, rows};
   const uint64_t str[1] = {ld_elems * 2};
   const uint32_t box[2] = {box_cols, box_rows};
@@ -1052,7 +1068,7 @@ const CUtensorMap& get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t row
 }
 
 // Residual L2 prefetch switch: DEPTHPRO_RES_PREFETCH=0/1 in the environment, or gemm_tc_set_res_prefetch() (A/B runs).
-static int g_res_prefetch = -1;
+static std::atomic<int> g_res_prefetch{-1};
 void gemm_tc_set_res_prefetch(int on) { g_res_prefetch = on != 0; }
 void gemm_tc_set_l2_persist(int mb) { set_l2_persist_impl(mb); }
 static bool res_prefetch_enabled() {
@@ -1090,7 +1106,8 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   static const bool no_cluster = getenv("DEPTHPRO_NO_CLUSTER") != nullptr;  // debugging switch
   const int cl = (!no_cluster && bn >= 128 && m_tiles_total * g.n_tiles >= num_sms()) ? 2 : 1;
 
-  const CUtensorMap* tmA;
+  CUtensorMap tmA_v;
+  const CUtensorMap* tmA = &tmA_v;
   if (op.a_mode == A_CONV3X3) {
     DP_CHECK(op.ngroups == 1, "conv3x3 launches are not grouped");
     DP_CHECK(op.C % BK == 0 && op.K == 9 * op.C, "conv3x3: C must be a multiple of 64");
@@ -1103,7 +1120,7 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
     const uint64_t dims[4] = {(uint64_t)op.C, (uint64_t)op.W, (uint64_t)op.H, (uint64_t)op.B};
     const uint64_t str[3] = {(uint64_t)op.C * 2, (uint64_t)op.W * op.C * 2, (uint64_t)op.H * op.W * op.C * 2};
     const uint32_t box[4] = {BK, TILE_W, TILE_H, 1};
-    tmA = &get_tmap(op.A, 4, dims, str, box);
+    tmA_v = get_tmap(op.A, 4, dims, str, box);
   } else {
     int mu = 0;
     for (int i = 0; i < 3; ++i) {
@@ -1122,7 +1139,7 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
     const uint64_t dims[2] = {(uint64_t)op.K, (uint64_t)op.a_rows};
     const uint64_t str[1] = {(uint64_t)op.lda * 2};
     const uint32_t box[2] = {BK, BM};
-    tmA = &get_tmap(op.A, 2, dims, str, box);
+    tmA_v = get_tmap(op.A, 2, dims, str, box);
   }
   WeightMaps tmW;
   const uint64_t wd[2] = {(uint64_t)op.K, (uint64_t)op.N};
@@ -1141,7 +1158,7 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   for (int i = 0; i < 3; ++i) tmW.o[i] = tmW.b[0];
   tmW.orelu = tmW.b[0];
   if (g.tma_out) {
-    auto make = [&](const void* base, int group) -> const CUtensorMap& {
+    auto make = [&](const void* base, int group) -> CUtensorMap {
       if (op.out_mode == O_CONVT2X2) {
         // output (b, 2y+dy, 2x+dx, c) viewed as [c][dx][x][dy][b*H+y]
         const uint64_t ld = (uint64_t)op.ldo * 2;

@@ -1053,7 +1053,7 @@ void compute_fpx(const float* fov_deg, const float* f_px_in, int W, float* f_px,
   DP_LAUNCH_CHECK();
 }
 
-static int g_hbm_v2 = -1;
+static std::atomic<int> g_hbm_v2{-1};
 void hbm_v2_set(int on) { g_hbm_v2 = on != 0; }
 static bool hbm_v2() {
   if (g_hbm_v2 < 0) {

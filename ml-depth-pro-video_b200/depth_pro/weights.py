@@ -214,9 +214,8 @@ def reference_like_tensor(name: str, shape: Tuple[int, ...], seed: int) -> torch
 
 
 def _bias_fan_in(name: str) -> int:
-    m = manifest()
     w = name.rsplit(".", 1)[0] + ".weight"
-    s = m[w]
+    s = manifest()[w] if w in manifest() else manifest("head")[w]   # fov.head.6 exists in the head-only config only
     if len(s) == 2:
         return s[1]
     return s[1] * s[2] * s[3]

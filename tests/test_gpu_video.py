@@ -56,7 +56,7 @@ def test_depth_to_3d_and_colours(model):
 def test_colorize_and_u16(model):
     depth = model.infer(torch.from_numpy(O.synthetic_frame_u8(2, 270, 480)))["depth"]
     lut = video.colormap_lut("turbo")
-    rgb = video.colorize_depth(model, depth, "turbo").cpu().numpy()
+    rgb = video.colorize_depth(model, depth, cmap="turbo").cpu().numpy()
     norm = O.normalize_depth(depth.cpu().numpy())
     assert np.array_equal(rgb, lut[np.minimum((norm * 256).astype(np.int64), 255)])
     u16 = video.depth_to_uint16(model, depth).cpu().numpy().view(np.uint16)
