@@ -603,6 +603,7 @@ constexpr int ATTN_EXP_DEFAULT = 13;  // measured on B200 (profiles/r2_attention
 static bool variant_compiled(int v) { return v == 0 || v == 5 || v == 12 || v == 13; }
 
 void attention_tc_set_variant(int expv, int pingpong) {
+  bump_config_epoch();
   if (expv < 0) {  // back to the environment's / built-in default on the next launch
     g_expv = -1;
     return;

@@ -37,6 +37,11 @@ struct Error : std::runtime_error {
 extern std::atomic<int64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Bumped by every process-wide A/B switch (attention variant, residual prefetch, L2 set-aside, HBM kernel generation):
+// an engine re-captures its CUDA graphs when the epoch it captured under is no longer current.
+extern std::atomic<unsigned> g_config_epoch;
+inline void bump_config_epoch() { g_config_epoch.fetch_add(1); }
+
 // NVTX ranges per stage of a frame (SURVEY.md §5 "tracing"): visible in Nsight Systems / ncu --nvtx, free when no tool
 // is attached (nvtx3 is header-only and resolves its injection library lazily).
 struct NvtxRange {
@@ -61,6 +66,7 @@ struct ProfScope {
   ~ProfScope() { prof_end(s); }
 };
 void prof_enable(bool on);
+bool prof_active();
 // sums since prof_enable(true); synchronises the device
 void prof_collect(double* ms_by_class, double* work_by_class, long long* launches_by_class);
 

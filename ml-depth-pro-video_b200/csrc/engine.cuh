@@ -69,6 +69,10 @@ class Engine {
  private:
   template <typename T>
   void forward_impl(const float* x, int B, float* canon, float* fov_deg, cudaStream_t s);
+  // xbuf_ -> canon_, fov_ (the buffers dp_infer uses): replays a captured CUDA graph of the whole forward pass when
+  // graphs are enabled and one exists for this batch size, captures one on the second call, runs eagerly otherwise
+  void forward_cached(int B, cudaStream_t s);
+  void drop_graphs();
   template <typename T>
   void run_vits(int B, cudaStream_t s);
   template <typename T>
@@ -111,6 +115,7 @@ class Engine {
   // per-frame decoder workspace
   void *u0a_, *u0b_, *u0c_, *enc0_, *enc0r_, *u1a_, *u1b_, *enc1_, *u2a_, *enc2_, *u3a_, *enc3_, *u4a_, *cat_, *enc4_;
   void *lowres_, *lowres_r_, *x1_, *x1r_, *t_, *x_, *xr_, *x2_, *y_, *feat_[5];
+  void *c1_, *c1r_, *c2_, *c2r_, *c3_, *c3r_;  // decoder.convs.{1,2,3} outputs (+ ReLU twins), one set per level
   void *h0_, *h1_;
   void* head_wc_ = nullptr;    // composed head.1 o head.2 weights (bf16 mode)
   float* head_cb_ = nullptr;
@@ -130,6 +135,25 @@ class Engine {
   int* unproject_scratch_ = nullptr;
   size_t unproject_scratch_ints_ = 0;
   cudaStream_t host_stream_ = nullptr;
+
+  // ---- concurrency inside a frame (decode_frame): the five encoder project + upsample branches, the three decoder skip
+  // convs and the FOV head are independent of the main fusion chain and are latency-bound small launches (18-80 CTAs
+  // each); they run on side streams forked from / joined into the caller's stream with events.
+  static constexpr int NSIDE = 5;
+  cudaStream_t side_[NSIDE] = {};
+  cudaEvent_t ev_fork_ = nullptr, ev_lowres_ = nullptr, ev_side_[NSIDE] = {};
+  bool multi_stream_ = true;     // DEPTHPRO_STREAMS=0: everything on the caller's stream (round-1 behaviour)
+
+  // ---- CUDA graphs: one instantiated graph of the forward pass per batch size (DEPTHPRO_GRAPH=0 disables)
+  struct FrameGraph {
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;      // kernel launches recorded while capturing (added to the launch counter per replay)
+    unsigned epoch = 0;
+    int eager_calls = 0;
+  };
+  std::map<int, FrameGraph> graphs_;
+  bool use_graph_ = true;
+  cudaStream_t cap_stream_ = nullptr;
 };
 
 }  // namespace dp

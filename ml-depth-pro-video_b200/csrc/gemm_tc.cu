@@ -1069,8 +1069,14 @@ CUtensorMap get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint
 
 // Residual L2 prefetch switch: DEPTHPRO_RES_PREFETCH=0/1 in the environment, or gemm_tc_set_res_prefetch() (A/B runs).
 static std::atomic<int> g_res_prefetch{-1};
-void gemm_tc_set_res_prefetch(int on) { g_res_prefetch = on != 0; }
-void gemm_tc_set_l2_persist(int mb) { set_l2_persist_impl(mb); }
+void gemm_tc_set_res_prefetch(int on) {
+  g_res_prefetch = on != 0;
+  bump_config_epoch();
+}
+void gemm_tc_set_l2_persist(int mb) {
+  set_l2_persist_impl(mb);
+  bump_config_epoch();
+}
 static bool res_prefetch_enabled() {
   if (g_res_prefetch < 0) {
     const char* e = getenv("DEPTHPRO_RES_PREFETCH");

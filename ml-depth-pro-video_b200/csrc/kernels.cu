@@ -1054,7 +1054,10 @@ void compute_fpx(const float* fov_deg, const float* f_px_in, int W, float* f_px,
 }
 
 static std::atomic<int> g_hbm_v2{-1};
-void hbm_v2_set(int on) { g_hbm_v2 = on != 0; }
+void hbm_v2_set(int on) {
+  g_hbm_v2 = on != 0;
+  bump_config_epoch();
+}
 static bool hbm_v2() {
   if (g_hbm_v2 < 0) {
     const char* e = getenv("DEPTHPRO_HBM_V2");
