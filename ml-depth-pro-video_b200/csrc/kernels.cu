@@ -82,6 +82,77 @@ __global__ void __launch_bounds__(256) resize_kernel(const void* __restrict__ sr
   }
 }
 
+// Second generation (default since round 2; DEPTHPRO_HBM_V2=0 restores the kernel above): one block = ONE output row
+// (384 threads x 4 consecutive pixels), so the row's source lines and vertical weights are computed once per block, every
+// thread keeps four independent gather chains in flight and each channel leaves as one 128-bit store.  Same arithmetic,
+// bit-identical output (test_resize_v2_is_bit_identical).
+template <int FMT>
+__global__ void __launch_bounds__(384) resize_kernel_v2(const void* __restrict__ src, int H, int W, float* __restrict__ x) {
+  __shared__ float lut[256];
+  if (FMT == 1) {
+    if (threadIdx.x < 256) {
+      const float t = __fdiv_rn(static_cast<float>(threadIdx.x), 255.f);
+      lut[threadIdx.x] = __fmul_rn(__fsub_rn(t, 0.5f), 2.f);
+    }
+    __syncthreads();
+  }
+  const int ox0 = threadIdx.x * 4, oy = blockIdx.x, b = blockIdx.y;
+  const bool same = H == IMG && W == IMG;
+  int y0 = oy, y1 = oy;
+  float ly1 = 0.f;
+  const float sh = static_cast<float>(H) / IMG, sw = static_cast<float>(W) / IMG;
+  if (!same) {
+    float fy = fmaf(sh, oy + 0.5f, -0.5f);
+    fy = fy < 0.f ? 0.f : fy;
+    y0 = static_cast<int>(fy);
+    y0 = y0 > H - 1 ? H - 1 : y0;
+    y1 = y0 + (y0 < H - 1 ? 1 : 0);
+    ly1 = fminf(fmaxf(fy - y0, 0.f), 1.f);
+  }
+  const float ly0 = 1.f - ly1;
+  int x0[4], x1[4];
+  float lx1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ox = ox0 + i;
+    x0[i] = ox, x1[i] = ox, lx1[i] = 0.f;
+    if (!same) {
+      float fx = fmaf(sw, ox + 0.5f, -0.5f);
+      fx = fx < 0.f ? 0.f : fx;
+      x0[i] = static_cast<int>(fx);
+      x0[i] = x0[i] > W - 1 ? W - 1 : x0[i];
+      x1[i] = x0[i] + (x0[i] < W - 1 ? 1 : 0);
+      lx1[i] = fminf(fmaxf(fx - x0[i], 0.f), 1.f);
+    }
+  }
+  float* dst = x + (static_cast<size_t>(b) * 3 * IMG + oy) * IMG + ox0;
+  const size_t r0 = static_cast<size_t>(y0) * W, r1 = static_cast<size_t>(y1) * W;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float p00, p01, p10, p11;
+      if (FMT == 1) {
+        const uint8_t* im = reinterpret_cast<const uint8_t*>(src) + static_cast<size_t>(b) * H * W * 3 + c;
+        p00 = lut[im[(r0 + x0[i]) * 3]], p01 = lut[im[(r0 + x1[i]) * 3]];
+        p10 = lut[im[(r1 + x0[i]) * 3]], p11 = lut[im[(r1 + x1[i]) * 3]];
+      } else {
+        const float* im = reinterpret_cast<const float*>(src) + (static_cast<size_t>(b) * 3 + c) * H * W;
+        p00 = im[r0 + x0[i]], p01 = im[r0 + x1[i]], p10 = im[r1 + x0[i]], p11 = im[r1 + x1[i]];
+      }
+      v[i] = p00;
+      if (!same) {
+        const float lx0 = 1.f - lx1[i];
+        const float t0 = __fadd_rn(__fmul_rn(lx0, p00), __fmul_rn(lx1[i], p01));
+        const float t1 = __fadd_rn(__fmul_rn(lx0, p10), __fmul_rn(lx1[i], p11));
+        v[i] = __fadd_rn(__fmul_rn(ly0, t0), __fmul_rn(ly1, t1));
+      }
+    }
+    *reinterpret_cast<float4*>(dst + static_cast<size_t>(c) * IMG * IMG) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // interpolation_mode = "bicubic" (depth_pro.py:247, 273-279, 288-291 pass the mode to F.interpolate): ATen's
 // upsample_bicubic2d with align_corners=False -- source index scale * (dst + 0.5) - 0.5 WITHOUT the clamp at 0 the
@@ -928,12 +999,29 @@ void compose_head(const float* w1, const float* b1, const float* w2, const float
   DP_LAUNCH_CHECK();
 }
 
+static std::atomic<int> g_hbm_v2{-1};
+void hbm_v2_set(int on) {
+  g_hbm_v2 = on != 0;
+  bump_config_epoch();
+}
+static bool hbm_v2() {
+  if (g_hbm_v2 < 0) {
+    const char* e = getenv("DEPTHPRO_HBM_V2");
+    g_hbm_v2 = e ? (atoi(e) != 0) : 1;  // default since round 2: bit-identical to v1 on B200 (test_depth_epilogue_v2_is_bit_identical)
+  }
+  return g_hbm_v2 != 0;
+}
+
 void resize_to_1536(const void* src, int src_fmt, int B, int H, int W, float* x, int interp, cudaStream_t s) {
   static_assert(IMG % 256 == 0, "one block = 256 pixels of a row");
   const dim3 grid(IMG / 256, IMG, B);
   if (interp == INTERP_BICUBIC && !(H == IMG && W == IMG)) {
     if (src_fmt == 1) resize_bicubic_kernel<1><<<grid, 256, 0, s>>>(src, H, W, x);
     else resize_bicubic_kernel<0><<<grid, 256, 0, s>>>(src, H, W, x);
+  } else if (hbm_v2()) {
+    static_assert(IMG == 384 * 4, "resize_kernel_v2: one block = one 1536-pixel row");
+    if (src_fmt == 1) resize_kernel_v2<1><<<dim3(IMG, B), 384, 0, s>>>(src, H, W, x);
+    else resize_kernel_v2<0><<<dim3(IMG, B), 384, 0, s>>>(src, H, W, x);
   } else {
     if (src_fmt == 1) resize_kernel<1><<<grid, 256, 0, s>>>(src, H, W, x);
     else resize_kernel<0><<<grid, 256, 0, s>>>(src, H, W, x);
@@ -1051,19 +1139,6 @@ template void fov_final<bf16>(const bf16*, const float*, const float*, float*, i
 void compute_fpx(const float* fov_deg, const float* f_px_in, int W, float* f_px, int B, cudaStream_t s) {
   fpx_kernel<<<1, 64, 0, s>>>(fov_deg, f_px_in, W, f_px, B);
   DP_LAUNCH_CHECK();
-}
-
-static std::atomic<int> g_hbm_v2{-1};
-void hbm_v2_set(int on) {
-  g_hbm_v2 = on != 0;
-  bump_config_epoch();
-}
-static bool hbm_v2() {
-  if (g_hbm_v2 < 0) {
-    const char* e = getenv("DEPTHPRO_HBM_V2");
-    g_hbm_v2 = e ? (atoi(e) != 0) : 1;  // default since round 2: bit-identical to v1 on B200 (test_depth_epilogue_v2_is_bit_identical)
-  }
-  return g_hbm_v2 != 0;
 }
 
 void depth_epilogue(const float* canon, const float* f_px, int B, int H, int W, float* depth, int interp, cudaStream_t s) {

@@ -1,5 +1,10 @@
 """Image IO helpers with the reference's contract (src/depth_pro/utils.py:42-112).
 
+RESTATED FROM THE REFERENCE: `load_rgb` and `fpx_from_f35` are contract-bound host IO that SURVEY.md marks out of scope
+for the GPU path ("kept as-is; only its output contract matters") -- the EXIF key chain, the orientation table and the
+35 mm formula ARE the contract (the returned `f_px` feeds `DepthPro.infer`), so this file follows the reference's control
+flow closely on purpose.  Nothing here touches the GPU.
+
 Host-side only: PIL decode, EXIF orientation, EXIF 35 mm focal length -> f_px.  HEIC needs
 `pillow_heif`, which is optional here.
 """

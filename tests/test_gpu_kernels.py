@@ -52,6 +52,24 @@ def test_resize_u8_fused_transform():
     assert _ulp_err(got2, ref2) <= 2.0
 
 
+@pytest.mark.parametrize("H,W", [(1080, 1920), (2160, 3840), (384, 640), (1536, 1536), (1537, 1535), (5, 3), (1, 1)])
+def test_resize_v2_is_bit_identical(H, W):
+    """The one-row-per-block / four-pixels-per-thread resize (default since round 2) against the round-1 kernel
+    (DEPTHPRO_HBM_V2=0, selected through dp_kernel_bench's A/B bits): uint8 and float sources, bit for bit."""
+    g = torch.Generator().manual_seed(H * 3 + W)
+    u8 = torch.randint(0, 256, (2, H, W, 3), dtype=torch.uint8, generator=g).to(DEV)
+    f32 = (torch.rand(2, 3, H, W, generator=g) * 2 - 1).to(DEV)
+    ms = ctypes.c_float()
+    outs = {}
+    try:
+        for tag, bit in (("v1", 0x2000), ("v2", 0x1000)):
+            _capi.check(lib().dp_kernel_bench(engine(), 8 | bit, 64, 64, 0, 1, ctypes.byref(ms)))
+            outs[tag] = (_preprocess(u8, _capi.SRC_U8_HWC, 2, H, W), _preprocess(f32, _capi.SRC_F32_CHW, 2, H, W))
+    finally:
+        _capi.check(lib().dp_kernel_bench(engine(), 8 | 0x1000, 64, 64, 0, 1, ctypes.byref(ms)))
+    assert torch.equal(outs["v1"][0], outs["v2"][0]) and torch.equal(outs["v1"][1], outs["v2"][1])
+
+
 @pytest.mark.parametrize("H,W", [(1080, 1920), (2160, 3840), (384, 640), (1537, 1535), (5, 3), (1, 1)])
 def test_resize_bicubic(H, W):
     """interpolation_mode="bicubic" (depth_pro.py:247, 273-279): ATen upsample_bicubic2d, align_corners=False.  The

@@ -368,6 +368,42 @@ def test_weight_edits_reach_the_engine(state_dict):
     del m
 
 
+def test_two_engines_on_two_threads(state_dict, model_bf16):
+    """the process-wide pieces of the library (tensor-map cache, launch counter, profiler,
+    A/B switches) are guarded, so two engines driven from two host threads on their own streams may run concurrently
+    (SURVEY.md §8e "one host thread per GPU").  Each thread's results must equal the single-threaded ones bit for bit."""
+    import threading
+
+    frames = [torch.from_numpy(O.synthetic_frame_u8(i, 270, 480)).to(DEV) for i in range(6)]
+    want = [model_bf16.infer(f)["depth"].clone() for f in frames]
+    second = _model(state_dict, torch.bfloat16)
+    models, got, errors = [model_bf16, second], [[None] * 6, [None] * 6], []
+    start = threading.Barrier(2)
+
+    def work(t):
+        try:
+            stream = torch.cuda.Stream(DEV)
+            with torch.cuda.stream(stream):
+                start.wait()
+                for rep in range(2):                 # eager call, graph capture, replays -- interleaved across threads
+                    for i in range(6):
+                        j = i if t == 0 else 5 - i
+                        got[t][j] = models[t].infer(frames[j])["depth"].clone()
+                stream.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for t in range(2):
+        for i in range(6):
+            assert torch.equal(got[t][i], want[i]), (t, i)
+    del second
+    torch.cuda.empty_cache()
+
+
 def test_batch_is_bit_identical(model_bf16):
     """Frames are independent units: a 2-frame batch must equal two single-frame calls bit for bit."""
     frames = np.stack([O.synthetic_frame_u8(i, 540, 960) for i in range(2)])

@@ -148,3 +148,29 @@ def test_oracle_fov_head_without_encoder_vs_live_reference():
     assert len(weights.manifest()) == 1119
     assert not any(k.startswith("fov.") for k in weights.manifest(None))
     assert sum(k.startswith("fov.") for k in want) == 8
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not RL.available(), reason="/root/reference not present (GPU box)")
+def test_vit_surgery_matches_the_reference_functions():
+    """a13 (`resize_patch_embed` / `resize_vit`, vit.py:51-123): the product's state-dict form against the reference's
+    own in-place surgery of a timm patch14 / 518 model, bit for bit, and the result loads into the engine's manifest."""
+    from depth_pro import vit_surgery
+
+    RL.load()
+    import timm  # the shim (oracle/timm)
+
+    vit_mod = sys.modules["ref_depth_pro.network.vit"]
+    torch.manual_seed(3)
+    raw_model = timm.create_model("vit_large_patch14_dinov2", pretrained=False, dynamic_img_size=True)
+    raw = {k: v.clone() for k, v in raw_model.state_dict().items()}
+    assert raw["patch_embed.proj.weight"].shape == (1024, 3, 14, 14) and raw["pos_embed"].shape == (1, 1370, 1024)
+    raw_model.patch_size = raw_model.patch_embed.patch_size
+    ref_model = vit_mod.resize_vit(vit_mod.resize_patch_embed(raw_model, new_patch_size=(16, 16)), img_size=(384, 384))
+    ref = ref_model.state_dict()
+    got = vit_surgery.convert_timm_vit_state_dict(raw, prefix="encoder.patch_encoder.")
+    want_shapes = {k: s for k, s in weights.manifest().items() if k.startswith("encoder.patch_encoder.")}
+    assert {k: tuple(v.shape) for k, v in got.items()} == want_shapes
+    for k, v in ref.items():
+        assert torch.equal(got["encoder.patch_encoder." + k], v), k
+    assert got["encoder.patch_encoder.pos_embed"].shape == (1, 577, 1024)
