@@ -150,6 +150,12 @@ template <int EXPV>
 __device__ __forceinline__ constexpr bool p_in_tmem() { return EXPV >= 12; }
 template <int EXPV>
 __device__ __forceinline__ constexpr int arrive_at() { return EXPV == 0 ? 16 : 12; }
+// Two more round-2 experiments, measured and removed again (profiles/r2_attention_variants.json,
+// r2_attention_phase_profile_*.log): variant 12 with every exponential replaced by one FMUL (wrong results on purpose)
+// still takes 71.4 us per layer against 82.0 us for variant 13 -- the MUFU is NOT what bounds this kernel, the load /
+// MMA-issue / barrier pipeline is (the MMA warp needs ~450 + ~320 cycles to get the 4 + 8 tcgen05.mma of a block through
+// the tensor core's queue while the other stream's MMAs interleave, and waits ~430 + ~290 cycles for K / V); and a producer
+// that requests K (G + 1) before it waits for V (G)'s stage changes nothing (82.0 us).
 
 // Debug counter (dp_debug_counter): how many times a softmax warp took the lazy-maximum RESCALE branch.
 __device__ unsigned long long g_attn_rescales;
