@@ -352,24 +352,36 @@ def run_ours(args):
     value = world * B / (ms_per_step / 1e3)
     finite = bool(torch.isfinite(out["depth"]).all())
 
-    # ---------------- e2e through the public API with HOST buffers
-    def e2e_step():
-        pred = model.infer(u8_host.to(dev, non_blocking=True))
-        depth_host.copy_(pred["depth"].reshape(B, 1536, 1536), non_blocking=True)
-        f_host.copy_(pred["focallength_px"].reshape(B), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+    # ---------------- e2e through the public API with HOST buffers: every step copies its uint8 frames from pinned host
+    # memory to the GPU and its fp32 depth + focal length back (video.DepthStream: H2D / compute / D2H on three streams,
+    # so the copies of step k overlap the compute of its neighbours; the last result is on the host when the clock stops)
+    from depth_pro import video
 
-    for _ in range(3):
-        e2e_step()
+    stream = video.DepthStream(model, 1536, 1536, batch=B, slots=3)
+    u8_np = u8_host.numpy()
+    got = {"frames": 0, "last": None}
+
+    def e2e_run(n_steps):
+        for r in stream.run(((k * B + i, u8_np[i]) for k in range(n_steps) for i in range(B))):
+            got["frames"] += 1
+            got["last"] = r
+        torch.cuda.synchronize(dev)
+
+    e2e_run(3)
+    got["frames"] = 0
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    assert got["frames"] == args.steps * B
+    depth_host[got["last"].index % B].copy_(torch.from_numpy(got["last"].depth))
     e2e = {"value": world * B / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
            "h2d_bytes_per_step": int(u8_host.numel()), "d2h_bytes_per_step": int(depth_host.numel() * 4 + B * 4),
-           "api": "model.infer(uint8 HWC pinned host frame) -> depth.cpu() (fp32)"}
+           "api": "video.DepthStream.run(pinned uint8 HWC host frames) -> pinned fp32 host depth + focal length "
+                  "(H2D / model.infer / D2H on three streams)",
+           "host_result_matches_device": bool(torch.equal(
+               depth_host[got["last"].index % B], model.infer(u8_host[got["last"].index % B].to(dev))["depth"].cpu()))}
 
     # ---------------- roofline: per-launch CUDA events over a replay of the timed steps
     roof = None

@@ -37,6 +37,14 @@ namespace dp {
 __device__ unsigned long long g_attn_prof[10];
 __device__ unsigned long long g_attn_prof_sj[5];    // softmax: cycles waiting for S, by key block j
 __device__ unsigned long long g_attn_prof_mma[8];   // MMA warp: q_full, k_full, s_empty, QK issue, v_full+o_empty, p_full, PV issue, #blocks
+// Event trace of ONE stream (CTA 0, stream 0): clock64 of every hand-shake of its first TRACE_BLOCKS key blocks, so the
+// actual ordering of producer / MMA / softmax events can be read off (scripts/ubench/attn_prof.cu prints it).
+constexpr int TRACE_BLOCKS = 40, TRACE_EVENTS = 16;
+__device__ long long g_attn_trace[TRACE_EVENTS][TRACE_BLOCKS];
+#define TRACE(ev, G)                                                                         \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && sidx == 0 && (G) < TRACE_BLOCKS) g_attn_trace[ev][G] = clock64(); \
+  } while (0)
 #define PROF_DECL long long prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_last = clock64();
 #define PROF_T(i)                          \
   {                                        \
@@ -47,6 +55,7 @@ __device__ unsigned long long g_attn_prof_mma[8];   // MMA warp: q_full, k_full,
 #else
 #define PROF_DECL
 #define PROF_T(i)
+#define TRACE(ev, G)
 #endif
 namespace {
 
@@ -237,12 +246,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             const int G = T * NB + j, st = G % RING;
             const uint32_t ph = ((G / RING) & 1) ^ 1;
             ptx::mbar_wait(&k_empty[st], ph);
+            if (lane == 0) TRACE(0, G);
             if (ptx::elect_one()) {
               ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
               ptx::tma_load_2d(sK + st * TILE_BYTES, &tmQKV, &k_full[st], NH * HD + h * HD, row0 + j * KB);
             }
             __syncwarp();
             ptx::mbar_wait(&v_empty[st], ph);
+            if (lane == 0) TRACE(1, G);
             if (ptx::elect_one()) {
               ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
               ptx::tma_load_2d(sV + st * TILE_BYTES, &tmQKV, &v_full[st], 2 * NH * HD + h * HD, row0 + j * KB);
@@ -271,9 +282,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             ptx::mbar_wait(&v_full[st], (G / RING) & 1);
             if (jj == 0) ptx::mbar_wait(o_empty, (Tt & 1) ^ 1);  // the previous tile's O has been read out
             MPROF(4)
+            if (lane == 0) TRACE(5, G);
             const int nks = jj == NB - 1 ? LAST_N / 16 : KB / 16;
             ptx::mbar_wait(p_full, G & 1);
             MPROF(5)
+            if (lane == 0) TRACE(6, G);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
 #pragma unroll
@@ -290,6 +303,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             }
             __syncwarp();
             MPROF(6)
+            if (lane == 0) TRACE(7, G);
       };
       // (Issuing the last P V of tile T after the first Q K^T of tile T+1 was measured and changed nothing: the
       // single-buffered Q tile and the first K block of the next tile arrive too late for it to matter.)
@@ -303,8 +317,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             const int G = T * NB + j, st = G % RING;
             ptx::mbar_wait(&k_full[st], (G / RING) & 1);
             MPROF(1)
+            if (lane == 0) TRACE(2, G);
             ptx::mbar_wait(s_empty, (G & 1) ^ 1);
             MPROF(2)
+            if (lane == 0) TRACE(3, G);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
 #pragma unroll
@@ -317,6 +333,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             }
             __syncwarp();
             MPROF(3)
+            if (lane == 0) TRACE(4, G);
 #ifdef ATTN_PROFILE
             mp[7] += 1;
 #endif
@@ -364,8 +381,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           constexpr int NKEY = LAST ? LAST_KEYS : KB;         // valid keys in this block
           constexpr int NG = (LAST ? LAST_N : KB) / 8;        // 8-key groups the P V MMA reads
           const int G = T * NB + j;
+          if (q == 0 && lane == 0) TRACE(8, G);
           ptx::mbar_wait(s_full, G & 1);
           ptx::tc_fence_after();
+          if (q == 0 && lane == 0) TRACE(9, G);
 #ifdef ATTN_PROFILE
           if (q == 0 && lane == 0) atomicAdd(&g_attn_prof_sj[j], static_cast<unsigned long long>(clock64() - prof_last));
 #endif
@@ -377,6 +396,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           ptx::tc_fence_before();
           ptx::mbar_arrive(s_empty);  // S is in registers: the next Q K^T may overwrite it
           PROF_T(1)  // TMEM load
+          if (q == 0 && lane == 0) TRACE(10, G);
           // row maximum over the valid keys, four independent chains
           float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -389,6 +409,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             ptx::tc_fence_after();
           }
           PROF_T(3)  // waiting for the previous P V
+          if (q == 0 && lane == 0) TRACE(11, G);
           if (j == 0) {
             m_ref = mx;
           } else if (__any_sync(0xffffffffu, (mx - m_ref) * c > RESCALE_LOG2)) {
@@ -412,6 +433,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           PROF_T(4)  // lazy-maximum check / rescale
           if (G < n_pp && (sidx == 1 || G > 0)) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");
           PROF_T(5)  // waiting for the MUFU turn
+          if (q == 0 && lane == 0) TRACE(12, G);
           if (j == 0) {  // the previous tile's output store must have drained this warp's P rows
             if (lane == 0) ptx::tma_store_wait_read();
             __syncwarp();
@@ -492,6 +514,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           ptx::tc_fence_before();
           ptx::mbar_arrive(p_full);
           PROF_T(7)  // hand-off
+          if (q == 0 && lane == 0) TRACE(13, G);
 #ifdef ATTN_PROFILE
           prof_acc[8] += 1;
 #endif
@@ -570,6 +593,7 @@ void attn_prof_read(unsigned long long* host10, bool reset) {
   DP_CUDA(cudaMemcpyFromSymbol(host10, g_attn_prof, sizeof(unsigned long long) * 10));
   DP_CUDA(cudaMemcpyFromSymbol(host10 + 10, g_attn_prof_sj, sizeof(unsigned long long) * 5));
   DP_CUDA(cudaMemcpyFromSymbol(host10 + 15, g_attn_prof_mma, sizeof(unsigned long long) * 8));
+  DP_CUDA(cudaMemcpyFromSymbol(host10 + 23, g_attn_trace, sizeof(long long) * TRACE_EVENTS * TRACE_BLOCKS));
   if (reset) {
     unsigned long long z[10] = {0};
     DP_CUDA(cudaMemcpyToSymbol(g_attn_prof, z, sizeof(z)));

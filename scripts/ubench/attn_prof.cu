@@ -13,7 +13,7 @@ int main() {
   cudaMalloc(&qkv, nq * 2); cudaMalloc(&out, no * 2);
   dp::fill_random_bf16(qkv, nq * 2, 12345u, nullptr);
   for (int i = 0; i < 3; ++i) dp::attention_bf16_tc(qkv, out, nseq, nullptr);
-  unsigned long long p[23];
+  static unsigned long long p[23 + 16 * 40];
   dp::attn_prof_read(p, true);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   const int iters = 20;
@@ -38,5 +38,19 @@ int main() {
   const double mb = (double)p[22];
   printf("MMA warp, cycles per block (%.0f blocks):\n", mb);
   for (int i = 0; i < 7; ++i) printf("  %-20s %8.1f\n", mn[i], p[15 + i] / mb);
+  // event trace of CTA 0 / stream 0 (last launch): cycles relative to the stream's first event
+  const char* ev[14] = {"prod: K req", "prod: V req", "mma: K ready", "mma: s_empty ok", "mma: QK issued", "mma: V ready",
+                        "mma: p_full ok", "mma: PV issued", "smx: at s_full", "smx: S ready", "smx: S loaded", "smx: PV(G-1) done",
+                        "smx: MUFU turn", "smx: P published"};
+  const long long* tr = reinterpret_cast<const long long*>(p + 23);
+  long long t0 = tr[0 * 40 + 0];
+  printf("event trace, CTA 0 stream 0, cycles since the first K request (columns = key block G):\n%-20s", "event");
+  for (int G = 10; G < 22; ++G) printf("%8d", G);
+  printf("\n");
+  for (int e = 0; e < 14; ++e) {
+    printf("%-20s", ev[e]);
+    for (int G = 10; G < 22; ++G) printf("%8lld", tr[e * 40 + G] - t0);
+    printf("\n");
+  }
   return 0;
 }
