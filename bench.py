@@ -285,6 +285,10 @@ def run_ours(args):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU: keep its threads and pinned buffers on the GPU's NUMA node (no-op if NVML says nothing)
+        from depth_pro import pipeline as _pl
+
+        _pl.pin_to_gpu_numa(local)
 
     lib_path = os.path.join(ROOT, "ml-depth-pro-video_b200", "depth_pro", "libdepthpro_b200.so")
     if not os.path.exists(lib_path):

@@ -164,7 +164,9 @@ __device__ __forceinline__ constexpr int arrive_at() { return EXPV == 0 ? 16 : 1
 // still takes 71.4 us per layer against 82.0 us for variant 13 -- the MUFU is NOT what bounds this kernel, the load /
 // MMA-issue / barrier pipeline is (the MMA warp needs ~450 + ~320 cycles to get the 4 + 8 tcgen05.mma of a block through
 // the tensor core's queue while the other stream's MMAs interleave, and waits ~430 + ~290 cycles for K / V); and a producer
-// that requests K (G + 1) before it waits for V (G)'s stage changes nothing (82.0 us).
+// that requests K (G + 1) before it waits for V (G)'s stage changes nothing (82.0 us).  An OPTIMISTIC running maximum (no
+// row-maximum pre-pass in blocks 1-4 of a tile: exponentials against the running reference, block maximum tracked inside
+// the exp loop, block redone if the threshold trips; bit-identical results) was slower too: 85.7 us against 83.1 us.
 
 // Debug counter (dp_debug_counter): how many times a softmax warp took the lazy-maximum RESCALE branch.
 __device__ unsigned long long g_attn_rescales;

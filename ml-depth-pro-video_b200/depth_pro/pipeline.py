@@ -38,6 +38,36 @@ PROGRESS_FILE = "processing_progress.json"
 
 
 # ----------------------------------------------------------------------------------------------
+# host placement: one process per GPU wants its threads and pinned buffers on the GPU's NUMA node
+# ----------------------------------------------------------------------------------------------
+def pin_to_gpu_numa(device_index: int) -> Optional[List[int]]:
+    """Restrict this process (and the threads / pinned allocations it makes from now on: first touch) to the CPU cores
+    NVML reports as local to GPU ``device_index``.  The reference's worker pool leaves placement to the OS with every
+    worker on ``cuda:0`` (pointcloud_pipeline.py:629-714); with one process per GPU on a two-socket B200 box a rank
+    whose decode / copy threads sit on the far socket pays for every H2D / D2H byte twice.  Returns the core list, or
+    None when NVML or ``sched_setaffinity`` is unavailable or the mask is empty (nothing is changed then).  If
+    ``CUDA_VISIBLE_DEVICES`` remaps devices, pass the physical index."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 -- placement is an optimisation, never a requirement
+        return None
+
+
+# ----------------------------------------------------------------------------------------------
 # frame selection  (pointcloud_pipeline.py:524-548)
 # ----------------------------------------------------------------------------------------------
 def frame_number(path: str) -> Optional[int]:

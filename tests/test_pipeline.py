@@ -198,3 +198,13 @@ def test_interrupted_multi_rank_resume_partitions_exactly_the_pending_set(tmp_pa
     assert sorted(got[0] + got[1]) == [5, 6, 7, 8, 9]                       # exactly the pending set, no overlap
     merged = json.load(open(out / pipeline.PROGRESS_FILE))
     assert set(merged) == {f"output_{i:04d}.png" for i in range(10)}
+
+
+def test_pin_to_gpu_numa_is_safe_without_a_gpu():
+    """No NVML / no GPU: placement must be a silent no-op that leaves the affinity mask alone."""
+    before = os.sched_getaffinity(0)
+    got = pipeline.pin_to_gpu_numa(0)
+    assert got is None or set(got) <= set(before)
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
