@@ -167,6 +167,11 @@ __device__ __forceinline__ constexpr int arrive_at() { return EXPV == 0 ? 16 : 1
 // that requests K (G + 1) before it waits for V (G)'s stage changes nothing (82.0 us).  An OPTIMISTIC running maximum (no
 // row-maximum pre-pass in blocks 1-4 of a tile: exponentials against the running reference, block maximum tracked inside
 // the exp loop, block redone if the threshold trips; bit-identical results) was slower too: 85.7 us against 83.1 us.
+// So were a SPLIT-COLUMN softmax (two warps per row: 16 softmax warps, each 64 of a block's 128 columns, half-row maxima
+// exchanged per block through shared memory + a 64-thread named barrier, row sums combined per tile; correct at the first
+// run, 101.2 us with / 108.9 us without the polynomial against 81.8 us) and ONE mbarrier arrival per softmax warp instead
+// of one per thread (84.0-85.2 us).  ncu (profiles/r2_ncu_full_vit_block_raw.csv): L2 -> SM traffic 0.53 GB per launch =
+// 6.1 TB/s at lts__throughput 27 % (the qkv GEMM pulls 11.7 TB/s), so the K / V re-reads are not the bound either.
 
 // Debug counter (dp_debug_counter): how many times a softmax warp took the lazy-maximum RESCALE branch.
 __device__ unsigned long long g_attn_rescales;
