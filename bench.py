@@ -305,7 +305,7 @@ def run_ours(args):
 
     from depth_pro import synthetic
 
-    prec = {"bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
+    prec = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
     B = args.batch
     model = depth_pro.DepthPro(device=dev, precision=prec, max_batch=B)
     model.init_weights("stress", SEED)
@@ -329,7 +329,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    lib = _capi.load()
+    lib = _capi.load(model._lib_flavour)
     for _ in range(max(args.warmup, 3)):
         out = model.infer(x_dev)
     barrier()
@@ -407,7 +407,7 @@ def run_ours(args):
                 kernels[nm] = {"launches_per_step": cnt[i] / prof_steps, "ms_per_step": ms[i] / prof_steps,
                                ("GB/s" if i == 3 else "TFLOP/s"): work[i] / (ms[i] * 1e-3) / (1e9 if i == 3 else 1e12)}
         peaks, src = _peaks()
-        if args.dtype == "bf16" and (cnt[0] + cnt[1]):
+        if args.dtype in ("bf16", "fp16") and (cnt[0] + cnt[1]):
             t_ms = ms[0] + ms[1]
             ach = (work[0] + work[1]) / (t_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
@@ -451,7 +451,7 @@ def run_ours(args):
 
     # ---------------- BASELINE video configs as extra keys of the same line (every rank takes part)
     vid = None
-    if not args.no_video and args.dtype == "bf16" and B == 1:
+    if not args.no_video and args.dtype in ("bf16", "fp16") and B == 1:
         vid = {name: video_workload(model, name, rank, world, dist) for name in ("clip1080p", "stream4k")}
 
     # ---------------- CPU baseline: the oracle on the host cores (rank 0, N = 1 only)
@@ -640,7 +640,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1, help="frames per GPU per step")
-    ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--dtype", choices=["bf16", "fp16", "fp32"], default="bf16",
+                    help="bf16 (BASELINE configs[1], default), fp16 (the fp16 build of the library), fp32 (parity mode)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video", action="store_true", help="skip the clip1080p / stream4k keys of the default line")

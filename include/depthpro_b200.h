@@ -41,6 +41,11 @@ enum {
 
 const char* dp_last_error(void);
 int dp_version(void);
+/* The library exists in two flavours built from the same sources: libdepthpro_b200.so stores 16-bit activations and
+ * weights as bfloat16 ("bf16"), libdepthpro_b200_fp16.so as IEEE half ("fp16": what the reference's model.half() means,
+ * src/depth_pro/depth_pro.py:122-123).  DP_PREC_BF16 below selects "the 16-bit mode" of whichever flavour is loaded;
+ * accumulation, the ViT residual stream and all statistics are fp32 in both. */
+const char* dp_act_dtype(void);
 
 /* src/depth_pro/depth_pro.py:72-123  create_model_and_transforms (model construction). */
 int dp_engine_create(int device, int precision, int max_batch, dp_engine** out);

@@ -32,7 +32,8 @@ inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 extern "C" {
 
 const char* dp_last_error(void) { return g_err.c_str(); }
-int dp_version(void) { return 100; }
+int dp_version(void) { return 200; }
+const char* dp_act_dtype(void) { return DP_ACT_NAME; }
 
 int dp_engine_create(int device, int precision, int max_batch, dp_engine** out) {
   return guard([&] {

@@ -91,7 +91,7 @@ __device__ __forceinline__ float ex2(float x) {  // MUFU ex2.approx: 2 ulp, -inf
   return y;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  bf16x2 h = f2_to_h2(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 

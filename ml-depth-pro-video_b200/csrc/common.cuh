@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -12,7 +13,35 @@
 
 namespace dp {
 
+// The engine's 16-bit storage type.  The library is built TWICE from the same sources (build.py): the default flavour
+// stores activations / weights as bfloat16 (libdepthpro_b200.so), -DDP_ACT_FP16 as IEEE half (libdepthpro_b200_fp16.so,
+// what `precision=torch.half` selects: the reference's model.half(), depth_pro.py:122-123).  Accumulation, the ViT
+// residual stream, LayerNorm / softmax statistics and the metric-depth epilogue are fp32 in both.  The type keeps the name
+// `bf16` ("the 16-bit activation type") throughout the sources; everything flavour-specific is in this block: the two
+// conversions, the tcgen05 operand-format bits, the mma.sync operand type and the TMA element type.
+#ifdef DP_ACT_FP16
+typedef __half bf16;
+typedef __half2 bf16x2;
+#define DP_ACT_NAME "fp16"
+#define DP_MMA_SYNC_TYPE "f16"
+#define DP_UMMA_AB_FORMAT 0u  // tcgen05 kind::f16 instruction descriptor: A / B format 0 = F16
+#define DP_TMAP_ELEM CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+__host__ __device__ __forceinline__ bf16x2 f2_to_h2(float a, float b) { return __floats2half2_rn(a, b); }
+__host__ __device__ __forceinline__ float2 h2_to_f2(bf16x2 v) { return __half22float2(v); }
+__host__ __device__ __forceinline__ bf16 f_to_h(float v) { return __float2half_rn(v); }
+__host__ __device__ __forceinline__ float h_to_f(bf16 v) { return __half2float(v); }
+#else
 typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf16x2;
+#define DP_ACT_NAME "bf16"
+#define DP_MMA_SYNC_TYPE "bf16"
+#define DP_UMMA_AB_FORMAT 1u  // A / B format 1 = BF16
+#define DP_TMAP_ELEM CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+__host__ __device__ __forceinline__ bf16x2 f2_to_h2(float a, float b) { return __floats2bfloat162_rn(a, b); }
+__host__ __device__ __forceinline__ float2 h2_to_f2(bf16x2 v) { return __bfloat1622float2(v); }
+__host__ __device__ __forceinline__ bf16 f_to_h(float v) { return __float2bfloat16_rn(v); }
+__host__ __device__ __forceinline__ float h_to_f(bf16 v) { return __bfloat162float(v); }
+#endif
 
 struct Error : std::runtime_error {
   explicit Error(const std::string& m) : std::runtime_error(m) {}

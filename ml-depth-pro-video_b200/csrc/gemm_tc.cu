@@ -144,10 +144,10 @@ __device__ __forceinline__ void load32<bf16>(const bf16* p, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint4 t = q[i];
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+    const bf16x2* h = reinterpret_cast<const bf16x2*>(&t);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float2 f = __bfloat1622float2(h[j]);
+      float2 f = h2_to_f2(h[j]);
       v[8 * i + 2 * j] = f.x, v[8 * i + 2 * j + 1] = f.y;
     }
   }
@@ -162,19 +162,19 @@ __device__ __forceinline__ void store32(bf16* p, const float (&v)[32], bool relu
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint4 t;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+    bf16x2* h = reinterpret_cast<bf16x2*>(&t);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float a = v[8 * i + 2 * j], b = v[8 * i + 2 * j + 1];
       if (relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
-      h[j] = __floats2bfloat162_rn(a, b);
+      h[j] = f2_to_h2(a, b);
     }
     q[i] = t;
   }
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  bf16x2 h = f2_to_h2(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
@@ -281,8 +281,8 @@ __device__ __forceinline__ void load_res(const GemmOp& op, long long m, int n0, 
 }
 
 __device__ __forceinline__ uint32_t relu2(uint32_t packed) {  // max(x, 0) on a bf16 pair
-  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&packed);
-  x = __hmax2(x, __floats2bfloat162_rn(0.f, 0.f));
+  bf16x2 x = *reinterpret_cast<bf16x2*>(&packed);
+  x = __hmax2(x, f2_to_h2(0.f, 0.f));
   return *reinterpret_cast<uint32_t*>(&x);
 }
 
@@ -307,10 +307,10 @@ __device__ __forceinline__ void epi_tma_chunk(const GemmOp& op, const GemmGroup&
   if (has_res) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&resraw[i]);
+      const bf16x2* h = reinterpret_cast<const bf16x2*>(&resraw[i]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h[j]);
+        const float2 f = h2_to_f2(h[j]);
         v[8 * i + 2 * j] += f.x, v[8 * i + 2 * j + 1] += f.y;
       }
     }
@@ -377,7 +377,7 @@ __device__ __forceinline__ void epi_rows4_resid32(float* __restrict__ out, long 
     if (row < cs.nv) {
       *reinterpret_cast<float4*>(p + 4 * i * ld) = o;
       if constexpr (LN_OUT) {
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        const bf16x2 lo = f2_to_h2(o.x, o.y), hi = f2_to_h2(o.z, o.w);
         uint2 pk;
         pk.x = *reinterpret_cast<const uint32_t*>(&lo), pk.y = *reinterpret_cast<const uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(xb + off + 4 * i * ld) = pk;
@@ -932,7 +932,7 @@ CUtensorMap get_tmap(const void* ptr, int rank, const uint64_t* dims, const uint
   for (int i = 0; i < rank; ++i) gd[i] = dims[i], bx[i] = box[i];
   for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
   DP_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16-byte aligned");
-  CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
+  CUresult r = encode_fn()(&tm, DP_TMAP_ELEM, rank, const_cast<void*>(ptr), gd, gs, bx, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");

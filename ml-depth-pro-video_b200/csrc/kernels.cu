@@ -12,13 +12,13 @@ namespace {
 constexpr int IMG = 1536;
 
 __device__ __forceinline__ float to_f(float v) { return v; }
-__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(bf16 v) { return h_to_f(v); }
 template <typename T>
 __device__ __forceinline__ T from_f(float v);
 template <>
 __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <>
-__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return f_to_h(v); }
 
 inline int blocks_for(long long n, int threads) { return static_cast<int>((n + threads - 1) / threads); }
 
@@ -259,11 +259,11 @@ __device__ __forceinline__ void store8(float* dst, const float (&v)[8]) {
 }
 __device__ __forceinline__ void store8(bf16* dst, const float (&v)[8]) {
   uint4 pk;
-  __nv_bfloat162 t;
-  t = __floats2bfloat162_rn(v[0], v[1]), pk.x = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(v[2], v[3]), pk.y = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(v[4], v[5]), pk.z = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(v[6], v[7]), pk.w = *reinterpret_cast<uint32_t*>(&t);
+  bf16x2 t;
+  t = f2_to_h2(v[0], v[1]), pk.x = *reinterpret_cast<uint32_t*>(&t);
+  t = f2_to_h2(v[2], v[3]), pk.y = *reinterpret_cast<uint32_t*>(&t);
+  t = f2_to_h2(v[4], v[5]), pk.z = *reinterpret_cast<uint32_t*>(&t);
+  t = f2_to_h2(v[6], v[7]), pk.w = *reinterpret_cast<uint32_t*>(&t);
   *reinterpret_cast<uint4*>(dst) = pk;
 }
 
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     if (sizeof(T) == 4) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + e) = v[i];
     } else {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x, v[i].y), hi = __floats2bfloat162_rn(v[i].z, v[i].w);
+      bf16x2 lo = f2_to_h2(v[i].x, v[i].y), hi = f2_to_h2(v[i].z, v[i].w);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(256) ln_stats_cast_kernel(const float* __restr
   for (int i = 0; i < 8; ++i) {
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     q += fmaf(v[i].x, v[i].x, v[i].y * v[i].y) + fmaf(v[i].z, v[i].z, v[i].w * v[i].w);
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(v[i].x, v[i].y), hi = __floats2bfloat162_rn(v[i].z, v[i].w);
+    const bf16x2 lo = f2_to_h2(v[i].x, v[i].y), hi = f2_to_h2(v[i].z, v[i].w);
     uint2 pk;
     pk.x = *reinterpret_cast<const uint32_t*>(&lo), pk.y = *reinterpret_cast<const uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(xb + d * 1024 + (lane + 32 * i) * 4) = pk;
@@ -454,9 +454,9 @@ __global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ 
   float cs = 0.f, ds = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const float wv = w[static_cast<long long>(n) * K + k];
-    const bf16 r = __float2bfloat16_rn(g[k] * wv);
+    const bf16 r = f_to_h(g[k] * wv);
     wf[static_cast<long long>(n) * K + k] = r;
-    cs += __bfloat162float(r);
+    cs += h_to_f(r);
     ds = fmaf(b_ln[k], wv, ds);
   }
   __shared__ float red[2][8];
@@ -482,7 +482,7 @@ __global__ void ln_apply_from_stats_kernel(const bf16* __restrict__ xb, const fl
   for (int i = 0; i < LN_SLOTS; ++i) s += stats[(m * LN_SLOTS + i) * 2], q += stats[(m * LN_SLOTS + i) * 2 + 1];
   const float mean = s * (1.f / 1024.f);
   const float var = fmaxf(q * (1.f / 1024.f) - mean * mean, 0.f);
-  y[idx] = (__bfloat162float(xb[idx]) - mean) * (1.f / sqrtf(var + 1e-6f));
+  y[idx] = (h_to_f(xb[idx]) - mean) * (1.f / sqrtf(var + 1e-6f));
 }
 
 __global__ void merge_f32_kernel(const float* __restrict__ in, float* __restrict__ out, long long total, int C,
@@ -958,7 +958,7 @@ __global__ void compose_head_w_kernel(const float* __restrict__ w1, const float*
         acc = fmaf(w1[((ci * 128 + c1) * 2 + dy) * 2 + dx], w2[((c2 * 128 + c1) * 3 + ky) * 3 + kx], acc);
     }
   }
-  wc[idx] = __float2bfloat16_rn(acc);
+  wc[idx] = f_to_h(acc);
 }
 __global__ void compose_head_b_kernel(const float* __restrict__ b1, const float* __restrict__ w2,
                                       const float* __restrict__ b2, float* __restrict__ cb) {
@@ -980,7 +980,7 @@ __global__ void compose_deconv_kernel(const float* __restrict__ wd, const float*
   const int ci = idx % C, n = idx / C, cop = n % C, q = n / C, dy = q >> 1, dx = q & 1;
   float acc = 0.f;
   for (int co = 0; co < C; ++co) acc = fmaf(wo[cop * C + co], wd[((ci * C + co) * 2 + dy) * 2 + dx], acc);
-  wc[idx] = __float2bfloat16_rn(acc);
+  wc[idx] = f_to_h(acc);
 }
 
 }  // namespace
@@ -1074,7 +1074,7 @@ __global__ void fill_random_bf16_kernel(uint16_t* __restrict__ p, long long n, u
   unsigned h = static_cast<unsigned>(i) * 2654435761u ^ seed;
   h ^= h >> 16, h *= 0x7feb352du, h ^= h >> 15, h *= 0x846ca68bu, h ^= h >> 16;
   const float v = static_cast<float>(h >> 8) * (2.f / 16777216.f) - 1.f;
-  const bf16 b = __float2bfloat16_rn(v);
+  const bf16 b = f_to_h(v);
   p[i] = *reinterpret_cast<const uint16_t*>(&b);
 }
 void fill_random_bf16(void* p, size_t bytes, unsigned seed, cudaStream_t s) {

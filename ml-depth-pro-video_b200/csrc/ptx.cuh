@@ -7,6 +7,8 @@
 #include <cuda.h>
 #include <stdint.h>
 
+#include "common.cuh"  // DP_UMMA_AB_FORMAT: the library's 16-bit flavour
+
 namespace dp {
 namespace ptx {
 
@@ -351,10 +353,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), both K-major,
-// N>>3 at [17,23), M>>4 at [24,29).
+// Instruction descriptor, kind::f16: D=f32 (1<<4), A and B format at [7,10) / [10,13) (1 = bf16, 0 = fp16: the
+// library's 16-bit flavour, common.cuh), both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+  return (1u << 4) | (DP_UMMA_AB_FORMAT << 7) | (DP_UMMA_AB_FORMAT << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdepthpro_b200.so")
+LIB_PATH = os.path.join(_HERE, "libdepthpro_b200.so")            # 16-bit mode = bfloat16 (also serves fp32 mode)
+LIB_PATH_FP16 = os.path.join(_HERE, "libdepthpro_b200_fp16.so")  # same sources, 16-bit mode = IEEE half
 
 PREC_FP32, PREC_BF16 = 0, 1
 SRC_F32_CHW, SRC_U8_HWC = 0, 1
@@ -24,6 +25,7 @@ _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 SIGNATURES = {
     "dp_last_error": (C.c_char_p, []),
     "dp_version": (_i, []),
+    "dp_act_dtype": (C.c_char_p, []),
     "dp_engine_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),
     "dp_engine_create_ex": (_i, [_i, _i, _i, _i, C.POINTER(_vp)]),
     "dp_engine_destroy": (_i, [_vp]),
@@ -54,28 +56,32 @@ SIGNATURES = {
     "dp_launch_count": (_i64, [_vp]),
 }
 
-_lib = None
+_libs = {}
 
 
-def load() -> C.CDLL:
-    """Load the shared library (once) and declare every prototype."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def load(flavour: str = "bf16") -> C.CDLL:
+    """Load a flavour of the shared library (once each) and declare every prototype."""
+    if flavour not in _libs:
+        path = {"bf16": LIB_PATH, "fp16": LIB_PATH_FP16}[flavour]
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} not found: build it with `python ml-depth-pro-video_b200/build.py` "
+                f"{path} not found: build it with `python ml-depth-pro-video_b200/build.py` "
                 "(there is no CPU / PyTorch fallback)")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        _lib = lib
-    return _lib
+        if lib.dp_act_dtype().decode() != flavour:
+            raise RuntimeError(f"{path} reports 16-bit type {lib.dp_act_dtype().decode()!r}, expected {flavour!r}")
+        _libs[flavour] = lib
+    return _libs[flavour]
 
 
-def check(rc: int) -> None:
+def check(rc: int, lib: C.CDLL = None) -> None:
+    """Raise with the failing library's message (each flavour keeps its own thread-local error string)."""
     if rc != 0:
-        raise RuntimeError("depthpro_b200: " + load().dp_last_error().decode(errors="replace"))
+        msgs = [l.dp_last_error().decode(errors="replace") for l in ([lib] if lib is not None else _libs.values())]
+        raise RuntimeError("depthpro_b200: " + " | ".join(m for m in msgs if m))
 
 
 def ptr(t) -> int:

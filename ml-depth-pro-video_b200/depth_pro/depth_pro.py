@@ -60,11 +60,15 @@ def _precision_code(precision: torch.dtype) -> int:
     if precision == torch.float32:
         return _capi.PREC_FP32
     if precision in (torch.bfloat16, torch.float16):
-        if precision == torch.float16:
-            LOGGER.warning("float16 requested: the B200 engine's reduced-precision mode is bfloat16 "
-                           "(fp32 accumulate); running that.")
-        return _capi.PREC_BF16
-    raise ValueError(f"unsupported precision {precision}; use torch.float32 or torch.bfloat16")
+        return _capi.PREC_BF16   # "the 16-bit mode" of the library flavour `_flavour` selects
+    raise ValueError(f"unsupported precision {precision}; use torch.float32, torch.float16 or torch.bfloat16")
+
+
+def _flavour(precision: torch.dtype) -> str:
+    """Which build of the engine serves this precision: torch.half (the reference's `model.half()`, depth_pro.py:122-123)
+    runs on libdepthpro_b200_fp16.so (16-bit storage = IEEE half), everything else on libdepthpro_b200.so (bfloat16 /
+    fp32).  Both keep fp32 accumulation, an fp32 ViT residual stream and fp32 statistics."""
+    return "fp16" if precision == torch.float16 else "bf16"
 
 
 class DepthPro(nn.Module):
@@ -85,6 +89,7 @@ class DepthPro(nn.Module):
         self._device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
         self._precision = precision
         self._prec_code = _precision_code(precision)
+        self._lib_flavour = _flavour(precision)
         self._max_batch = int(max_batch)
         self._engine = None
         self._dirty = True
@@ -129,7 +134,7 @@ class DepthPro(nn.Module):
         return self
 
     def _ensure_engine(self, batch: int):
-        lib = _capi.load()
+        lib = _capi.load(self._lib_flavour)
         if self._engine is not None and batch > self._max_batch:
             _capi.check(lib.dp_engine_destroy(self._engine))
             self._engine = None
@@ -157,7 +162,7 @@ class DepthPro(nn.Module):
     def __del__(self):
         try:
             if getattr(self, "_engine", None) is not None:
-                _capi.load().dp_engine_destroy(self._engine)
+                _capi.load(self._lib_flavour).dp_engine_destroy(self._engine)
                 self._engine = None
         except Exception:
             pass
@@ -247,7 +252,7 @@ class DepthPro(nn.Module):
         return out[: n.value]
 
     def launch_count(self) -> int:
-        return int(_capi.load().dp_launch_count(self._engine))
+        return int(_capi.load(self._lib_flavour).dp_launch_count(self._engine))
 
 
 def create_backbone_model(preset: ViTPreset):

@@ -9,17 +9,17 @@ from depth_pro import _capi
 _engines = {}
 
 
-def lib():
-    return _capi.load()
+def lib(flavour="bf16"):
+    return _capi.load(flavour)
 
 
-def engine(prec=_capi.PREC_FP32):
+def engine(prec=_capi.PREC_FP32, flavour="bf16"):
     """A bare engine (no weights) — enough for the kernel-level entry points."""
-    if prec not in _engines:
+    if (prec, flavour) not in _engines:
         h = ctypes.c_void_p()
-        _capi.check(lib().dp_engine_create(0, prec, 1, ctypes.byref(h)))
-        _engines[prec] = h
-    return _engines[prec]
+        _capi.check(lib(flavour).dp_engine_create(0, prec, 1, ctypes.byref(h)))
+        _engines[(prec, flavour)] = h
+    return _engines[(prec, flavour)]
 
 
 def stream():

@@ -233,6 +233,46 @@ def test_attention(backend, n, tol):
     assert relerr(out, ref) < tol
 
 
+def test_fp16_flavour_cores():
+    """The fp16 build of the library (16-bit storage = IEEE half, `precision=torch.half`): tcgen05 GEMM, implicit-GEMM
+    conv and attention against fp64 references on the FP16-rounded inputs -- proves the operand-format bits of the
+    instruction descriptor, the TMA element type and every pack / unpack switched together."""
+    L, E = lib("fp16"), engine(_capi.PREC_FP32, "fp16")
+    assert L.dp_act_dtype() == b"fp16"
+    g = torch.Generator(device=DEV).manual_seed(9)
+    M, N, K = 1155, 512, 1024
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    C = torch.empty(M, N, device=DEV)
+    _capi.check(L.dp_gemm_test(E, 1, A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 0, stream()), L)
+    torch.cuda.synchronize()
+    ref16 = A.half().double() @ W.half().double().t() + b.double()
+    refbf = A.bfloat16().double() @ W.bfloat16().double().t() + b.double()
+    assert relerr(C, ref16) < 2e-5                      # fp32 output: exact up to accumulation order
+    assert relerr(C, refbf) > 1e-4                      # ... and it is NOT the bf16 arithmetic
+    Cb = torch.empty(M, N, device=DEV)                  # 16-bit output through the TMA-store epilogue: half an fp16 ulp
+    _capi.check(L.dp_gemm_test(E, 1, A.data_ptr(), W.data_ptr(), b.data_ptr(), Cb.data_ptr(), M, N, K, 0x100, stream()), L)
+    torch.cuda.synchronize()
+    assert relerr(Cb, ref16) < 6e-4
+    x = torch.randn(1, 48, 48, 128, device=DEV, generator=g)
+    w = torch.randn(256, 128, 3, 3, device=DEV, generator=g) / (9 * 128) ** 0.5
+    y = torch.empty(1, 48, 48, 256, device=DEV)
+    _capi.check(L.dp_conv3x3_test(E, 1, x.data_ptr(), w.data_ptr(), None, y.data_ptr(), 1, 48, 48, 128, 256, stream()), L)
+    torch.cuda.synchronize()
+    refc = F.conv2d(x.permute(0, 3, 1, 2).half().double(), w.half().double(), None, padding=1).permute(0, 2, 3, 1)
+    assert relerr(y, refc) < 2e-5
+    n = 3
+    qkv = torch.randn(n, 577, 3072, device=DEV, generator=g)
+    out = torch.empty(n, 577, 1024, device=DEV)
+    for backend in (1, 2):                              # tcgen05 and mma.sync attention kernels
+        _capi.check(L.dp_attention_test(E, backend, qkv.data_ptr(), out.data_ptr(), n, stream()), L)
+        torch.cuda.synchronize()
+        q, k, v = qkv.half().double().reshape(n, 577, 3, 16, 64).permute(2, 0, 3, 1, 4)
+        ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(n, 577, 1024)
+        assert relerr(out, ref) < 1e-3, backend          # fp16 P and output: 8x finer than the bf16 kernel's 4e-3
+
+
 def _attn_variant(expv, pingpong, qkv):
     """Run the tcgen05 kernel in variant `expv`, then switch back to the default (the switch is process-wide)."""
     n = qkv.shape[0]

@@ -298,6 +298,40 @@ def test_bf16_layernorm_fold_matches_standalone_layernorm(model_bf16, oracle_run
     del plain_model
 
 
+def test_fp16_mode_vs_oracle(state_dict, oracle_run, model_bf16, golden_dir):
+    """VERDICT r1 missing #4: `precision=torch.half` (the reference's model.half(), depth_pro.py:122-123) runs a TRUE fp16
+    engine (libdepthpro_b200_fp16.so: the same sources with IEEE-half storage, fp32 accumulation / residual stream /
+    statistics).  Against the fp32 oracle it must meet the bf16 tolerance with room to spare -- the reference's own
+    all-fp16 arithmetic measures median 3.3e-4 on this frame (profiles/r2_reduced_precision_probe.json) -- and it must
+    really be a different arithmetic from the bf16 engine."""
+    x, ref, taps = oracle_run
+    m = _model(state_dict, torch.float16)
+    assert m._lib_flavour == "fp16"
+    pred = m.infer(x.to(DEV))
+    depth = pred["depth"].cpu()
+    ok = (ref["depth"] < 1e4 - 1) & (depth < 1e4 - 1)
+    rel = _pix_rel(depth, ref["depth"])[ok].float()
+    q = torch.quantile(rel[:: max(1, rel.numel() // 1_000_000)], torch.tensor([0.5, 0.99]))
+    f_rel = abs(float(pred["focallength_px"]) - float(ref["focallength_px"])) / float(ref["focallength_px"])
+    print(f"fp16: depth abs-rel median {float(q[0]):.3e} p99 {float(q[1]):.3e} max {float(rel.max()):.3e}; f_px rel {f_rel:.3e}")
+    for name in ("lat0_merged", "x0_merged", "enc0", "enc4", "decoder_out"):
+        r = taps[name]
+        got = m.tap(name).cpu().reshape(r.shape)
+        print(f"  tap {name:14s} rms-err/rms {float((got - r).pow(2).mean().sqrt() / r.pow(2).mean().sqrt()):.3e}")
+    assert float(q[0]) <= 1e-3 and float(q[1]) <= 5e-3 and float(rel.max()) <= 2e-2
+    assert f_rel <= 1e-3 and float((~ok).float().mean()) <= 1e-3
+    bf = model_bf16.infer(x.to(DEV))["depth"].cpu()
+    assert not torch.equal(bf, depth)
+    assert float(_pix_rel(bf, ref["depth"])[ok].float().median()) > float(q[0])      # fp16 is the closer one here
+    # uint8 video frame through the fp16 engine vs the reference's recorded output
+    gold = np.load(os.path.join(golden_dir, "reference_outputs.npz"))
+    p2 = m.infer(torch.from_numpy(O.synthetic_frame_u8(0)))
+    r2 = _pix_rel(p2["depth"].cpu()[::16, ::16], torch.from_numpy(gold["depth_1080p"])).float()
+    assert float(r2.median()) <= 1e-3 and float(r2.max()) <= 2e-2
+    del m
+    torch.cuda.empty_cache()
+
+
 def test_interpolation_mode_bicubic(model_fp32, state_dict):
     """VERDICT r1 missing #2: DepthPro.infer(interpolation_mode="bicubic") (depth_pro.py:247, 273-279, 288-291) against the
     oracle in fp32, down- and up-sampling in one call (540x960 -> 1536^2 -> 540x960), tolerance of the fp32 mode."""

@@ -42,10 +42,11 @@ def test_capi_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "depthpro_b200.h")).read()
     declared = set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
-    lib = _capi.load()  # loads without a GPU; no compute call is made here
-    for name in declared:
-        assert hasattr(lib, name), name
-    assert lib.dp_version() >= 100
+    for flavour in ("bf16", "fp16"):   # both builds of the library (16-bit storage = bfloat16 / IEEE half)
+        lib = _capi.load(flavour)      # loads without a GPU; no compute call is made here
+        for name in declared:
+            assert hasattr(lib, name), (flavour, name)
+        assert lib.dp_version() >= 200 and lib.dp_act_dtype().decode() == flavour
 
 
 def test_engine_create_fails_loudly_without_gpu():
