@@ -26,9 +26,27 @@ typedef __half2 bf16x2;
 #define DP_MMA_SYNC_TYPE "f16"
 #define DP_UMMA_AB_FORMAT 0u  // tcgen05 kind::f16 instruction descriptor: A / B format 0 = F16
 #define DP_TMAP_ELEM CU_TENSOR_MAP_DATA_TYPE_FLOAT16
-__host__ __device__ __forceinline__ bf16x2 f2_to_h2(float a, float b) { return __floats2half2_rn(a, b); }
+// float -> half conversions SATURATE to +-65504 on the device (F2FP.SATFINITE, one instruction like the plain form): fp16
+// has no headroom above 65504, and an activation outlier must not turn into inf and poison a whole row of a GEMM.
+__host__ __device__ __forceinline__ bf16x2 f2_to_h2(float a, float b) {
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // d = {hi: %1, lo: %2}
+  return *reinterpret_cast<bf16x2*>(&r);
+#else
+  return __floats2half2_rn(a, b);
+#endif
+}
 __host__ __device__ __forceinline__ float2 h2_to_f2(bf16x2 v) { return __half22float2(v); }
-__host__ __device__ __forceinline__ bf16 f_to_h(float v) { return __float2half_rn(v); }
+__host__ __device__ __forceinline__ bf16 f_to_h(float v) {
+#ifdef __CUDA_ARCH__
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return *reinterpret_cast<bf16*>(&r);
+#else
+  return __float2half_rn(v);
+#endif
+}
 __host__ __device__ __forceinline__ float h_to_f(bf16 v) { return __half2float(v); }
 #else
 typedef __nv_bfloat16 bf16;

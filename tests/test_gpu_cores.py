@@ -255,6 +255,13 @@ def test_fp16_flavour_cores():
     _capi.check(L.dp_gemm_test(E, 1, A.data_ptr(), W.data_ptr(), b.data_ptr(), Cb.data_ptr(), M, N, K, 0x100, stream()), L)
     torch.cuda.synchronize()
     assert relerr(Cb, ref16) < 6e-4
+    # fp16 has no headroom above 65504: 16-bit outputs saturate (F2FP.SATFINITE) instead of turning into inf
+    A2 = A.clone()
+    A2[0] *= 3e4
+    _capi.check(L.dp_gemm_test(E, 1, A2.data_ptr(), W.data_ptr(), b.data_ptr(), Cb.data_ptr(), M, N, K, 0x100, stream()), L)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(Cb).all()) and float(Cb[0].abs().max()) == 65504.0
+    assert relerr(Cb[1:], ref16[1:]) < 6e-4
     x = torch.randn(1, 48, 48, 128, device=DEV, generator=g)
     w = torch.randn(256, 128, 3, 3, device=DEV, generator=g) / (9 * 128) ** 0.5
     y = torch.empty(1, 48, 48, 256, device=DEV)
