@@ -11,9 +11,14 @@
 // It is computed EXACTLY, without sorting, by a segmented radix select on order-preserving 32-bit keys:
 // three histogram passes (11 + 11 + 10 bits) narrow every cell's k-th smallest key, one more pass finds the
 // next larger key when the (k+1)-th order statistic is not a duplicate, and numpy's linear interpolation
-// (lib/_function_base_impl.py _lerp) finishes in double.
+// (lib/_function_base_impl.py _lerp) finishes in double.  Since round 2 each entry point is ONE cooperative
+// kernel (grid-wide barriers between the phases) working on a compacted copy of the percentile's population.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace dp {
 namespace {
@@ -44,43 +49,25 @@ __device__ __forceinline__ float key2f(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// MODE 0: one cell; population = heights y of the points with |dist| < 0.1     (:947)
-// MODE 1: cell = cells[i]; population = heights y < 0.2 of each cell            (:1058)
-template <int MODE>
-__device__ __forceinline__ bool in_population(const float* __restrict__ xyz, const double* __restrict__ dist,
-                                              const unsigned short* __restrict__ cells, long long i, int& cell, float& y) {
-  y = xyz[3 * i + 1];
-  if (MODE == 0) {
-    cell = 0;
-    return fabs(dist[i]) < 0.1;
-  }
-  cell = cells[i];
-  return static_cast<double>(y) < 0.2;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(T) sel_count_kernel(const float* __restrict__ xyz, const double* __restrict__ dist,
-                                                      const unsigned short* __restrict__ cells, long long n, SelCell* st) {
-  for (long long i = blockIdx.x * static_cast<long long>(T) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * T) {
-    int c;
-    float y;
-    const bool in = in_population<MODE>(xyz, dist, cells, i, c, y);
-    if (MODE == 1) {
-      atomicAdd(&st[c].count_all, 1u);
-      if (in) atomicAdd(&st[c].count, 1u);
-    } else {
-      // one cell: warp-aggregate before touching the single counter
-      const unsigned b = __ballot_sync(__activemask(), in);
-      if (in && (threadIdx.x & 31) == __ffs(b) - 1) atomicAdd(&st[0].count, static_cast<unsigned>(__popc(b)));
-    }
-  }
-}
+// ---- second generation (round 2): ONE cooperative launch per entry point ---------------------------------------------
+// Round 1 ran 12 (normalise) / 16 (grid adjustment) launches, each re-reading all n points (24 B of xyz + dist per point
+// and pass): 197 / 308 us for a 1080p cloud, 0.04 / 0.017 of the copy bandwidth.  Now each entry point is one persistent
+// kernel launched with cudaLaunchCooperativeKernel; its phases are separated by grid-wide barriers:
+//   * the first sweep over the points does the geometry AND compacts the percentile's population into a dense array of
+//     32-bit order-preserving keys (+ cell ids), so the three radix-select passes and the next-key pass read 4-6 bytes per
+//     POPULATION element instead of 24 bytes per point;
+//   * the plane distances survive as one flag byte per point instead of a double;
+//   * the single-block / per-cell scans between the passes are done by the blocks themselves after a barrier.
+// The arithmetic (double, same operation order) and therefore every output bit is unchanged: the golden and oracle tests
+// of round 1 run against it as they are.  Data another block wrote in an earlier phase is read with __ldcg (L2): L1 is not
+// coherent across the grid barrier.
+struct SelParams {
+  double q;
+  unsigned min_all, min_pop;
+};
 
 // numpy percentile, method 'linear': virtual index = n q + (1 - q) - 1, k = floor, gamma = fraction
-__global__ void sel_begin_kernel(SelCell* st, int ncells, double q, unsigned min_all, unsigned min_pop) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncells) return;
-  SelCell& s = st[c];
+__device__ __forceinline__ void sel_begin(SelCell& s, double q, unsigned min_all, unsigned min_pop) {
   s.active = (s.count_all >= min_all && s.count >= min_pop && s.count > 0) ? 1 : 0;
   s.prefix = 0, s.less = 0, s.eq = 0, s.next = 0xffffffffu, s.value = 0.0;
   if (!s.active) return;
@@ -93,111 +80,89 @@ __global__ void sel_begin_kernel(SelCell* st, int ncells, double q, unsigned min
   s.rank = s.k;
   s.gamma = v - fl;
 }
-
-// histogram of the next digit over the elements whose fixed bits match the cell's prefix
-template <int MODE>
-__global__ void __launch_bounds__(T) sel_hist_kernel(const float* __restrict__ xyz, const double* __restrict__ dist,
-                                                     const unsigned short* __restrict__ cells, long long n,
-                                                     const SelCell* __restrict__ st, unsigned* __restrict__ hist, int shift,
-                                                     int bits, unsigned fixed_mask) {
-  __shared__ unsigned sh[MODE == 0 ? SEL_BINS : 1];
-  if (MODE == 0) {
-    for (int b = threadIdx.x; b < SEL_BINS; b += T) sh[b] = 0;
-    __syncthreads();
-  }
-  const unsigned dmask = (1u << bits) - 1u;
-  for (long long i = blockIdx.x * static_cast<long long>(T) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * T) {
-    int c;
-    float y;
-    if (!in_population<MODE>(xyz, dist, cells, i, c, y)) continue;
-    if (!st[c].active) continue;
-    const unsigned key = f2key(y);
-    if ((key & fixed_mask) != st[c].prefix) continue;
-    const unsigned dgt = (key >> shift) & dmask;
-    if (MODE == 0) atomicAdd(&sh[dgt], 1u);
-    else atomicAdd(&hist[static_cast<size_t>(c) * SEL_BINS + dgt], 1u);
-  }
-  if (MODE == 0) {
-    __syncthreads();
-    for (int b = threadIdx.x; b < SEL_BINS; b += T)
-      if (sh[b]) atomicAdd(&hist[b], sh[b]);
-  }
+// State in GLOBAL memory (LOCAL = false): every field other blocks may have updated since this SM last touched the cell is
+// read through L2.  LOCAL = true: the block's own copy in shared memory.
+template <typename V>
+__device__ __forceinline__ V ld_state(const V* p, bool local) { return local ? *p : __ldcg(p); }
+template <bool LOCAL = false>
+__device__ __forceinline__ void sel_finish(SelCell& s) {
+  if (!ld_state(&s.active, LOCAL)) return;
+  const unsigned prefix = ld_state(&s.prefix, LOCAL), less = ld_state(&s.less, LOCAL), eq = ld_state(&s.eq, LOCAL),
+                 next = ld_state(&s.next, LOCAL), k = ld_state(&s.k, LOCAL), count = ld_state(&s.count, LOCAL);
+  const double a = static_cast<double>(key2f(prefix));
+  double b = a;
+  // ranks less .. less + eq - 1 hold the k-th key; the (k+1)-th is a duplicate unless k is the last of them
+  if (k + 1 >= less + eq && k + 1 < count && next != 0xffffffffu) b = static_cast<double>(key2f(next));
+  // numpy _lerp: a + (b - a) t, evaluated from the other end for t >= 0.5
+  const double diff = __dadd_rn(b, -a), t = ld_state(&s.gamma, LOCAL);
+  double r = __dadd_rn(a, __dmul_rn(diff, t));
+  if (t >= 0.5) r = __dadd_rn(b, -__dmul_rn(diff, __dadd_rn(1.0, -t)));
+  if (t == 0.0) r = a;  // numpy's gamma == 0 short cut keeps the lower statistic exactly
+  s.value = r;
 }
-
-// one block per cell: find the digit whose cumulative count crosses the residual rank, clear the histogram
-__global__ void __launch_bounds__(T) sel_scan_kernel(SelCell* st, unsigned* hist, int shift, int bits, int last) {
-  const int c = blockIdx.x;
-  SelCell& s = st[c];
-  unsigned* h = hist + static_cast<size_t>(c) * SEL_BINS;
-  __shared__ unsigned part[T];
+// One block: the digit of cell `s` whose cumulative count crosses the residual rank; clears the histogram row (LOCAL: the
+// state is the block's shared-memory copy, the histogram is shared by all blocks and left alone).
+// All T threads of the block call it (contains __syncthreads); `part` is T + 2 words of shared memory.
+template <bool LOCAL = false>
+__device__ void sel_scan_block(SelCell* sp, unsigned* h, int shift, int bits, int last, unsigned* part) {
   const int nb = 1 << bits, per = SEL_BINS / T;  // 8 consecutive bins per thread
   unsigned loc[SEL_BINS / T];
   unsigned sum = 0;
 #pragma unroll
   for (int j = 0; j < per; ++j) {
     const int b = threadIdx.x * per + j;
-    loc[j] = b < nb ? h[b] : 0u;
+    loc[j] = b < nb ? __ldcg(&h[b]) : 0u;
     sum += loc[j];
-    h[b] = 0;
+    if (!LOCAL) h[b] = 0;
   }
+  const int active = ld_state(&sp->active, LOCAL);
+  const unsigned rank = ld_state(&sp->rank, LOCAL);
+  __syncthreads();  // `part` may still be in use by the previous call
   part[threadIdx.x] = sum;
   __syncthreads();
-  if (!s.active) return;
+  if (!active) return;
   if (threadIdx.x == 0) {
     unsigned acc = 0;
     int t = 0;
     for (; t < T; ++t) {
-      if (acc + part[t] > s.rank) break;
+      if (acc + part[t] > rank) break;
       acc += part[t];
     }
-    part[0] = static_cast<unsigned>(t < T ? t : T - 1);  // thread that owns the crossing
-    part[1] = acc;
+    part[T] = static_cast<unsigned>(t < T ? t : T - 1);  // thread that owns the crossing
+    part[T + 1] = acc;
   }
   __syncthreads();
-  if (threadIdx.x == static_cast<int>(part[0])) {
-    unsigned acc = part[1];
+  if (threadIdx.x == static_cast<int>(part[T])) {
+    unsigned acc = part[T + 1];
     int j = 0;
     for (; j < per - 1; ++j) {
-      if (acc + loc[j] > s.rank) break;
+      if (acc + loc[j] > rank) break;
       acc += loc[j];
     }
     const unsigned dgt = static_cast<unsigned>(threadIdx.x * per + j);
-    s.prefix |= dgt << shift;
-    s.less += acc;
-    s.rank -= acc;
-    if (last) s.eq = loc[j];
+    sp->prefix = ld_state(&sp->prefix, LOCAL) | (dgt << shift);
+    sp->less = ld_state(&sp->less, LOCAL) + acc;
+    sp->rank = rank - acc;
+    if (last) sp->eq = loc[j];
   }
 }
 
-// smallest population key greater than the k-th key (needed when the (k+1)-th statistic is not a duplicate)
-template <int MODE>
-__global__ void __launch_bounds__(T) sel_next_kernel(const float* __restrict__ xyz, const double* __restrict__ dist,
-                                                     const unsigned short* __restrict__ cells, long long n, SelCell* st) {
-  for (long long i = blockIdx.x * static_cast<long long>(T) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * T) {
-    int c;
-    float y;
-    if (!in_population<MODE>(xyz, dist, cells, i, c, y)) continue;
-    if (!st[c].active) continue;
-    const unsigned key = f2key(y);
-    if (key > st[c].prefix && key < st[c].next) atomicMin(&st[c].next, key);
-  }
-}
-
-__global__ void sel_finish_kernel(SelCell* st, int ncells) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncells) return;
-  SelCell& s = st[c];
-  if (!s.active) return;
-  const double a = static_cast<double>(key2f(s.prefix));
-  double b = a;
-  // ranks less .. less + eq - 1 hold the k-th key; the (k+1)-th is a duplicate unless k is the last of them
-  if (s.k + 1 >= s.less + s.eq && s.k + 1 < s.count && s.next != 0xffffffffu) b = static_cast<double>(key2f(s.next));
-  // numpy _lerp: a + (b - a) t, evaluated from the other end for t >= 0.5
-  const double diff = __dadd_rn(b, -a), t = s.gamma;
-  double r = __dadd_rn(a, __dmul_rn(diff, t));
-  if (t >= 0.5) r = __dadd_rn(b, -__dmul_rn(diff, __dadd_rn(1.0, -t)));
-  if (t == 0.0) r = a;  // numpy's gamma == 0 short cut keeps the lower statistic exactly
-  s.value = r;
+// Append `key` (+ cell) to THIS BLOCK's segment of the compact population arrays.  Every block owns the same points in
+// every phase, so its population lives in a private segment `seg` = [blockIdx.x * cap, ...) and is counted in shared
+// memory: no global atomic per element (one same-address global atomic per warp was what round 1's count pass, and the
+// first version of this kernel, spent most of their time on).
+__device__ __forceinline__ void pop_append(bool in, unsigned key, unsigned short cell, unsigned* s_count,
+                                           unsigned* __restrict__ seg_keys, unsigned short* __restrict__ seg_cell) {
+  const unsigned b = __ballot_sync(0xffffffffu, in);
+  if (!b) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(b) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(s_count, static_cast<unsigned>(__popc(b)));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (!in) return;
+  const unsigned pos = base + __popc(b & ((1u << lane) - 1u));
+  seg_keys[pos] = key;
+  if (seg_cell) seg_cell[pos] = cell;
 }
 
 struct GroundXf {
@@ -207,42 +172,136 @@ struct GroundXf {
   double shift;   // y offset of the rotated plane: -d / (R normal).y, 0 without rotation
 };
 
-// distances to the plane, rotation, plane to y = const   (:900-945)
-__global__ void __launch_bounds__(T) ground_transform_kernel(float* __restrict__ xyz, double* __restrict__ dist, long long n,
-                                                             const GroundXf xf) {
-  const long long i = blockIdx.x * static_cast<long long>(T) + threadIdx.x;
-  if (i >= n) return;
-  const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-  // np.dot(points, normal) + d
-  dist[i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, xf.n[0]), __dmul_rn(y, xf.n[1])), __dmul_rn(z, xf.n[2])), xf.d);
-  const double rx = __dadd_rn(__dadd_rn(__dmul_rn(xf.r[0], x), __dmul_rn(xf.r[1], y)), __dmul_rn(xf.r[2], z));
-  const double ry = __dadd_rn(__dadd_rn(__dmul_rn(xf.r[3], x), __dmul_rn(xf.r[4], y)), __dmul_rn(xf.r[5], z));
-  const double rz = __dadd_rn(__dadd_rn(__dmul_rn(xf.r[6], x), __dmul_rn(xf.r[7], y)), __dmul_rn(xf.r[8], z));
-  xyz[3 * i] = static_cast<float>(rx);
-  xyz[3 * i + 1] = static_cast<float>(__dadd_rn(ry, -xf.shift));
-  xyz[3 * i + 2] = static_cast<float>(rz);
-}
 
-// ground level shift + clamps   (:947-972)
-__global__ void __launch_bounds__(T) ground_clamp_kernel(float* __restrict__ xyz, const double* __restrict__ dist, long long n,
-                                                         const SelCell* __restrict__ st, unsigned long long* __restrict__ counters) {
-  const long long i = blockIdx.x * static_cast<long long>(T) + threadIdx.x;
-  if (i >= n) return;
-  double y = xyz[3 * i + 1];
-  if (st[0].count > 10) y = __dadd_rn(y, -st[0].value);   // "if len(ground_y_values) > 10"
-  const bool ground = fabs(dist[i]) < 0.05;
-  const bool to_zero = y < 0.0 && ground;
-  if (to_zero) y = 0.0;
-  const bool to_floor = y < -0.1 && !ground;
-  if (to_floor) y = -0.1;
-  xyz[3 * i + 1] = static_cast<float>(y);
-  // the reference prints these three counts; kept for the caller's log
-  const unsigned bg = __ballot_sync(__activemask(), ground), bz = __ballot_sync(__activemask(), to_zero),
-                 bf = __ballot_sync(__activemask(), to_floor);
-  if ((threadIdx.x & 31) == 0) {
-    if (bg) atomicAdd(&counters[0], static_cast<unsigned long long>(__popc(bg)));
-    if (bz) atomicAdd(&counters[1], static_cast<unsigned long long>(__popc(bz)));
-    if (bf) atomicAdd(&counters[2], static_cast<unsigned long long>(__popc(bf)));
+struct NormArgs {
+  float* xyz;
+  long long n;
+  GroundXf xf;
+  uint8_t* flags;             // bit 0: |dist| < 0.1 (population of the percentile), bit 1: |dist| < 0.05 ("ground")
+  unsigned* keys;             // compact population: order-preserving keys of the rotated heights, one segment per block
+  long long seg;              // segment capacity (points a block owns)
+  unsigned* pop_count;
+  unsigned* next_key;         // smallest population key above the k-th one (starts at 0xffffffff)
+  SelCell* st;                // one cell
+  unsigned* hist;             // 3 x SEL_BINS: one histogram per radix pass
+  unsigned long long* counters;
+};
+
+// normalize_point_cloud_to_ground (:880-975) in one cooperative launch
+__global__ void __launch_bounds__(T) ground_normalize_kernel(const NormArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ unsigned sh[SEL_BINS];
+  __shared__ unsigned part[T + 2];
+  __shared__ unsigned s_pop;                 // this block's population count (kept across the phases)
+  const long long stride = static_cast<long long>(gridDim.x) * T;
+  const GroundXf& xf = a.xf;
+  unsigned* seg_keys = a.keys + blockIdx.x * a.seg;
+  if (threadIdx.x == 0) s_pop = 0;
+  __syncthreads();
+  // ---- phase 0: distances to the plane, rotation, plane to y = const (:900-945); population -> compact keys
+  for (long long i0 = blockIdx.x * static_cast<long long>(T); i0 < a.n; i0 += stride) {
+    const long long i = i0 + threadIdx.x;
+    bool in = false;
+    unsigned key = 0;
+    if (i < a.n) {
+      const double x = a.xyz[3 * i], y = a.xyz[3 * i + 1], z = a.xyz[3 * i + 2];
+      // np.dot(points, normal) + d
+      const double dist = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, xf.n[0]), __dmul_rn(y, xf.n[1])), __dmul_rn(z, xf.n[2])), xf.d);
+      const double rx = __dadd_rn(__dadd_rn(__dmul_rn(xf.r[0], x), __dmul_rn(xf.r[1], y)), __dmul_rn(xf.r[2], z));
+      const double ry = __dadd_rn(__dadd_rn(__dmul_rn(xf.r[3], x), __dmul_rn(xf.r[4], y)), __dmul_rn(xf.r[5], z));
+      const double rz = __dadd_rn(__dadd_rn(__dmul_rn(xf.r[6], x), __dmul_rn(xf.r[7], y)), __dmul_rn(xf.r[8], z));
+      const float yn = static_cast<float>(__dadd_rn(ry, -xf.shift));
+      a.xyz[3 * i] = static_cast<float>(rx);
+      a.xyz[3 * i + 1] = yn;
+      a.xyz[3 * i + 2] = static_cast<float>(rz);
+      in = fabs(dist) < 0.1;
+      a.flags[i] = static_cast<uint8_t>((in ? 1 : 0) | (fabs(dist) < 0.05 ? 2 : 0));
+      key = f2key(yn);
+    }
+    pop_append(in, key, 0, &s_pop, seg_keys, nullptr);
+  }
+  __syncthreads();
+  const unsigned mine = s_pop;
+  if (threadIdx.x == 0 && mine) atomicAdd(a.pop_count, mine);
+  grid.sync();
+  // ---- phase 1: exact 2nd percentile of the population by radix select.  Every block keeps ITS OWN copy of the (single)
+  // cell's select state in shared memory and scans the shared histogram of a pass itself (one histogram per pass, never
+  // cleared): one grid barrier per pass instead of two.
+  const unsigned M = __ldcg(a.pop_count);
+  __shared__ SelCell cs;
+  if (threadIdx.x == 0) {
+    cs = SelCell();
+    cs.count_all = M, cs.count = M;
+    sel_begin(cs, 0.02, 0, 1);
+  }
+  __syncthreads();
+  const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+  unsigned fixed = 0;
+  if (M > 0) {
+    for (int p = 0; p < 3; ++p) {
+      for (int b = threadIdx.x; b < SEL_BINS; b += T) sh[b] = 0;
+      __syncthreads();
+      const unsigned prefix = cs.prefix, dmask = (1u << bits[p]) - 1u;
+      for (unsigned i = threadIdx.x; i < mine; i += T) {
+        const unsigned key = seg_keys[i];
+        if ((key & fixed) == prefix) atomicAdd(&sh[(key >> shifts[p]) & dmask], 1u);
+      }
+      __syncthreads();
+      unsigned* hist = a.hist + p * SEL_BINS;
+      for (int b = threadIdx.x; b < SEL_BINS; b += T)
+        if (sh[b]) atomicAdd(&hist[b], sh[b]);
+      grid.sync();
+      sel_scan_block<true>(&cs, hist, shifts[p], bits[p], p == 2, part);
+      __syncthreads();
+      fixed |= dmask << shifts[p];
+    }
+    // smallest population key greater than the k-th key (needed when the (k+1)-th statistic is not a duplicate)
+    const unsigned kth = cs.prefix;
+    unsigned nx = 0xffffffffu;
+    for (unsigned i = threadIdx.x; i < mine; i += T) {
+      const unsigned key = seg_keys[i];
+      if (key > kth && key < nx) nx = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nx = min(nx, __shfl_xor_sync(0xffffffffu, nx, o));
+    if ((threadIdx.x & 31) == 0 && nx != 0xffffffffu) atomicMin(a.next_key, nx);
+    grid.sync();
+    if (threadIdx.x == 0) {
+      cs.next = __ldcg(a.next_key);
+      sel_finish<true>(cs);
+      if (blockIdx.x == 0) *a.st = cs;   // for the record (tests / debugging read the state back)
+    }
+    __syncthreads();
+  }
+  // ---- phase 2: ground level shift + clamps (:947-972)
+  const bool apply = M > 10;                       // "if len(ground_y_values) > 10"
+  const double value = cs.value;
+  unsigned n_ground = 0, n_zero = 0, n_floor = 0;  // the reference prints these three counts; kept for the caller's log
+  for (long long i0 = blockIdx.x * static_cast<long long>(T); i0 < a.n; i0 += stride) {
+    const long long i = i0 + threadIdx.x;
+    bool ground = false, to_zero = false, to_floor = false;
+    if (i < a.n) {
+      double y = a.xyz[3 * i + 1];
+      if (apply) y = __dadd_rn(y, -value);
+      ground = (a.flags[i] & 2) != 0;
+      to_zero = y < 0.0 && ground;
+      if (to_zero) y = 0.0;
+      to_floor = y < -0.1 && !ground;
+      if (to_floor) y = -0.1;
+      a.xyz[3 * i + 1] = static_cast<float>(y);
+    }
+    n_ground += ground, n_zero += to_zero, n_floor += to_floor;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_ground += __shfl_xor_sync(0xffffffffu, n_ground, o);
+    n_zero += __shfl_xor_sync(0xffffffffu, n_zero, o);
+    n_floor += __shfl_xor_sync(0xffffffffu, n_floor, o);
+  }
+  if ((threadIdx.x & 31) == 0) {   // one atomic per warp and counter for the whole kernel
+    if (n_ground) atomicAdd(&a.counters[0], static_cast<unsigned long long>(n_ground));
+    if (n_zero) atomicAdd(&a.counters[1], static_cast<unsigned long long>(n_zero));
+    if (n_floor) atomicAdd(&a.counters[2], static_cast<unsigned long long>(n_floor));
   }
 }
 
@@ -255,39 +314,6 @@ __device__ __forceinline__ double key2d(unsigned long long k) {
   return __longlong_as_double(static_cast<long long>((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
 }
 
-__global__ void bounds_init_kernel(unsigned long long* b) {
-  b[0] = b[2] = 0xffffffffffffffffull;  // x min, z min
-  b[1] = b[3] = 0ull;                   // x max, z max
-}
-__global__ void __launch_bounds__(T) bounds_kernel(const float* __restrict__ xyz, long long n, unsigned long long* b) {
-  unsigned long long lo_x = 0xffffffffffffffffull, hi_x = 0, lo_z = lo_x, hi_z = 0;
-  for (long long i = blockIdx.x * static_cast<long long>(T) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * T) {
-    const unsigned long long kx = dkey(static_cast<double>(xyz[3 * i])), kz = dkey(static_cast<double>(xyz[3 * i + 2]));
-    lo_x = kx < lo_x ? kx : lo_x, hi_x = kx > hi_x ? kx : hi_x;
-    lo_z = kz < lo_z ? kz : lo_z, hi_z = kz > hi_z ? kz : hi_z;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long t;
-    t = __shfl_xor_sync(0xffffffffu, lo_x, o), lo_x = t < lo_x ? t : lo_x;
-    t = __shfl_xor_sync(0xffffffffu, hi_x, o), hi_x = t > hi_x ? t : hi_x;
-    t = __shfl_xor_sync(0xffffffffu, lo_z, o), lo_z = t < lo_z ? t : lo_z;
-    t = __shfl_xor_sync(0xffffffffu, hi_z, o), hi_z = t > hi_z ? t : hi_z;
-  }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&b[0], lo_x), atomicMax(&b[1], hi_x), atomicMin(&b[2], lo_z), atomicMax(&b[3], hi_z);
-  }
-}
-// np.linspace(lo, hi, g + 1): step = (hi - lo) / g, edge[i] = i * step + lo, last edge = hi exactly
-__global__ void edges_kernel(const unsigned long long* __restrict__ b, double* __restrict__ edges, int g) {
-  const int i = threadIdx.x;
-  if (i > g) return;
-  for (int a = 0; a < 2; ++a) {
-    const double lo = key2d(b[2 * a]), hi = key2d(b[2 * a + 1]);
-    const double step = __ddiv_rn(__dadd_rn(hi, -lo), static_cast<double>(g));
-    edges[a * (g + 1) + i] = i == g ? hi : __dadd_rn(__dmul_rn(static_cast<double>(i), step), lo);
-  }
-}
 // np.digitize(v, edges) - 1 clipped to [0, g - 1]; digitize = number of edges <= v (edges increasing)
 __device__ __forceinline__ int bin_of(double v, const double* __restrict__ e, int g) {
   int lo = 0, hi = g + 1;  // first index with e[idx] > v
@@ -300,103 +326,263 @@ __device__ __forceinline__ int bin_of(double v, const double* __restrict__ e, in
   bin = bin < 0 ? 0 : bin;
   return bin > g - 1 ? g - 1 : bin;
 }
-__global__ void __launch_bounds__(T) cells_kernel(const float* __restrict__ xyz, long long n, const double* __restrict__ edges,
-                                                  int g, unsigned short* __restrict__ cells) {
-  extern __shared__ double se[];
-  for (int i = threadIdx.x; i < 2 * (g + 1); i += T) se[i] = edges[i];
+
+constexpr int PRIV_CELLS = 2048;   // grids up to 45 x 45 keep their per-cell counters in shared memory (16 KB)
+struct GridArgs {
+  float* xyz;
+  long long n;
+  int g;                      // grid_size
+  double q;                   // percentile / 100
+  unsigned short* cells;      // cell of every point
+  unsigned* keys;             // compact population (heights y < 0.2): keys ...
+  unsigned short* kcell;      // ... and their cells, one segment per block
+  long long seg;
+  unsigned* pop_count;
+  SelCell* st;                // g * g cells
+  unsigned* hist;             // g * g * SEL_BINS
+  unsigned long long* bounds; // x min, z min, x max, z max (order-preserving keys of doubles)
+  double* edges;              // 2 * (g + 1)
+  unsigned long long* counters;
+};
+
+// grid_based_ground_adjustment (:977-1118) in one cooperative launch
+__global__ void __launch_bounds__(T) ground_grid_kernel(const GridArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double se[];            // 2 * (g + 1) edges, then (small grids) 2 * ncells per-block cell counters
+  __shared__ unsigned part[T + 2];
+  __shared__ unsigned s_pop;
+  __shared__ unsigned long long s_box[4];
+  const int g = a.g, ncells = g * g;
+  const long long stride = static_cast<long long>(gridDim.x) * T;
+  const long long first = blockIdx.x * static_cast<long long>(T) + threadIdx.x;
+  unsigned* seg_keys = a.keys + blockIdx.x * a.seg;
+  unsigned short* seg_cell = a.kcell + blockIdx.x * a.seg;
+  const bool priv = ncells <= PRIV_CELLS;   // per-block counters in shared memory instead of one global atomic per point
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(se + 2 * (g + 1));
+  if (threadIdx.x == 0) s_pop = 0, s_box[0] = s_box[1] = 0xffffffffffffffffull, s_box[2] = s_box[3] = 0ull;
+  if (priv)
+    for (int c = threadIdx.x; c < 2 * ncells; c += T) s_cnt[c] = 0;
   __syncthreads();
-  const long long i = blockIdx.x * static_cast<long long>(T) + threadIdx.x;
-  if (i >= n) return;
-  const int bx = bin_of(static_cast<double>(xyz[3 * i]), se, g), bz = bin_of(static_cast<double>(xyz[3 * i + 2]), se + g + 1, g);
-  cells[i] = static_cast<unsigned short>(bx * g + bz);
-}
-// per-cell lowering with the height-graded factor, clamp at y = 0   (:1067-1106)
-__global__ void __launch_bounds__(T) grid_apply_kernel(float* __restrict__ xyz, long long n,
-                                                       const unsigned short* __restrict__ cells,
-                                                       const SelCell* __restrict__ st, unsigned long long* __restrict__ counters) {
-  const long long i = blockIdx.x * static_cast<long long>(T) + threadIdx.x;
-  if (i >= n) return;
-  const SelCell& s = st[cells[i]];
-  if (!s.active || !(s.value > 0.01)) return;
-  const double y = xyz[3 * i + 1], p = s.value;
-  double adj = 0.0;
-  if (y < 0.1) adj = p;
-  else if (y < 1.5) adj = __dmul_rn(p, __dadd_rn(1.0, -__ddiv_rn(__dadd_rn(y, -0.1), 1.4)));
-  double out = __dadd_rn(y, -adj);
-  if (out < 0.0) out = 0.0;
-  xyz[3 * i + 1] = static_cast<float>(out);
-  if (adj > 0.0) atomicAdd(&counters[3], 1ull);
-}
-__global__ void grid_stats_kernel(const SelCell* __restrict__ st, int ncells, unsigned long long* __restrict__ counters) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncells) return;
-  if (st[c].count_all >= 10) atomicAdd(&counters[4], 1ull);          // cells with sufficient points
-  if (st[c].active && st[c].value > 0.01) atomicAdd(&counters[5], 1ull);  // cells requiring adjustment
-}
-
-int grid_blocks(long long n) {
-  const long long b = (n + T - 1) / T;
-  return static_cast<int>(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
-}
-
-template <int MODE>
-void select_percentile(const float* xyz, const double* dist, const unsigned short* cells, long long n, SelCell* st,
-                       unsigned* hist, int ncells, double q, unsigned min_all, unsigned min_pop, cudaStream_t s) {
-  const int gb = grid_blocks(n);
-  sel_count_kernel<MODE><<<gb, T, 0, s>>>(xyz, dist, cells, n, st);
-  DP_LAUNCH_CHECK();
-  sel_begin_kernel<<<(ncells + 127) / 128, 128, 0, s>>>(st, ncells, q, min_all, min_pop);
-  DP_LAUNCH_CHECK();
+  // ---- phase 0: XZ bounding box (:1009-1018)
+  {
+    unsigned long long lo_x = 0xffffffffffffffffull, hi_x = 0, lo_z = lo_x, hi_z = 0;
+    for (long long i = first; i < a.n; i += stride) {
+      const unsigned long long kx = dkey(static_cast<double>(a.xyz[3 * i])), kz = dkey(static_cast<double>(a.xyz[3 * i + 2]));
+      lo_x = kx < lo_x ? kx : lo_x, hi_x = kx > hi_x ? kx : hi_x;
+      lo_z = kz < lo_z ? kz : lo_z, hi_z = kz > hi_z ? kz : hi_z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long t;
+      t = __shfl_xor_sync(0xffffffffu, lo_x, o), lo_x = t < lo_x ? t : lo_x;
+      t = __shfl_xor_sync(0xffffffffu, hi_x, o), hi_x = t > hi_x ? t : hi_x;
+      t = __shfl_xor_sync(0xffffffffu, lo_z, o), lo_z = t < lo_z ? t : lo_z;
+      t = __shfl_xor_sync(0xffffffffu, hi_z, o), hi_z = t > hi_z ? t : hi_z;
+    }
+    if ((threadIdx.x & 31) == 0)
+      atomicMin(&s_box[0], lo_x), atomicMin(&s_box[1], lo_z), atomicMax(&s_box[2], hi_x), atomicMax(&s_box[3], hi_z);
+    __syncthreads();
+    if (threadIdx.x == 0)   // one global atomic per block and bound
+      atomicMin(&a.bounds[0], s_box[0]), atomicMin(&a.bounds[1], s_box[1]), atomicMax(&a.bounds[2], s_box[2]),
+          atomicMax(&a.bounds[3], s_box[3]);
+  }
+  grid.sync();
+  // ---- phase 1: np.linspace edges (every block its own copy), cell of every point, per-cell counts, population
+  for (int i = threadIdx.x; i <= g; i += T) {
+    for (int ax = 0; ax < 2; ++ax) {
+      const double lo = key2d(__ldcg(&a.bounds[ax])), hi = key2d(__ldcg(&a.bounds[2 + ax]));
+      const double step = __ddiv_rn(__dadd_rn(hi, -lo), static_cast<double>(g));
+      const double e = i == g ? hi : __dadd_rn(__dmul_rn(static_cast<double>(i), step), lo);
+      se[ax * (g + 1) + i] = e;
+      if (blockIdx.x == 0) a.edges[ax * (g + 1) + i] = e;
+    }
+  }
+  __syncthreads();
+  for (long long i0 = blockIdx.x * static_cast<long long>(T); i0 < a.n; i0 += stride) {
+    const long long i = i0 + threadIdx.x;
+    bool in = false;
+    unsigned key = 0;
+    unsigned short c = 0;
+    if (i < a.n) {
+      const int bx = bin_of(static_cast<double>(a.xyz[3 * i]), se, g), bz = bin_of(static_cast<double>(a.xyz[3 * i + 2]), se + g + 1, g);
+      c = static_cast<unsigned short>(bx * g + bz);
+      a.cells[i] = c;
+      const float y = a.xyz[3 * i + 1];
+      in = static_cast<double>(y) < 0.2;                              // the cell's low points (:1058)
+      key = f2key(y);
+      if (priv) {
+        atomicAdd(&s_cnt[2 * c], 1u);
+        if (in) atomicAdd(&s_cnt[2 * c + 1], 1u);
+      } else {
+        atomicAdd(&a.st[c].count_all, 1u);
+        if (in) atomicAdd(&a.st[c].count, 1u);
+      }
+    }
+    pop_append(in, key, c, &s_pop, seg_keys, seg_cell);
+  }
+  __syncthreads();
+  if (priv)
+    for (int c = threadIdx.x; c < ncells; c += T) {
+      if (s_cnt[2 * c]) atomicAdd(&a.st[c].count_all, s_cnt[2 * c]);
+      if (s_cnt[2 * c + 1]) atomicAdd(&a.st[c].count, s_cnt[2 * c + 1]);
+    }
+  const unsigned mine = s_pop;
+  grid.sync();
+  // cells with >= 10 points and >= 5 low points (:1046, :1061); np.percentile(lowest_y, percentile)
+  for (long long c = first; c < ncells; c += stride) sel_begin(a.st[c], a.q, 10, 5);
+  grid.sync();
+  // Small grids keep a per-block copy of the cells' select state in shared memory (the 8 bytes per cell the counters
+  // used), refreshed after every grid barrier: per-element __ldcg reads of a few hundred hot lines were the bottleneck.
+  unsigned* s_pref = s_cnt;                                             // [ncells] key bits fixed so far
+  uint8_t* s_act = reinterpret_cast<uint8_t*>(s_cnt + ncells);          // [ncells] cell takes part in the selection
+  unsigned* s_next = s_cnt + ncells;                                    // [ncells] (next-key pass) block-local minimum
+  double* s_val = reinterpret_cast<double*>(s_cnt);                     // [ncells] (apply pass) amount to lower by, 0 = none
+  auto load_state = [&]() {
+    __syncthreads();
+    if (priv)
+      for (int c = threadIdx.x; c < ncells; c += T) s_pref[c] = __ldcg(&a.st[c].prefix), s_act[c] = __ldcg(&a.st[c].active) != 0;
+    __syncthreads();
+  };
   const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
   unsigned fixed = 0;
   for (int p = 0; p < 3; ++p) {
-    sel_hist_kernel<MODE><<<gb, T, 0, s>>>(xyz, dist, cells, n, st, hist, shifts[p], bits[p], fixed);
-    DP_LAUNCH_CHECK();
-    sel_scan_kernel<<<ncells, T, 0, s>>>(st, hist, shifts[p], bits[p], p == 2);
-    DP_LAUNCH_CHECK();
-    fixed |= ((1u << bits[p]) - 1u) << shifts[p];
+    const unsigned dmask = (1u << bits[p]) - 1u;
+    load_state();
+    // consecutive points of an unprojected frame are image neighbours: same cell, similar height, so most lanes of a
+    // warp hit the SAME (cell, digit) bin -- lanes with equal bins elect one to add their count (same-address global
+    // atomics serialise in L2; one per lane was what this pass spent its time on)
+    for (unsigned base = threadIdx.x & ~31u; base < mine; base += T) {
+      const unsigned i = base + (threadIdx.x & 31);
+      unsigned tag = 0xffffffffu;
+      if (i < mine) {
+        const unsigned key = seg_keys[i];
+        const unsigned c = seg_cell[i];
+        const bool act = priv ? s_act[c] != 0 : __ldcg(&a.st[c].active) != 0;
+        const unsigned pref = priv ? s_pref[c] : __ldcg(&a.st[c].prefix);
+        if (act && (key & fixed) == pref) tag = c * SEL_BINS + ((key >> shifts[p]) & dmask);
+      }
+      const unsigned same = __match_any_sync(0xffffffffu, tag);
+      if (tag != 0xffffffffu && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&a.hist[tag], static_cast<unsigned>(__popc(same)));
+    }
+    grid.sync();
+    for (int c = blockIdx.x; c < ncells; c += gridDim.x)
+      sel_scan_block(&a.st[c], a.hist + static_cast<size_t>(c) * SEL_BINS, shifts[p], bits[p], p == 2, part);
+    grid.sync();
+    fixed |= dmask << shifts[p];
   }
-  sel_next_kernel<MODE><<<gb, T, 0, s>>>(xyz, dist, cells, n, st);
-  DP_LAUNCH_CHECK();
-  sel_finish_kernel<<<(ncells + 127) / 128, 128, 0, s>>>(st, ncells);
-  DP_LAUNCH_CHECK();
+  // smallest population key greater than the k-th key, per cell
+  __syncthreads();
+  if (priv)
+    for (int c = threadIdx.x; c < ncells; c += T)
+      s_pref[c] = __ldcg(&a.st[c].active) ? __ldcg(&a.st[c].prefix) : 0xffffffffu, s_next[c] = 0xffffffffu;   // inactive: nothing is greater
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < mine; i += T) {
+    const unsigned key = seg_keys[i];
+    const int c = seg_cell[i];
+    if (priv) {
+      if (key > s_pref[c] && key < s_next[c]) atomicMin(&s_next[c], key);
+    } else {
+      if (!__ldcg(&a.st[c].active)) continue;
+      if (key > __ldcg(&a.st[c].prefix) && key < __ldcg(&a.st[c].next)) atomicMin(&a.st[c].next, key);
+    }
+  }
+  __syncthreads();
+  if (priv)
+    for (int c = threadIdx.x; c < ncells; c += T)
+      if (s_next[c] != 0xffffffffu) atomicMin(&a.st[c].next, s_next[c]);
+  grid.sync();
+  for (long long c = first; c < ncells; c += stride) {
+    sel_finish(a.st[c]);
+    if (__ldcg(&a.st[c].count_all) >= 10) atomicAdd(&a.counters[4], 1ull);                    // cells with sufficient points
+    if (__ldcg(&a.st[c].active) && a.st[c].value > 0.01) atomicAdd(&a.counters[5], 1ull);    // cells requiring adjustment
+  }
+  grid.sync();
+  // ---- per-cell lowering with the height-graded factor, clamp at y = 0   (:1067-1106)
+  __syncthreads();
+  if (priv)
+    for (int c = threadIdx.x; c < ncells; c += T) s_val[c] = __ldcg(&a.st[c].active) ? __ldcg(&a.st[c].value) : 0.0;
+  __syncthreads();
+  unsigned lowered = 0;
+  for (long long i = first; i < a.n; i += stride) {
+    const int c = a.cells[i];
+    double p;
+    if (priv) {
+      p = s_val[c];
+    } else {
+      if (!__ldcg(&a.st[c].active)) continue;
+      p = __ldcg(&a.st[c].value);
+    }
+    if (!(p > 0.01)) continue;
+    const double y = a.xyz[3 * i + 1];
+    double adj = 0.0;
+    if (y < 0.1) adj = p;
+    else if (y < 1.5) adj = __dmul_rn(p, __dadd_rn(1.0, -__ddiv_rn(__dadd_rn(y, -0.1), 1.4)));
+    double out = __dadd_rn(y, -adj);
+    if (out < 0.0) out = 0.0;
+    a.xyz[3 * i + 1] = static_cast<float>(out);
+    if (adj > 0.0) ++lowered;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lowered += __shfl_xor_sync(0xffffffffu, lowered, o);
+  if ((threadIdx.x & 31) == 0 && lowered) atomicAdd(&a.counters[3], static_cast<unsigned long long>(lowered));
+}
+
+// persistent grid of a cooperative launch: every block must be resident
+template <typename K>
+int coop_blocks(K kernel, size_t smem, long long n) {
+  int dev = 0, sms = 0, per_sm = 0;
+  DP_CUDA(cudaGetDevice(&dev));
+  DP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, T, smem));
+  DP_CHECK(per_sm >= 1, "ground kernels: no resident block fits");
+  long long want = (n + T - 1) / T;
+  const long long cap = static_cast<long long>(sms) * (per_sm > 4 ? 4 : per_sm);
+  want = want < 1 ? 1 : (want > cap ? cap : want);
+  return static_cast<int>(want);
 }
 
 }  // namespace
 
-size_t ground_scratch_bytes(long long n, int grid_size) {
-  const size_t cells = static_cast<size_t>(grid_size) * grid_size;
-  size_t b = 0;
-  b += (static_cast<size_t>(n) * 8 + 255) & ~size_t(255);                  // dist (double)
-  b += (static_cast<size_t>(n) * 2 + 255) & ~size_t(255);                  // cell index
-  b += (cells * sizeof(SelCell) + 255) & ~size_t(255);                     // select state
-  b += cells * SEL_BINS * 4;                                               // histograms
-  b += 256 + (2 * (static_cast<size_t>(grid_size) + 1) * 8 + 255) / 256 * 256;  // bounds, edges
-  return b + 256;
-}
-
 namespace {
+inline size_t up256(size_t v) { return (v + 255) & ~size_t(255); }
+// per-block population segments: blocks * ceil(n / (blocks * T)) * T <= n + blocks * T entries, blocks <= 4 per SM
+constexpr size_t SEG_SLACK = 256 * 4 * T;
 struct Scratch {
-  double* dist;
+  uint8_t* flags;             // normalise: one flag byte per point  |  grid: uint16 cell per point (same storage)
   unsigned short* cells;
+  unsigned* keys;             // compact population keys (at most n)
+  unsigned short* kcell;      // their cells (grid adjustment)
   SelCell* st;
   unsigned* hist;
+  unsigned* pop_count;        // misc block: +0 population counter, +64 bounds (4 x u64), +128 spare counters (6 x u64)
   unsigned long long* bounds;
+  unsigned long long* spare;
   double* edges;
 };
 Scratch carve(void* base, long long n, int grid_size) {
   const size_t cells = static_cast<size_t>(grid_size) * grid_size;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   Scratch sc;
-  sc.dist = reinterpret_cast<double*>(p), p += (static_cast<size_t>(n) * 8 + 255) & ~size_t(255);
-  sc.cells = reinterpret_cast<unsigned short*>(p), p += (static_cast<size_t>(n) * 2 + 255) & ~size_t(255);
-  sc.st = reinterpret_cast<SelCell*>(p), p += (cells * sizeof(SelCell) + 255) & ~size_t(255);
-  sc.hist = reinterpret_cast<unsigned*>(p), p += cells * SEL_BINS * 4;
-  sc.bounds = reinterpret_cast<unsigned long long*>(p), p += 256;
+  sc.flags = p, sc.cells = reinterpret_cast<unsigned short*>(p), p += up256(static_cast<size_t>(n) * 2);
+  sc.keys = reinterpret_cast<unsigned*>(p), p += up256((static_cast<size_t>(n) + SEG_SLACK) * 4);
+  sc.kcell = reinterpret_cast<unsigned short*>(p), p += up256((static_cast<size_t>(n) + SEG_SLACK) * 2);
+  sc.st = reinterpret_cast<SelCell*>(p), p += up256(cells * sizeof(SelCell));
+  sc.hist = reinterpret_cast<unsigned*>(p), p += (cells < 3 ? 3 : cells) * SEL_BINS * 4;
+  sc.pop_count = reinterpret_cast<unsigned*>(p);
+  sc.bounds = reinterpret_cast<unsigned long long*>(p + 64);
+  sc.spare = reinterpret_cast<unsigned long long*>(p + 128);
+  p += 256;
   sc.edges = reinterpret_cast<double*>(p);
   return sc;
 }
 }  // namespace
+
+size_t ground_scratch_bytes(long long n, int grid_size) {
+  const size_t cells = static_cast<size_t>(grid_size) * grid_size;
+  return up256(static_cast<size_t>(n) * 2) + up256((static_cast<size_t>(n) + SEG_SLACK) * 4) +
+         up256((static_cast<size_t>(n) + SEG_SLACK) * 2) +
+         up256(cells * sizeof(SelCell)) + (cells < 3 ? 3 : cells) * SEL_BINS * 4 + 256 + up256(2 * (static_cast<size_t>(grid_size) + 1) * 8) + 256;
+}
 
 // counters (device, 6 x uint64): [0] ground points (|dist| < 0.05), [1] set to y = 0, [2] limited to -0.1,
 // [3] points lowered by the grid pass, [4] cells with >= 10 points, [5] cells adjusted
@@ -429,14 +615,20 @@ void ground_normalize(float* xyz, long long n, const double normal[3], double d,
     const double rn_y = xf.r[3] * normal[0] + xf.r[4] * normal[1] + xf.r[5] * normal[2];  // (R @ normal)[1], raw normal
     xf.shift = -d / rn_y;
   }
-  DP_CUDA(cudaMemsetAsync(sc.st, 0, sizeof(SelCell), s));
-  DP_CUDA(cudaMemsetAsync(sc.hist, 0, SEL_BINS * 4, s));
+  DP_CHECK(n < (1ll << 32), "ground_normalize: more than 2^32 points");
+  // scratch tail: [3 histograms | misc block]; one memset clears both, a second sets the next-key word (misc + 8) to ~0
+  DP_CUDA(cudaMemsetAsync(sc.hist, 0, 3 * SEL_BINS * 4 + 256, s));
+  DP_CUDA(cudaMemsetAsync(sc.pop_count + 2, 0xff, 4, s));
   if (counters) DP_CUDA(cudaMemsetAsync(counters, 0, 3 * 8, s));
-  const int nb = static_cast<int>((n + T - 1) / T);
-  ground_transform_kernel<<<nb, T, 0, s>>>(xyz, sc.dist, n, xf);
-  DP_LAUNCH_CHECK();
-  select_percentile<0>(xyz, sc.dist, nullptr, n, sc.st, sc.hist, 1, 0.02, 0, 1, s);
-  ground_clamp_kernel<<<nb, T, 0, s>>>(xyz, sc.dist, n, sc.st, counters ? counters : sc.bounds + 8);
+  NormArgs a;
+  a.xyz = xyz, a.n = n, a.xf = xf, a.flags = sc.flags, a.keys = sc.keys, a.pop_count = sc.pop_count, a.st = sc.st;
+  a.next_key = sc.pop_count + 2;
+  a.hist = sc.hist, a.counters = counters ? counters : sc.spare;
+  const int blocks = coop_blocks(ground_normalize_kernel, 0, n);
+  a.seg = (n + static_cast<long long>(blocks) * T - 1) / (static_cast<long long>(blocks) * T) * T;
+  DP_CHECK(static_cast<size_t>(blocks) * a.seg <= static_cast<size_t>(n) + SEG_SLACK, "ground_normalize: segment plan");
+  void* args[] = {&a};
+  DP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(ground_normalize_kernel), dim3(blocks), dim3(T), args, 0, s));
   DP_LAUNCH_CHECK();
 }
 
@@ -444,26 +636,24 @@ void ground_grid_adjust(float* xyz, long long n, int grid_size, double percentil
                         cudaStream_t s) {
   if (n <= 0) return;
   DP_CHECK(grid_size >= 1 && grid_size <= 255, "grid_size must be in 1..255");
+  DP_CHECK(n < (1ll << 32), "ground_grid_adjust: more than 2^32 points");
   const int ncells = grid_size * grid_size;
   Scratch sc = carve(scratch, n, grid_size);
   DP_CUDA(cudaMemsetAsync(sc.st, 0, ncells * sizeof(SelCell), s));
   DP_CUDA(cudaMemsetAsync(sc.hist, 0, static_cast<size_t>(ncells) * SEL_BINS * 4, s));
+  DP_CUDA(cudaMemsetAsync(sc.pop_count, 0, 256, s));
+  DP_CUDA(cudaMemsetAsync(sc.bounds, 0xff, 16, s));   // x min, z min start at the largest key; x max, z max at 0
   if (counters) DP_CUDA(cudaMemsetAsync(counters + 3, 0, 3 * 8, s));
-  const int nb = static_cast<int>((n + T - 1) / T);
-  bounds_init_kernel<<<1, 1, 0, s>>>(sc.bounds);
-  DP_LAUNCH_CHECK();
-  bounds_kernel<<<grid_blocks(n), T, 0, s>>>(xyz, n, sc.bounds);
-  DP_LAUNCH_CHECK();
-  edges_kernel<<<1, 256, 0, s>>>(sc.bounds, sc.edges, grid_size);
-  DP_LAUNCH_CHECK();
-  cells_kernel<<<nb, T, 2 * (grid_size + 1) * sizeof(double), s>>>(xyz, n, sc.edges, grid_size, sc.cells);
-  DP_LAUNCH_CHECK();
-  // cells with >= 10 points and >= 5 low points (:1046, :1061); np.percentile(lowest_y, percentile)
-  select_percentile<1>(xyz, nullptr, sc.cells, n, sc.st, sc.hist, ncells, percentile / 100.0, 10, 5, s);
-  unsigned long long* ctr = counters ? counters : sc.bounds + 8;
-  grid_apply_kernel<<<nb, T, 0, s>>>(xyz, n, sc.cells, sc.st, ctr);
-  DP_LAUNCH_CHECK();
-  grid_stats_kernel<<<(ncells + 127) / 128, 128, 0, s>>>(sc.st, ncells, ctr);
+  GridArgs a;
+  a.xyz = xyz, a.n = n, a.g = grid_size, a.q = percentile / 100.0, a.cells = sc.cells, a.keys = sc.keys, a.kcell = sc.kcell;
+  a.pop_count = sc.pop_count, a.st = sc.st, a.hist = sc.hist, a.bounds = sc.bounds, a.edges = sc.edges;
+  a.counters = counters ? counters : sc.spare;
+  const size_t smem = 2 * (static_cast<size_t>(grid_size) + 1) * sizeof(double) + (ncells <= PRIV_CELLS ? 2 * ncells * 4 : 0);
+  const int blocks = coop_blocks(ground_grid_kernel, smem, n);
+  a.seg = (n + static_cast<long long>(blocks) * T - 1) / (static_cast<long long>(blocks) * T) * T;
+  DP_CHECK(static_cast<size_t>(blocks) * a.seg <= static_cast<size_t>(n) + SEG_SLACK, "ground_grid_adjust: segment plan");
+  void* args[] = {&a};
+  DP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(ground_grid_kernel), dim3(blocks), dim3(T), args, smem, s));
   DP_LAUNCH_CHECK();
 }
 
