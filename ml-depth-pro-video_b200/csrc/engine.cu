@@ -984,6 +984,9 @@ void Engine::infer_host(const void* img_host, int B, int H, int W, int src_fmt, 
     DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&hdepth_), out_bytes));
     hdepth_bytes_ = out_bytes;
   }
+  // a synchronous helper on the engine's own stream: work a caller enqueued earlier on ANOTHER stream may still be
+  // using the (single) workspace, so wait for the device first
+  DP_CUDA(cudaDeviceSynchronize());
   cudaStream_t s = host_stream_;
   DP_CUDA(cudaMemcpyAsync(himg_, img_host, in_bytes, cudaMemcpyHostToDevice, s));
   infer(himg_, B, H, W, src_fmt, f_px_host, hdepth_, fpx_, INTERP_BILINEAR, s);

@@ -438,6 +438,29 @@ def test_two_engines_on_two_threads(state_dict, model_bf16):
     torch.cuda.empty_cache()
 
 
+def test_infer_host_entry_point(model_bf16):
+    """`dp_infer_host` (include/depthpro_b200.h: the call generate_depth_maps.py:113-121 amounts to -- host frame in,
+    host depth out, one synchronous C call) equals `model.infer` on the same frame bit for bit, with and without a
+    caller-supplied focal length."""
+    import ctypes
+
+    from depth_pro import _capi
+
+    frame = np.ascontiguousarray(O.synthetic_frame_u8(3, 270, 480))
+    lib = model_bf16._ensure_engine(1)
+    depth = np.empty((270, 480), np.float32)
+    f_out = np.empty((1,), np.float32)
+    _capi.check(lib.dp_infer_host(model_bf16._engine, frame.ctypes.data, 1, 270, 480, _capi.SRC_U8_HWC, None,
+                                  depth.ctypes.data, f_out.ctypes.data), lib)
+    want = model_bf16.infer(torch.from_numpy(frame))
+    assert np.array_equal(depth, want["depth"].cpu().numpy()) and float(f_out[0]) == float(want["focallength_px"])
+    f_in = np.array([777.0], np.float32)
+    _capi.check(lib.dp_infer_host(model_bf16._engine, frame.ctypes.data, 1, 270, 480, _capi.SRC_U8_HWC, f_in.ctypes.data,
+                                  depth.ctypes.data, f_out.ctypes.data), lib)
+    want = model_bf16.infer(torch.from_numpy(frame), f_px=777.0)
+    assert np.array_equal(depth, want["depth"].cpu().numpy()) and float(f_out[0]) == 777.0
+
+
 def test_batch_is_bit_identical(model_bf16):
     """Frames are independent units: a 2-frame batch must equal two single-frame calls bit for bit."""
     frames = np.stack([O.synthetic_frame_u8(i, 540, 960) for i in range(2)])
