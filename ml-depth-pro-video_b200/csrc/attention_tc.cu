@@ -167,6 +167,12 @@ __device__ __forceinline__ constexpr int arrive_at() { return EXPV == 0 ? 16 : 1
 // that requests K (G + 1) before it waits for V (G)'s stage changes nothing (82.0 us).  An OPTIMISTIC running maximum (no
 // row-maximum pre-pass in blocks 1-4 of a tile: exponentials against the running reference, block maximum tracked inside
 // the exp loop, block redone if the threshold trips; bit-identical results) was slower too: 85.7 us against 83.1 us.
+// A second form of it (variant 20, profiles/r2_attention_variant20_optimistic.*) used the scale invariance of floating
+// point instead: NO maximum at all in blocks 1-4 (any reference works as long as nothing overflows), checked after the
+// fact on the row sum the block needs anyway (sum < 2^60, else the block is redone against its true maximum).  Correct
+// (all parity cases, incl. scores growing by 2^36 per block), no spills, 250 cycles less work per block -- and 84.96 us
+// against 82.84: the phase profile shows the exponential phase growing by exactly what the pre-pass lost (1231 -> 1384
+// cycles per block, total 2728 -> 2736).  The period of a stream is NOT set by the softmax warp's own instruction chain.
 // So were a SPLIT-COLUMN softmax (two warps per row: 16 softmax warps, each 64 of a block's 128 columns, half-row maxima
 // exchanged per block through shared memory + a 64-thread named barrier, row sums combined per tile; correct at the first
 // run, 101.2 us with / 108.9 us without the polynomial against 81.8 us) and ONE mbarrier arrival per softmax warp instead
@@ -411,6 +417,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
           PROF_T(2)  // row maximum
           // P and O are single-buffered: the previous block's P V must have retired
+          if (q == 0 && lane == 0) TRACE(14, G);
           if (j > 0) {
             ptx::mbar_wait(pv_done, (G - 1) & 1);
             ptx::tc_fence_after();

@@ -39,15 +39,15 @@ int main() {
   printf("MMA warp, cycles per block (%.0f blocks):\n", mb);
   for (int i = 0; i < 7; ++i) printf("  %-20s %8.1f\n", mn[i], p[15 + i] / mb);
   // event trace of CTA 0 / stream 0 (last launch): cycles relative to the stream's first event
-  const char* ev[14] = {"prod: K req", "prod: V req", "mma: K ready", "mma: s_empty ok", "mma: QK issued", "mma: V ready",
+  const char* ev[15] = {"prod: K req", "prod: V req", "mma: K ready", "mma: s_empty ok", "mma: QK issued", "mma: V ready",
                         "mma: p_full ok", "mma: PV issued", "smx: at s_full", "smx: S ready", "smx: S loaded", "smx: PV(G-1) done",
-                        "smx: MUFU turn", "smx: P published"};
+                        "smx: MUFU turn", "smx: P published", "smx: at pv_done wait"};
   const long long* tr = reinterpret_cast<const long long*>(p + 23);
   long long t0 = tr[0 * 40 + 0];
   printf("event trace, CTA 0 stream 0, cycles since the first K request (columns = key block G):\n%-20s", "event");
   for (int G = 10; G < 22; ++G) printf("%8d", G);
   printf("\n");
-  for (int e = 0; e < 14; ++e) {
+  for (int e = 0; e < 15; ++e) {
     printf("%-20s", ev[e]);
     for (int G = 10; G < 22; ++G) printf("%8lld", tr[e * 40 + G] - t0);
     printf("\n");
