@@ -231,6 +231,10 @@ struct GemmOp {
   const float* ln_stats = nullptr;
   void* ln_xb = nullptr;
   float* ln_stats_out = nullptr;
+  //  * pair-residual producer (`ln_xlo` set; res / out unused): the stream itself lives in 16-bit storage as
+  //    x = hi + lo, hi = round16(x) in `ln_xb` (the consumer's operand, as above), lo = round16(x - hi) in `ln_xlo`,
+  //    both updated in place -- 8 B of traffic per element instead of 10.
+  void* ln_xlo = nullptr;
   // groups
   int ngroups = 1;
   GemmGroup grp[3];

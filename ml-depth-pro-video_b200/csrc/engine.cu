@@ -235,6 +235,10 @@ Engine::Engine(int device, int prec, int max_batch, int fov_mode)
   attn_legacy_ = a != nullptr && std::string(a) == "mma";
   const char* lf = getenv("DEPTHPRO_LN_FUSE");  // debugging switch: "0" keeps the stand-alone LayerNorm launches
   ln_fuse_ = prec_ == BF16 && !(lf != nullptr && lf[0] == '0');
+  // the ViT residual stream as a (hi, lo) pair of 16-bit arrays (common.cuh GemmOp::ln_xlo) instead of fp32 + a 16-bit
+  // copy; needs the folded LayerNorm.  "0" keeps the fp32 stream (A/B, debugging)
+  const char* rp = getenv("DEPTHPRO_RES_PAIR");
+  res_pair_ = ln_fuse_ && !(rp != nullptr && rp[0] == '0');
   DP_CUDA(cudaStreamCreateWithFlags(&host_stream_, cudaStreamNonBlocking));
   const char* ms = getenv("DEPTHPRO_STREAMS");  // "0": no side streams inside a frame
   multi_stream_ = !(ms != nullptr && ms[0] == '0');
@@ -483,6 +487,7 @@ void Engine::finalize() {
   resid_ = (float*)alloc(T * EMB * 4);
   xn_ = alloc(T * EMB * e);
   if (ln_fuse_) ln_stats_ = (float*)alloc(T * LN_SLOTS * 2 * 4);
+  if (res_pair_) xlo_ = alloc(T * EMB * e);
   qkv_ = alloc(T * 3 * EMB * e);
   attn_ = alloc(T * EMB * e);
   hid_ = alloc(T * 4 * EMB * e);
@@ -605,7 +610,10 @@ void Engine::run_vits(int B, cudaStream_t s) {
   // bf16 residual stream, written with its row statistics by this one launch for layer 0 and by the
   // proj / fc2 epilogues from then on
   const bool fuse = ln_fuse_ && std::is_same<T, bf16>::value;
-  if (fuse) ln_stats_cast(resid, (bf16*)xn, ln_stats_, M, s);
+  // pair form: from here on the stream is (xn, xlo) = (hi, lo); the fp32 array only holds the patch-embed output
+  const bool pair = fuse && res_pair_;
+  bf16* xlo = pair ? (bf16*)xlo_ : nullptr;
+  if (fuse) ln_stats_cast(resid, (bf16*)xn, ln_stats_, M, s, xlo);
   for (int i = 0; i < 24; ++i) {
     NvtxRange r_blk("vit.block");
     if (!fuse) {
@@ -635,12 +643,12 @@ void Engine::run_vits(int B, cudaStream_t s) {
     }
     {
       GemmOp op;
-      op.N = EMB, op.K = EMB, op.A = attn, op.lda = EMB;
-      op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
+      op.N = EMB, op.K = EMB, op.A = attn, op.lda = EMB, op.ldo = EMB;
+      if (!pair) op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1;
       grouped(op, SEQ, false);
       for (int g = 0; g < NG; ++g)
         op.grp[g].Wt = vw[g]->blk[i].proj_w, op.grp[g].bias = vw[g]->blk[i].proj_b, op.grp[g].gamma = vw[g]->blk[i].g1;
-      if (fuse) op.ln_xb = xn, op.ln_stats_out = ln_stats_;
+      if (fuse) op.ln_xb = xn, op.ln_stats_out = ln_stats_, op.ln_xlo = xlo;
       gemm(prec_, op, s);
     }
     if (!fuse) {
@@ -661,12 +669,13 @@ void Engine::run_vits(int B, cudaStream_t s) {
     }
     {
       GemmOp op;
-      op.N = EMB, op.K = 4 * EMB, op.A = hid, op.lda = 4 * EMB;
-      op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1, op.ldo = EMB;
+      op.N = EMB, op.K = 4 * EMB, op.A = hid, op.lda = 4 * EMB, op.ldo = EMB;
+      if (!pair) op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1;
       grouped(op, SEQ, false);
       for (int g = 0; g < NG; ++g)
         op.grp[g].Wt = vw[g]->blk[i].fc2_w, op.grp[g].bias = vw[g]->blk[i].fc2_b, op.grp[g].gamma = vw[g]->blk[i].g2;
-      if (fuse && i < 23) op.ln_xb = xn, op.ln_stats_out = ln_stats_;
+      // (the pair form has no fp32 output: the last block writes (hi, lo) + unused row sums like every other)
+      if (fuse && (i < 23 || pair)) op.ln_xb = xn, op.ln_stats_out = ln_stats_, op.ln_xlo = xlo;
       gemm(prec_, op, s);
     }
     if (i == 5 || i == 11) {
@@ -674,7 +683,8 @@ void Engine::run_vits(int B, cudaStream_t s) {
       // stream of the 25 level-0 patches, cls dropped, merged with padding 3 (encoder.py:268-289)
       RowMap m;
       m.mode = 1, m.S = 96, m.steps = 5, m.pad = 3, m.patch_base = 0;
-      layernorm_rows<T>(resid, (T*)(i == 5 ? lat0m_ : lat1m_), nullptr, nullptr, (long long)B * 96 * 96, m, 0, s);
+      layernorm_rows<T>(resid, (T*)(i == 5 ? lat0m_ : lat1m_), nullptr, nullptr, (long long)B * 96 * 96, m, 0, s,
+                        pair ? (const bf16*)xn : nullptr, xlo);
     }
   }
 }
@@ -689,21 +699,23 @@ void Engine::forward_impl(const float* x, int B, float* canon, float* fov_deg, c
   run_vits<T>(B, s);
   {  // final norms fused with the merges (encoder.py:267-305), one launch per consumer
     NvtxRange r("final norm + merge");
+    const bool pair = res_pair_ && std::is_same<T, bf16>::value;  // the stream ended as (xn, xlo) = (hi, lo)
+    const bf16 *hi = pair ? (const bf16*)xn_ : nullptr, *lo = pair ? (const bf16*)xlo_ : nullptr;
     RowMap m;
     m.mode = 1, m.S = 96, m.steps = 5, m.pad = 3, m.patch_base = 0;
-    layernorm_rows<T>(resid_, (T*)x0m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 96 * 96, m, 1, s);
+    layernorm_rows<T>(resid_, (T*)x0m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 96 * 96, m, 1, s, hi, lo);
     m.S = 48, m.steps = 3, m.pad = 6, m.patch_base = 25;
-    layernorm_rows<T>(resid_, (T*)x1m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 48 * 48, m, 1, s);
+    layernorm_rows<T>(resid_, (T*)x1m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 48 * 48, m, 1, s, hi, lo);
     m.S = 24, m.steps = 1, m.pad = 0, m.patch_base = 34;
-    layernorm_rows<T>(resid_, (T*)x2m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 24 * 24, m, 1, s);
+    layernorm_rows<T>(resid_, (T*)x2m_, vit_patch_.norm_w, vit_patch_.norm_b, (long long)B * 24 * 24, m, 1, s, hi, lo);
     // image encoder (encoder.py:308-311) and fov encoder (fov.py:70-77): sequences 35B.. and 36B..
     RowMap ms;
     ms.mode = 1, ms.S = 24, ms.steps = 1, ms.pad = 0, ms.patch_base = 0, ms.sb = 1, ms.sp = 1;
     ms.seq_off = 35 * B;
-    layernorm_rows<T>(resid_, (T*)globm_, vit_image_.norm_w, vit_image_.norm_b, (long long)B * 24 * 24, ms, 1, s);
+    layernorm_rows<T>(resid_, (T*)globm_, vit_image_.norm_w, vit_image_.norm_b, (long long)B * 24 * 24, ms, 1, s, hi, lo);
     if (fov_mode_ == 2) {
       ms.seq_off = 36 * B;
-      layernorm_rows<T>(resid_, (T*)fovtok_, vit_fov_.norm_w, vit_fov_.norm_b, (long long)B * 24 * 24, ms, 1, s);
+      layernorm_rows<T>(resid_, (T*)fovtok_, vit_fov_.norm_w, vit_fov_.norm_b, (long long)B * 24 * 24, ms, 1, s, hi, lo);
     }
   }
   NvtxRange r_dec("decode (encoder upsample, decoder, head, fov)");
@@ -1115,13 +1127,24 @@ void Engine::gemm_test(int backend, const float* A, const float* Wt, const float
       op.grp[0].M = M, op.grp[0].Wt = w, op.grp[0].bias = ln_d, op.grp[0].ln_c = ln_c;
       op.bias = ln_d;
     }
+    // 0x4000 (with 0x200 | 0x2000): the producer in its PAIR form -- C is split into (hi, lo) 16-bit arrays first,
+    //        updated in place by the epilogue, and rebuilt as hi + lo afterwards
+    bf16* ln_xlo = nullptr;
     if (flags & 0x2000) {
       DP_CHECK((flags & 0x200) && N == 1024, "LN producer test: 0x200, N = 1024");
       DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_stats), (size_t)M * LN_SLOTS * 8, s));
       DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_xb), n_out * 2, s));
       op.ln_xb = ln_xb, op.ln_stats_out = ln_stats;
+      if (flags & 0x4000) {
+        DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ln_xlo), n_out * 2, s));
+        ln_stats_cast(C, ln_xb, ln_stats, M, s, ln_xlo);
+        op.ln_xlo = ln_xlo;
+      }
     }
-    if (flags & 0x200) {
+    if (flags & 0x4000) {
+      DP_CHECK(flags & 0x2000, "pair producer test: 0x200 | 0x2000 | 0x4000");
+      op.gamma = bias, op.out = nullptr, op.out_f32 = 0;
+    } else if (flags & 0x200) {
       op.gamma = bias, op.res = C, op.res_f32 = 1, op.ldres = N;
     } else if (flags & (0x100 | 0x400)) {
       DP_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ob), n_out * 2, s));
@@ -1140,8 +1163,9 @@ void Engine::gemm_test(int backend, const float* A, const float* Wt, const float
     }
     gemm_tc(op, s);
     if (ob) convert<bf16, float>((flags & 0x800) ? orelu : ob, C, (long long)n_out, s);
+    if (flags & 0x4000) pair_to_f32(ln_xb, ln_xlo, C, (long long)n_out, s);
     if (flags & 0x2000) ln_apply_from_stats(ln_xb, ln_stats, C + n_out, M, s);
-    for (void* p : {(void*)ln_stats, (void*)ln_c, (void*)ln_d, (void*)ln_g, (void*)ln_b, (void*)ln_xb})
+    for (void* p : {(void*)ln_stats, (void*)ln_c, (void*)ln_d, (void*)ln_g, (void*)ln_b, (void*)ln_xb, (void*)ln_xlo})
       if (p) DP_CUDA(cudaFreeAsync(p, s));
     DP_CUDA(cudaFreeAsync(a, s));
     DP_CUDA(cudaFreeAsync(w, s));
@@ -1256,7 +1280,7 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   // B200, a GEMM on zero-filled operands runs at the full 1965 MHz (913 W), the same kernel on real data is
   // power-capped to ~1.5 GHz -- zeros overstate the sustained rate by ~40 %.
   static const bool zeros = [] { const char* e = getenv("DEPTHPRO_BENCH_DATA"); return e && std::string(e) == "zeros"; }();
-  const bool tensor_kind = kind <= 4 || (kind >= 11 && kind <= 13);
+  const bool tensor_kind = kind <= 4 || (kind >= 11 && kind <= 14);
   auto B = [&](size_t bytes) {
     void* p = dalloc(bytes);
     if (tensor_kind && !zeros && bytes >= 2) fill_random_bf16(p, bytes, 0x9e3779b9u + static_cast<unsigned>(bufs.size()), s);
@@ -1265,11 +1289,15 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   };
   GemmOp op;
   std::function<void()> run;
-  if (kind <= 2 || (kind >= 11 && kind <= 13)) {
-    // 11 / 12 / 13: kinds 0 / 1 / 2 in their LayerNorm-folded forms (consumer, consumer + GELU, producer)
+  if (kind <= 2 || (kind >= 11 && kind <= 14)) {
+    // 11 / 12 / 13: kinds 0 / 1 / 2 in their LayerNorm-folded forms (consumer, consumer + GELU, producer);
+    // 14: the producer over a (hi, lo) 16-bit pair residual stream
     op.M = M, op.N = N, op.K = K, op.lda = K;
     op.A = B((size_t)M * K * 2), op.Wt = B((size_t)N * K * 2), op.bias = (float*)B((size_t)N * 4);
-    if (kind == 2 || kind == 13) {
+    if (kind == 14) {
+      op.gamma = (float*)B((size_t)N * 4), op.ldo = N;
+      op.ln_xb = B((size_t)M * N * 2), op.ln_xlo = B((size_t)M * N * 2), op.ln_stats_out = (float*)B((size_t)M * LN_SLOTS * 8);
+    } else if (kind == 2 || kind == 13) {
       float* r = (float*)B((size_t)M * N * 4);
       op.gamma = (float*)B((size_t)N * 4), op.res = r, op.res_f32 = 1, op.ldres = N, op.out = r, op.out_f32 = 1, op.ldo = N;
       if (kind == 13) op.ln_xb = B((size_t)M * N * 2), op.ln_stats_out = (float*)B((size_t)M * LN_SLOTS * 8);

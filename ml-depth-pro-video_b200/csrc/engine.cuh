@@ -126,6 +126,8 @@ class Engine {
   size_t himg_bytes_ = 0;
   float* hdepth_ = nullptr;
   size_t hdepth_bytes_ = 0;
+  bool res_pair_ = false;      // bf16 mode + folded LayerNorm: residual stream as a (hi, lo) 16-bit pair (DEPTHPRO_RES_PAIR=0 disables)
+  void* xlo_ = nullptr;        // ... its low half (the high half is xn_)
   bool ln_fuse_ = false;       // bf16 mode: LayerNorm folded into qkv / fc1 (DEPTHPRO_LN_FUSE=0 disables)
   float* ln_stats_ = nullptr;  // (tokens, LN_SLOTS, 2) partial row sums of the residual stream
   float* colorize_mm_ = nullptr;

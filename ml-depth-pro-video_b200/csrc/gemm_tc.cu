@@ -402,8 +402,11 @@ __device__ __forceinline__ void epi_rows4_resid32(float* __restrict__ out, long 
 //   EPI_TMA_LN   EPI_TMA for a LayerNorm-folded GEMM (qkv / fc1): acc * rstd[m] - rstd[m] * mean[m] * c[n] + d[n]
 //   EPI_RES32_LN EPI_RES32 that also emits bf16(x) and per-row partial (sum, sum of squares) for the next
 //                LayerNorm-folded GEMM (common.cuh GemmOp::ln_stats)
+//   EPI_RES16_LN the same over a residual stream stored as a (hi, lo) pair of 16-bit arrays, x = hi + lo with
+//                hi = round16(x), lo = round16(x - hi) (GemmOp::ln_xlo): hi IS the next folded GEMM's operand, so the
+//                separate copy disappears -- 4 B read + 4 B written per element instead of 4 + 6
 constexpr int RES_PREFETCH_DEFAULT = 0;  // measured A/B pending: opt-in
-enum { EPI_TMA = 0, EPI_RES32 = 1, EPI_MISC = 2, EPI_TMA2 = 3, EPI_TMA_LN = 4, EPI_RES32_LN = 5 };
+enum { EPI_TMA = 0, EPI_RES32 = 1, EPI_MISC = 2, EPI_TMA2 = 3, EPI_TMA_LN = 4, EPI_RES32_LN = 5, EPI_RES16_LN = 6 };
 
 template <int BN, int CL, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -665,7 +668,113 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
         continue;
       }
-      if constexpr (EPI == EPI_RES32 || EPI == EPI_RES32_LN) {
+      if constexpr (EPI == EPI_RES16_LN) {
+        // ---- proj / fc2 over the (hi, lo) pair stream: x = hi + lo; x += gamma * (acc + bias); hi, lo and the row sums
+        // of the new x go back in place.  Same smem transpose as the fp32 form below, but a lane owns EIGHT columns
+        // (cq = lane & 3) of rows rg, rg + 8, rg + 16, rg + 24 (rg = lane >> 2), so that hi and lo move as 16-byte
+        // pieces: the first version with 8-byte pieces doubled the number of memory requests in flight per warp and
+        // ran proj at HALF the speed of the fp32 form (118 us vs 66 us) although it moved fewer bytes.
+        static_assert(COLS_PER_GRP == 128, "LN partial sums are kept per 128-column slice");
+        bf16* const xhi = reinterpret_cast<bf16*>(op.ln_xb);
+        bf16* const xlo = reinterpret_cast<bf16*>(op.ln_xlo);
+        const uint32_t tile = stg_all + (warp - EPI_WARP0) * STG_WARP_BYTES;
+        const int rg = lane >> 2, cq = lane & 3;
+        const long long ld = op.ldo;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f}, lq[4] = {0.f, 0.f, 0.f, 0.f};
+        auto prefetch = [&](int cc, uint4 (&h)[4], uint4 (&l)[4]) {
+          const long long o = (cs.row0 + rg) * ld + cc + cq * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (8 * i + rg < cs.nv) {
+              h[i] = *reinterpret_cast<const uint4*>(xhi + o + 8 * i * ld);
+              l[i] = *reinterpret_cast<const uint4*>(xlo + o + 8 * i * ld);
+            } else {
+              h[i] = l[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        };
+        auto ld_bg = [&](int c, float4 (&b)[2], float4 (&gm)[2]) {
+          const int nq = col0 + c + cq * 8;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            b[k] = gp.bias ? *reinterpret_cast<const float4*>(gp.bias + nq + 4 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gm[k] = gp.gamma ? *reinterpret_cast<const float4*>(gp.gamma + nq + 4 * k) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        };
+        uint4 hv[4], lv[4], hn[4], ln1[4];
+        prefetch(col0, hv, lv);
+        prefetch(col0 + 32, hn, ln1);
+        float4 b4[2], g4[2], b4n[2], g4n[2];
+        ld_bg(0, b4, g4);
+        ptx::mbar_wait(&tfull[acc], acc_ph);
+        ptx::tc_fence_after();
+        uint32_t r[32];
+        ptx::tmem_ld32(t_acc, r);
+#pragma unroll 1
+        for (int c = 0; c < COLS_PER_GRP; c += 32) {
+          uint4 hn2[4], ln2[4];
+          if (c + 64 < COLS_PER_GRP) prefetch(col0 + c + 64, hn2, ln2);
+          if (c + 32 < COLS_PER_GRP) ld_bg(c + 32, b4n, g4n);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ptx::sts_v4(tile + lane * 128 + ((j ^ (lane & 7)) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          if (c + 32 < COLS_PER_GRP) {
+            ptx::tmem_ld32(t_acc + c + 32, r);
+          } else {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(tempty_leader + acc * 8);
+          }
+          __syncwarp();
+          const long long off = (cs.row0 + rg) * ld + col0 + c + cq * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = 8 * i + rg;
+            const float4 a0 = ptx::lds_v4(tile + row * 128 + (((2 * cq) ^ (row & 7)) << 4));
+            const float4 a1 = ptx::lds_v4(tile + row * 128 + (((2 * cq + 1) ^ (row & 7)) << 4));
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b4[0].x, b4[0].y, b4[0].z, b4[0].w, b4[1].x, b4[1].y, b4[1].z, b4[1].w};
+            const float gv[8] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w};
+            const uint32_t hw[4] = {hv[i].x, hv[i].y, hv[i].z, hv[i].w}, lw[4] = {lv[i].x, lv[i].y, lv[i].z, lv[i].w};
+            float o[8];
+            uint32_t nh[4], nl[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 xh = h2_to_f2(*reinterpret_cast<const bf16x2*>(&hw[k]));
+              const float2 xl = h2_to_f2(*reinterpret_cast<const bf16x2*>(&lw[k]));
+              o[2 * k] = fmaf(av[2 * k] + bv[2 * k], gv[2 * k], xh.x + xl.x);
+              o[2 * k + 1] = fmaf(av[2 * k + 1] + bv[2 * k + 1], gv[2 * k + 1], xh.y + xl.y);
+              const bf16x2 h2 = f2_to_h2(o[2 * k], o[2 * k + 1]);
+              const float2 rb = h2_to_f2(h2);
+              const bf16x2 l2 = f2_to_h2(o[2 * k] - rb.x, o[2 * k + 1] - rb.y);
+              nh[k] = *reinterpret_cast<const uint32_t*>(&h2), nl[k] = *reinterpret_cast<const uint32_t*>(&l2);
+              ls[i] += o[2 * k] + o[2 * k + 1];
+              lq[i] += fmaf(o[2 * k], o[2 * k], o[2 * k + 1] * o[2 * k + 1]);
+            }
+            if (row < cs.nv) {
+              *reinterpret_cast<uint4*>(xhi + off + 8 * i * ld) = make_uint4(nh[0], nh[1], nh[2], nh[3]);
+              *reinterpret_cast<uint4*>(xlo + off + 8 * i * ld) = make_uint4(nl[0], nl[1], nl[2], nl[3]);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hv[i] = hn[i], lv[i] = ln1[i], hn[i] = hn2[i], ln1[i] = ln2[i];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) b4[k] = b4n[k], g4[k] = g4n[k];
+        }
+        // the 4 lanes that share a row add up their 8 columns x 4 chunks; slot = this warp's 128-column slice
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float sv = ls[i], qv = lq[i];
+          sv += __shfl_xor_sync(0xffffffffu, sv, 1), qv += __shfl_xor_sync(0xffffffffu, qv, 1);
+          sv += __shfl_xor_sync(0xffffffffu, sv, 2), qv += __shfl_xor_sync(0xffffffffu, qv, 2);
+          const int rr = 8 * i + rg;
+          if (cq == 0 && rr < cs.nv)
+            *reinterpret_cast<float2*>(op.ln_stats_out + ((cs.row0 + rr) * LN_SLOTS + (col0 >> 7)) * 2) = make_float2(sv, qv);
+        }
+      } else if constexpr (EPI == EPI_RES32 || EPI == EPI_RES32_LN) {
         constexpr bool LN_OUT = EPI == EPI_RES32_LN;
         float ls[8], lq[8];  // LN_OUT: this lane's partial row sums of rows (lane >> 3) + 4 i
 #pragma unroll
@@ -1198,6 +1307,17 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   g.tma_out = tma_epi ? 1 : 0;
   g.res_prefetch = (resid32 && res_prefetch_enabled() && op.ldres % 4 == 0 && op.N % 4 == 0 &&
                     reinterpret_cast<uintptr_t>(op.res) % 16 == 0) ? 1 : 0;
+  if (op.ln_xlo != nullptr) {
+    // residual stream as a (hi, lo) pair of 16-bit arrays, updated in place; hi doubles as the LayerNorm-folded operand
+    DP_CHECK(bn == 256 && op.a_mode == A_ROWMAJOR && op.out_mode == O_ROWMAJOR && op.N == 1024 && op.ldo == 1024 &&
+                 op.ln_xb != nullptr && op.ln_stats_out != nullptr && op.ln_stats == nullptr && op.res == nullptr &&
+                 op.res2 == nullptr && op.out == nullptr && op.out_relu == nullptr && op.act == ACT_NONE && op.col_off == 0,
+             "pair-residual producer: N = ldo = 1024, ln_xb + ln_xlo + ln_stats_out, no other output");
+    g.tma_out = 0, g.res_prefetch = 0;
+    if (cl == 2) launch<256, 2, EPI_RES16_LN>(op, g, *tmA, tmW, stream);
+    else launch<256, 1, EPI_RES16_LN>(op, g, *tmA, tmW, stream);
+    return;
+  }
   if (op.ln_stats != nullptr || op.ln_xb != nullptr) {
     // LayerNorm-folded forms exist for the ViT shapes only (BN = 256)
     DP_CHECK(bn == 256 && op.a_mode == A_ROWMAJOR, "LN-folded GEMM: N must be a multiple of 256");

@@ -353,10 +353,13 @@ __device__ __forceinline__ long long map_row(const RowMap& m, long long d) {
   return (m.seq_off + b * m.sb + static_cast<long long>(patch) * m.sp) * 577 + 1 + ty * 24 + tx;
 }
 
+// `in` is the fp32 token matrix, or -- when `in_hi` is set -- the stream's (hi, lo) pair of 16-bit arrays (x = hi + lo,
+// common.cuh GemmOp::ln_xlo).
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, T* __restrict__ out,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                        long long n_out, RowMap map, int ln, LnGroups grp) {
+                                                        long long n_out, RowMap map, int ln, LnGroups grp,
+                                                        const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo) {
   const long long d = blockIdx.x * 8LL + (threadIdx.x >> 5);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: `in` comes from the previous kernel
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -366,10 +369,25 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     w = grp.w[gi], bias = grp.b[gi];
   }
   const int lane = threadIdx.x & 31;
-  const float4* src = reinterpret_cast<const float4*>(in + map_row(map, d) * 1024);
   float4 v[8];
+  if (in_hi != nullptr) {
+    const long long r = map_row(map, d) * 1024;
+    const uint2* sh = reinterpret_cast<const uint2*>(in_hi + r);
+    const uint2* sl = reinterpret_cast<const uint2*>(in_lo + r);
+    uint2 h[8], l[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = src[lane + 32 * i];
+    for (int i = 0; i < 8; ++i) h[i] = sh[lane + 32 * i], l[i] = sl[lane + 32 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 h0 = h2_to_f2(*reinterpret_cast<const bf16x2*>(&h[i].x)), h1 = h2_to_f2(*reinterpret_cast<const bf16x2*>(&h[i].y));
+      const float2 l0 = h2_to_f2(*reinterpret_cast<const bf16x2*>(&l[i].x)), l1 = h2_to_f2(*reinterpret_cast<const bf16x2*>(&l[i].y));
+      v[i] = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+    }
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(in + map_row(map, d) * 1024);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = src[lane + 32 * i];
+  }
   if (ln) {
     float s = 0.f;
 #pragma unroll
@@ -419,8 +437,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // Entry of the folded chain (the residual stream right after patch embed): x fp32 -> raw bf16 copy +
 // per-row (sum, sum of squares) in slot 0, the other slots zero.  Later layers get both from the
 // proj / fc2 epilogues.
+// With `xlo` the stream continues as a (hi, lo) pair: xb = hi = round16(x), xlo = round16(x - hi).
 __global__ void __launch_bounds__(256) ln_stats_cast_kernel(const float* __restrict__ in, bf16* __restrict__ xb,
-                                                            float* __restrict__ stats, long long rows) {
+                                                            bf16* __restrict__ xlo, float* __restrict__ stats,
+                                                            long long rows) {
   const long long d = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (d >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -437,6 +457,13 @@ __global__ void __launch_bounds__(256) ln_stats_cast_kernel(const float* __restr
     uint2 pk;
     pk.x = *reinterpret_cast<const uint32_t*>(&lo), pk.y = *reinterpret_cast<const uint32_t*>(&hi);
     *reinterpret_cast<uint2*>(xb + d * 1024 + (lane + 32 * i) * 4) = pk;
+    if (xlo != nullptr) {
+      const float2 r0 = h2_to_f2(lo), r1 = h2_to_f2(hi);
+      const bf16x2 e0 = f2_to_h2(v[i].x - r0.x, v[i].y - r0.y), e1 = f2_to_h2(v[i].z - r1.x, v[i].w - r1.y);
+      uint2 pe;
+      pe.x = *reinterpret_cast<const uint32_t*>(&e0), pe.y = *reinterpret_cast<const uint32_t*>(&e1);
+      *reinterpret_cast<uint2*>(xlo + d * 1024 + (lane + 32 * i) * 4) = pe;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o), q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -1052,19 +1079,23 @@ void write_cls_rows(float* resid, const float* cls, const float* pos, int nseq, 
 
 template <typename T>
 void layernorm_rows(const float* in, T* out, const float* w, const float* b, long long n_out, RowMap map, int ln,
-                    cudaStream_t s) {
-  launch_pdl(layernorm_kernel<T>, dim3(blocks_for(n_out, 8)), dim3(256), 0, s, in, out, w, b, n_out, map, ln, LnGroups());
+                    cudaStream_t s, const bf16* in_hi, const bf16* in_lo) {
+  launch_pdl(layernorm_kernel<T>, dim3(blocks_for(n_out, 8)), dim3(256), 0, s, in, out, w, b, n_out, map, ln, LnGroups(),
+             in_hi, in_lo);
   DP_LAUNCH_CHECK();
 }
 template <typename T>
 void layernorm_rows_grouped(const float* in, T* out, const LnGroups& g, long long n_out, cudaStream_t s) {
-  launch_pdl(layernorm_kernel<T>, dim3(blocks_for(n_out, 8)), dim3(256), 0, s, in, out, g.w[0], g.b[0], n_out, RowMap(), 1, g);
+  launch_pdl(layernorm_kernel<T>, dim3(blocks_for(n_out, 8)), dim3(256), 0, s, in, out, g.w[0], g.b[0], n_out, RowMap(), 1, g,
+             static_cast<const bf16*>(nullptr), static_cast<const bf16*>(nullptr));
   DP_LAUNCH_CHECK();
 }
 template void layernorm_rows_grouped<float>(const float*, float*, const LnGroups&, long long, cudaStream_t);
 template void layernorm_rows_grouped<bf16>(const float*, bf16*, const LnGroups&, long long, cudaStream_t);
-template void layernorm_rows<float>(const float*, float*, const float*, const float*, long long, RowMap, int, cudaStream_t);
-template void layernorm_rows<bf16>(const float*, bf16*, const float*, const float*, long long, RowMap, int, cudaStream_t);
+template void layernorm_rows<float>(const float*, float*, const float*, const float*, long long, RowMap, int, cudaStream_t,
+                                    const bf16*, const bf16*);
+template void layernorm_rows<bf16>(const float*, bf16*, const float*, const float*, long long, RowMap, int, cudaStream_t,
+                                   const bf16*, const bf16*);
 
 // micro-benchmark operands: bf16 values uniform in [-1, 1) from a counter hash (an fp32 view of the same
 // bytes is a float in that range too).  Zero-filled operands hide most of the tensor-core power.
@@ -1083,8 +1114,16 @@ void fill_random_bf16(void* p, size_t bytes, unsigned seed, cudaStream_t s) {
   DP_LAUNCH_CHECK();
 }
 
-void ln_stats_cast(const float* in, bf16* xb, float* stats, long long rows, cudaStream_t s) {
-  ln_stats_cast_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(in, xb, stats, rows);
+void ln_stats_cast(const float* in, bf16* xb, float* stats, long long rows, cudaStream_t s, bf16* xlo) {
+  ln_stats_cast_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(in, xb, xlo, stats, rows);
+  DP_LAUNCH_CHECK();
+}
+__global__ void pair_to_f32_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float* __restrict__ x, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) x[i] = h_to_f(hi[i]) + h_to_f(lo[i]);
+}
+void pair_to_f32(const bf16* hi, const bf16* lo, float* x, long long n, cudaStream_t s) {
+  pair_to_f32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(hi, lo, x, n);
   DP_LAUNCH_CHECK();
 }
 void ln_fold(const float* w, const float* g, const float* b_ln, const float* bias, bf16* wf, float* c, float* d, int N,

@@ -45,7 +45,7 @@ struct LnGroups {
 };
 template <typename T>
 void layernorm_rows(const float* in, T* out, const float* w, const float* b, long long n_out,
-                    RowMap map, int ln, cudaStream_t s);
+                    RowMap map, int ln, cudaStream_t s, const bf16* in_hi = nullptr, const bf16* in_lo = nullptr);
 template <typename T>
 void layernorm_rows_grouped(const float* in, T* out, const LnGroups& g, long long n_out, cudaStream_t s);
 // generic-width gather without LN (used by dp_merge): in (nseq,577,C) f32 -> out (B,S,S,C) f32
@@ -70,7 +70,10 @@ void fill_random_bf16(void* p, size_t bytes, unsigned seed, cudaStream_t s);
 
 // ---- LayerNorm folded into the ViT GEMMs (common.cuh GemmOp::ln_stats) -------------------------
 // x fp32 (rows, 1024) -> raw bf16 copy + per-row partial sums [rows][LN_SLOTS][2] (slot 0 filled)
-void ln_stats_cast(const float* in, bf16* xb, float* stats, long long rows, cudaStream_t s);
+// with `xlo`: also the low half of the (hi, lo) pair form of the stream, xlo = round16(x - xb)
+void ln_stats_cast(const float* in, bf16* xb, float* stats, long long rows, cudaStream_t s, bf16* xlo = nullptr);
+// x = hi + lo (test helper of the pair form)
+void pair_to_f32(const bf16* hi, const bf16* lo, float* x, long long n, cudaStream_t s);
 // wf = bf16(g * w) [N,K], c = colsum(wf), d = bias + w b_ln   (w fp32 [N,K], K = 1024)
 void ln_fold(const float* w, const float* g, const float* b_ln, const float* bias, bf16* wf, float* c, float* d, int N,
              int K, cudaStream_t s);

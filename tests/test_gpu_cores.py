@@ -144,6 +144,47 @@ def test_gemm_bf16_layernorm_emitting_producer(M, K):
     assert float(err.mean()) < 2e-3
 
 
+@pytest.mark.parametrize("M,K", [(300, 128), (21349, 1024), (21349, 4096)])
+def test_gemm_bf16_pair_residual_producer(M, K):
+    """The same producer over a residual stream stored as a (hi, lo) pair of 16-bit arrays (x = hi + lo, hi = the next
+    folded GEMM's operand; common.cuh GemmOp::ln_xlo): the update must match the fp32-stream form to the pair's
+    2^-16 resolution, the emitted statistics are those of the updated stream, and 48 consecutive updates (a whole
+    ViT-L worth of proj / fc2) must not drift."""
+    N = 1024
+    g = torch.Generator(device=DEV).manual_seed(M + K + 1)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    res = torch.randn(M, N, device=DEV, generator=g) * 3 + 0.7
+    res[:, 5] *= 200.0                                     # an outlier channel, as DINOv2 has
+    C = torch.zeros(2 * M, N, device=DEV)
+    C[:M] = res
+    flags = 0x200 | 0x2000 | 0x4000
+    _capi.check(lib().dp_gemm_test(engine(), 1, A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, flags, stream()))
+    torch.cuda.synchronize()
+    upd = b.double() * (_bf16r(A).double() @ _bf16r(W).double().t() + b.double())
+    ref = res.double() + upd
+    # element-wise: the pair resolves 2^-16 of each VALUE (two 8-bit mantissas + the sign of lo), on top of the fp32
+    # accumulation-order error of the GEMM itself (the fp32-stream test allows 2e-5 of the tensor's maximum)
+    gemm_err = 1e-5 * float(upd.abs().max())
+    assert float(((C[:M].double() - ref).abs() - 2.0 ** -15 * ref.abs()).max()) < gemm_err
+    ln = F.layer_norm(C[:M].double(), (N,), eps=1e-6)
+    err = (C[M:].double() - ln).abs()
+    assert float(err.max()) < 2.0 ** -8 * float((C[:M].abs().max(dim=1).values / C[:M].std(dim=1)).max()) + 1e-4
+    assert float(err.mean()) < 2e-3
+    if M == 300:
+        x = C[:M].clone()
+        want = ref.clone()
+        for _ in range(47):
+            C[:M] = x
+            _capi.check(lib().dp_gemm_test(engine(), 1, A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, flags,
+                                           stream()))
+            torch.cuda.synchronize()
+            x = C[:M].clone()
+            want += upd
+        assert float(((x.double() - want).abs() - 48 * 2.0 ** -16 * want.abs()).max()) < 48 * gemm_err
+
+
 @pytest.mark.parametrize("S,Cout,K,dual", [(32, 64, 128, 0), (96, 256, 256, 0), (192, 256, 256, 1), (32, 128, 64, 1)])
 def test_gemm_bf16_convt_pixel_shuffle_epilogue(S, Cout, K, dual):
     """ConvTranspose2d k2 s2 as GEMM (N = (dy, dx, o)) + pixel shuffle through a 5-D TMA store; dual = ReLU twin."""

@@ -270,6 +270,30 @@ def test_bf16_layernorm_fold_with_outlier_channels(monkeypatch):
     assert float(e_f.median()) <= 1.5 * float(e_p.median()) + 5e-4
 
 
+def test_bf16_pair_residual_stream_matches_fp32_stream(model_bf16, oracle_run, monkeypatch):
+    """Default: the ViT residual stream is a (hi, lo) pair of 16-bit arrays whose hi half is the next GEMM's operand
+    (csrc/common.cuh GemmOp::ln_xlo).  DEPTHPRO_RES_PAIR=0 (read at engine creation) keeps the fp32 stream + separate
+    16-bit copy.  The pair resolves 2^-16 per value against the 2^-9 of every GEMM operand: the two engines must agree
+    far inside the bf16 tolerance and sit equally close to the fp32 reference."""
+    x, ref, _ = oracle_run
+    pair = model_bf16.infer(x.to(DEV))
+    monkeypatch.setenv("DEPTHPRO_RES_PAIR", "0")
+    f32_model = depth_pro.DepthPro(device=DEV, precision=torch.bfloat16).init_weights("stress", 1234).eval()
+    f32 = f32_model.infer(x.to(DEV))
+    monkeypatch.delenv("DEPTHPRO_RES_PAIR")
+    d_a, d_b, d_r = pair["depth"].cpu(), f32["depth"].cpu(), ref["depth"]
+    assert not torch.equal(d_a, d_b), "DEPTHPRO_RES_PAIR=0 did not select the fp32 residual stream"
+    ok = (d_r < 1e4 - 1) & (d_a < 1e4 - 1) & (d_b < 1e4 - 1)
+    between = _pix_rel(d_a, d_b)[ok].float()
+    e_a, e_b = _pix_rel(d_a, d_r)[ok].float().median(), _pix_rel(d_b, d_r)[ok].float().median()
+    print(f"pair vs fp32 residual stream: median rel diff {float(between.median()):.3e}; vs fp32 reference: pair "
+          f"{float(e_a):.3e}, fp32 stream {float(e_b):.3e}")
+    assert float(between.median()) <= 1.5e-3
+    assert float(e_a) <= 5e-3 and float(e_a) <= 1.2 * float(e_b) + 2e-4
+    assert abs(float(pair["focallength_px"]) - float(f32["focallength_px"])) <= 1e-3 * float(f32["focallength_px"])
+    del f32_model
+
+
 def test_bf16_layernorm_fold_matches_standalone_layernorm(model_bf16, oracle_run, monkeypatch):
     """The LayerNorm-folded ViT (default) and the stand-alone LayerNorm launches (DEPTHPRO_LN_FUSE=0, read at
     engine creation) are two roundings of the same arithmetic: they must agree far inside the bf16 tolerance,
