@@ -78,6 +78,79 @@ __global__ void __launch_bounds__(256, 1) rmw_kernel(float* __restrict__ x, __nv
   }
 }
 
+// ---- the residual stream as a (hi, lo) pair of bf16 arrays (EPI_RES16_LN): both read and written in place ----------
+//   W32: the epilogue's 32-column chunks, a lane moves 8 columns (16 B) of rows rg + 8 i  -> 64-byte row segments
+//   W64: 64-column chunks, a lane moves 8 columns (16 B) of rows rg + 4 i                 -> 128-byte row segments
+// DEPTH = chunks requested ahead of the one being processed.
+template <int W, int DEPTH>
+__global__ void __launch_bounds__(256, 1) pair_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int M) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, grp = warp >> 2;
+  const int m_tiles = (M + BM - 1) / BM, tiles = m_tiles * (N / BN);
+  constexpr int NCH = 128 / W;                       // chunks per warp-tile
+  constexpr int LPR = W / 8;                         // lanes per row segment
+  constexpr int RPI = 32 / LPR;                      // rows per instruction
+  constexpr int NI = 32 / RPI;                       // instructions per chunk and array
+  constexpr int NBUF = DEPTH + 1;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int nt = t % (N / BN), mt = t / (N / BN);
+    const int rows_left = M - (mt * BM + q * 32);
+    const int rg = lane / LPR, cq = lane % LPR;
+    auto off = [&](int c, int i) {
+      return static_cast<long long>(mt * BM + q * 32 + rg + RPI * i) * N + nt * BN + grp * 128 + c * W + cq * 8;
+    };
+    uint4 h[NBUF][NI], l[NBUF][NI];
+    auto load = [&](int c, uint4 (&hh)[NI], uint4 (&ll)[NI]) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if (rg + RPI * i < rows_left) {
+          hh[i] = *reinterpret_cast<const uint4*>(hi + off(c, i));
+          ll[i] = *reinterpret_cast<const uint4*>(lo + off(c, i));
+        } else {
+          hh[i] = ll[i] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    };
+#pragma unroll
+    for (int c = 0; c < DEPTH && c < NCH; ++c) load(c, h[c % NBUF], l[c % NBUF]);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (c + DEPTH < NCH) load(c + DEPTH, h[(c + DEPTH) % NBUF], l[(c + DEPTH) % NBUF]);
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if (rg + RPI * i >= rows_left) continue;
+        uint4 a = h[c % NBUF][i], b = l[c % NBUF][i];
+        a.x += b.x, a.y ^= b.y, a.z += b.w, a.w ^= b.z;   // any dependence on both loads
+        b.x ^= a.y, b.y += a.x, b.z ^= a.w, b.w += a.z;
+        *reinterpret_cast<uint4*>(hi + off(c, i)) = a;
+        *reinterpret_cast<uint4*>(lo + off(c, i)) = b;
+      }
+    }
+  }
+}
+template <int W, int DEPTH>
+static void run_pair(const char* name, __nv_bfloat16* hi, __nv_bfloat16* lo, int M, void* flush, size_t flush_bytes, int sms) {
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  float tot = 0.f, best = 1e9f;
+  const int iters = 12;
+  for (int i = 0; i < iters + 2; ++i) {
+    CK(cudaMemsetAsync(flush, i & 0xff, flush_bytes));
+    CK(cudaEventRecord(a));
+    pair_kernel<W, DEPTH><<<sms, 256>>>(hi, lo, M);
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    if (i >= 2) tot += ms, best = ms < best ? ms : best;
+  }
+  CK(cudaGetLastError());
+  const double mp = (M + 31) / 32 * 32;
+  const double bytes = mp * N * 8.0;
+  printf("%-58s %8.1f us mean %8.1f us best  %6.2f TB/s (mean)\n", name, tot / iters * 1e3, best * 1e3, bytes / (tot / iters * 1e-3) / 1e12);
+}
+
 template <bool BLK32, bool BF16, bool BLK16>
 static void run(const char* name, float* x, __nv_bfloat16* xb, int M, void* flush, size_t flush_bytes, int sms) {
   cudaEvent_t a, b;
@@ -122,5 +195,14 @@ int main() {
   run<false, false, false>("D fp32 row-major only", x, xb, M, flush, flush_bytes, sms);
   run<true, false, false>("E fp32 blocked only", x, xb, M, flush, flush_bytes, sms);
   run<false, true, false>("A again", x, xb, M, flush, flush_bytes, sms);
+  // pair stream: hi in xb, lo in the first half of x
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(x);
+  printf("(hi, lo) pair stream, 8 B per element (%.0f MB)\n", (double)mp * N * 8 / 1e6);
+  run_pair<32, 2>("P1 32-col chunks (64 B segments), 2 ahead (engine today)", xb, lo, M, flush, flush_bytes, sms);
+  run_pair<32, 3>("P1b 32-col chunks, 3 ahead (whole warp-tile in flight)", xb, lo, M, flush, flush_bytes, sms);
+  run_pair<64, 1>("P2 64-col chunks (128 B segments), 1 ahead", xb, lo, M, flush, flush_bytes, sms);
+  run_pair<64, 2>("P3 64-col chunks, whole warp-tile in flight", xb, lo, M, flush, flush_bytes, sms);
+  run_pair<128, 1>("P4 128-col chunks (256 B segments), whole tile in flight", xb, lo, M, flush, flush_bytes, sms);
+  run_pair<32, 2>("P1 again", xb, lo, M, flush, flush_bytes, sms);
   return 0;
 }
