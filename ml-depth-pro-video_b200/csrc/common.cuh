@@ -220,6 +220,9 @@ struct GemmOp {
   const float* dot_w = nullptr; // O_DOT_RELU: head.4 weight (32), dot_b: bias (1)
   const float* dot_b = nullptr;
   const float* head_cb = nullptr;  // O_HEAD_FUSED: [9][32] per-tap bias terms, then [32] full bias
+  // conv3x3 with a composed 1x1 in front (bf16 TMA-store epilogue): [9][N] per-tap share of the 1x1's bias; `bias` holds
+  // the interior value (all nine included), pixels on the image border subtract the taps that fall into the zero padding
+  const float* border_cb = nullptr;
   // LayerNorm folded into the surrounding GEMMs (bf16 tcgen05 core only).  With x the fp32 residual
   // stream, LN(x) W^T + b  =  rstd * (x (g*W)^T)  -  rstd * mean * colsum(g*W)  +  (W b_ln + b):
   //  * producer (the fp32-residual form, proj / fc2, N == 1024): besides x += gamma * (acc + bias) it

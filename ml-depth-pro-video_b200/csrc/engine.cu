@@ -237,6 +237,8 @@ Engine::Engine(int device, int prec, int max_batch, int fov_mode)
   ln_fuse_ = prec_ == BF16 && !(lf != nullptr && lf[0] == '0');
   // the ViT residual stream as a (hi, lo) pair of 16-bit arrays (common.cuh GemmOp::ln_xlo) instead of fp32 + a 16-bit
   // copy; needs the folded LayerNorm.  "0" keeps the fp32 stream (A/B, debugging)
+  const char* hf = getenv("DEPTHPRO_HEAD0_FUSE");  // "0": keep fusions.0.out_conv as its own 1x1 launch (A/B, debugging)
+  head0_fused_ = prec_ == BF16 && !(hf != nullptr && hf[0] == '0');
   const char* rp = getenv("DEPTHPRO_RES_PAIR");
   res_pair_ = ln_fuse_ && !(rp != nullptr && rp[0] == '0');
   DP_CUDA(cudaStreamCreateWithFlags(&host_stream_, cudaStreamNonBlocking));
@@ -316,8 +318,11 @@ void Engine::set_weight(const std::string& name, const void* data, const int64_t
   // folded at finalize with the block's norm1 / norm2 affine, from the fp32 originals
   const bool ln_folded = ln_fuse_ && (ends_with(name, ".attn.qkv.weight") || ends_with(name, ".mlp.fc1.weight") ||
                                       ends_with(name, ".attn.qkv.bias") || ends_with(name, ".mlp.fc1.bias"));
+  // fusions.0.out_conv (1x1) is composed into head.0 (conv3x3) at finalize
+  const bool head0_chain = name == "head.0.weight" || name == "head.0.bias" || name == "decoder.fusions.0.out_conv.weight" ||
+                           name == "decoder.fusions.0.out_conv.bias";
   if (bf && (name == "head.1.weight" || name == "head.1.bias" || name == "head.2.weight" || name == "head.2.bias" ||
-             fusion_tail || ln_folded)) {
+             fusion_tail || ln_folded || head0_chain)) {
     Packed& rw = raw_[name];
     if (rw.bytes != n * 4) {
       if (rw.ptr) DP_CUDA(cudaFree(rw.ptr));
@@ -460,6 +465,11 @@ void Engine::finalize() {
     auto R = [&](const char* k) { return reinterpret_cast<const float*>(raw_.at(k).ptr); };
     compose_head(R("head.1.weight"), R("head.1.bias"), R("head.2.weight"), R("head.2.bias"), (bf16*)head_wc_, head_cb_,
                  nullptr);
+    // exact-linear fusion fusions.0.out_conv (1x1 + bias, decoder.py:178 with deconv=False) o head.0 (conv3x3,
+    // depth_pro.py:183-185): the decoder's 768^2 x 256 output map is never written or re-read (604 MB per frame)
+    if (!head0_wc_) head0_wc_ = alloc(128 * 9 * 256 * 2), head0_cb_ = (float*)alloc(10 * 128 * 4);
+    compose_1x1_conv3x3(R("decoder.fusions.0.out_conv.weight"), R("decoder.fusions.0.out_conv.bias"), R("head.0.weight"),
+                        R("head.0.bias"), (bf16*)head0_wc_, head0_cb_, 128, 256, nullptr);
     // exact-linear fusion deconv (no bias) o out_conv (1x1 + bias) of fusion blocks 1-4 (decoder.py:176-178)
     for (int i = 1; i <= 4; ++i) {
       const std::string p = "decoder.fusions." + std::to_string(i) + ".";
@@ -870,14 +880,21 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
     } else if (i != 0) {
       convT(s, x2_, S, 256, p + "deconv.weight", 256, y_, 256, 0, nullptr, nullptr);
       conv1x1(s, y_, 2 * S, 256, p + "out_conv.weight", 256, feat_[i], F(p + "out_conv.bias"));
-    } else {
+    } else if (prec_ != BF16 || !head0_fused_) {
       conv1x1(s, x2_, S, 256, p + "out_conv.weight", 256, feat_[0], F(p + "out_conv.bias"));
-    }
+    }  // bf16: composed into head.0 below; tap("decoder_out") evaluates it on demand
   }
 
   // ---- depth head (depth_pro.py:182-204)
   NvtxRange r_head("head+fov");
-  conv3x3(s, feat_[0], 768, 256, "head.0.weight", 128, F("head.0.bias"), ACT_NONE, nullptr, nullptr, h0_, nullptr);
+  if (prec_ == BF16 && head0_fused_) {
+    GemmOp op;
+    op.M = 768 * 768, op.N = 128, op.K = 9 * 256, op.A = x2_, op.a_mode = A_CONV3X3, op.B = 1, op.H = 768, op.W = 768, op.C = 256;
+    op.Wt = head0_wc_, op.bias = head0_cb_ + 9 * 128, op.border_cb = head0_cb_, op.out = h0_, op.ldo = 128;
+    gemm(prec_, op, s);
+  } else {
+    conv3x3(s, feat_[0], 768, 256, "head.0.weight", 128, F("head.0.bias"), ACT_NONE, nullptr, nullptr, h0_, nullptr);
+  }
   if (prec_ == BF16) {
     // head.1 (ConvT) + head.2 (conv3x3) + ReLU + head.4 (1x1) + ReLU as ONE conv over the 768^2 map:
     // the 604 MB 128x1536^2 intermediate is never materialised and 77 GF of ConvT work disappears
@@ -1074,6 +1091,15 @@ int64_t Engine::tap_impl(const std::string& stage, float* out, int64_t capacity,
 int64_t Engine::tap(const std::string& stage, float* out, int64_t capacity, cudaStream_t s) {
   DP_CHECK(finalized_ && last_B_ > 0, "dp_tap needs a previous dp_forward");
   DP_CUDA(cudaSetDevice(device_));
+  if (stage == "decoder_out" && prec_ == BF16 && head0_fused_) {
+    // bf16 mode never materialises the decoder's output map (fusions.0.out_conv is composed into head.0): evaluate the
+    // 1x1 on demand from resnet2's output of the last decoded frame
+    GemmOp op;
+    const std::string p = "decoder.fusions.0.out_conv.";
+    op.M = 768 * 768, op.N = 256, op.K = 256, op.A = x2_, op.lda = 256, op.Wt = W(p + "weight"), op.bias = F(p + "bias");
+    op.out = feat_[0], op.ldo = 256;
+    gemm(prec_, op, s);
+  }
   return prec_ == BF16 ? tap_impl<bf16>(stage, out, capacity, s) : tap_impl<float>(stage, out, capacity, s);
 }
 

@@ -119,6 +119,9 @@ class Engine {
   void *h0_, *h1_;
   void* head_wc_ = nullptr;    // composed head.1 o head.2 weights (bf16 mode)
   float* head_cb_ = nullptr;
+  void* head0_wc_ = nullptr;   // composed fusions.0.out_conv o head.0 weights (bf16 mode), [128][9][256]
+  float* head0_cb_ = nullptr;  // [9][128] per-tap share of out_conv's bias, then [128] the interior bias
+  bool head0_fused_ = false;   // DEPTHPRO_HEAD0_FUSE=0 disables
   void *fovlin_, *fov_a_, *fov_b_, *fov_c_, *fovcol_;
   int last_B_ = 0;
   // host-call staging

@@ -892,6 +892,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (gp.bias ? bias[j] : 0.f);
+              if (op.border_cb != nullptr && valid) {
+                // composed 1x1 -> conv3x3: the 1x1's bias does not exist in the zero padding (GemmOp::border_cb)
+                const int px = static_cast<int>(m % op.W), py = static_cast<int>((m / op.W) % op.H);
+                if (px == 0 || px == op.W - 1 || py == 0 || py == op.H - 1) {
+                  for (int ky = 0; ky < 3; ++ky)
+                    for (int kx = 0; kx < 3; ++kx) {
+                      const int yy = py + ky - 1, xx = px + kx - 1;
+                      if (yy < 0 || yy >= op.H || xx < 0 || xx >= op.W) {
+                        float t[32];
+                        load32<float>(op.border_cb + (ky * 3 + kx) * op.N + col0 + cc, t);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] -= t[j];
+                      }
+                    }
+                }
+              }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) resc[i] = resn[i];
@@ -1302,6 +1318,9 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
                        op.out_relu == nullptr && op.act == ACT_NONE && op.a_mode == A_ROWMAJOR && op.res == op.out &&
                        op.ldres == op.ldo && op.col_off == 0 && bn >= 128;
   if (op.out_mode == O_CONVT2X2) DP_CHECK(op.res == nullptr && op.res2 == nullptr, "ConvT epilogue has no residual");
+  if (op.border_cb != nullptr)
+    DP_CHECK(op.a_mode == A_CONV3X3 && g.tma_out && op.out_relu == nullptr && !(op.res && op.res_f32) && op.act == ACT_NONE,
+             "border_cb: conv3x3 with the single-store TMA epilogue only");
   const bool tma_epi = g.tma_out && !(op.res && op.res_f32);
   const int epi = resid32 ? EPI_RES32 : (tma_epi ? (op.out_relu ? EPI_TMA2 : EPI_TMA) : EPI_MISC);
   g.tma_out = tma_epi ? 1 : 0;

@@ -1010,9 +1010,44 @@ __global__ void compose_deconv_kernel(const float* __restrict__ wd, const float*
   wc[idx] = f_to_h(acc);
 }
 
+// 1x1 conv (C -> C, weights wo [c][i], bias bo) followed by a 3x3 conv (C -> O, weights w3 OIHW [o][c][ky][kx], bias b3,
+// zero padding) is ONE 3x3 conv:  wc[o][tap][i] = sum_c w3[o][c][tap] wo[c][i]  (O(HW)I, the implicit-GEMM order).
+// The 1x1's bias reaches the output through every tap that lies INSIDE the image: cb[tap][o] = sum_c w3[o][c][tap] bo[c],
+// cb[9][o] = b3[o] + all nine (interior pixels); border pixels subtract the taps that fall into the padding.
+__global__ void compose_1x1_3x3_w_kernel(const float* __restrict__ wo, const float* __restrict__ w3, bf16* __restrict__ wc,
+                                         int O, int C) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;  // over [O][9][C]
+  if (idx >= static_cast<long long>(O) * 9 * C) return;
+  const int i = static_cast<int>(idx % C), tap = static_cast<int>((idx / C) % 9), o = static_cast<int>(idx / (9LL * C));
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) acc = fmaf(w3[(static_cast<long long>(o) * C + c) * 9 + tap], wo[static_cast<long long>(c) * C + i], acc);
+  wc[idx] = f_to_h(acc);
+}
+__global__ void compose_1x1_3x3_b_kernel(const float* __restrict__ bo, const float* __restrict__ w3,
+                                         const float* __restrict__ b3, float* __restrict__ cb, int O, int C) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  float full = b3[o];
+  for (int tap = 0; tap < 9; ++tap) {
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(w3[(static_cast<long long>(o) * C + c) * 9 + tap], bo[c], acc);
+    cb[tap * O + o] = acc;
+    full += acc;
+  }
+  cb[9 * O + o] = full;
+}
+
 }  // namespace
 
 // ============================================================================ host wrappers
+void compose_1x1_conv3x3(const float* wo, const float* bo, const float* w3, const float* b3, bf16* wc, float* cb, int O,
+                         int C, cudaStream_t s) {
+  compose_1x1_3x3_w_kernel<<<blocks_for(static_cast<long long>(O) * 9 * C, 256), 256, 0, s>>>(wo, w3, wc, O, C);
+  DP_LAUNCH_CHECK();
+  compose_1x1_3x3_b_kernel<<<blocks_for(O, 128), 128, 0, s>>>(bo, w3, b3, cb, O, C);
+  DP_LAUNCH_CHECK();
+}
+
 void compose_deconv_1x1(const float* wd, const float* wo, bf16* wc, int C, cudaStream_t s) {
   compose_deconv_kernel<<<blocks_for(4LL * C * C, 256), 256, 0, s>>>(wd, wo, wc, C);
   DP_LAUNCH_CHECK();

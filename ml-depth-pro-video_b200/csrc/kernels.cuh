@@ -127,6 +127,9 @@ void compose_head(const float* w1, const float* b1, const float* w2, const float
 // FeatureFusionBlock2d tail (decoder.py:176-178): ConvTranspose2d k2 s2 (no bias, weight (ci,co,2,2))
 // followed by a 1x1 conv (weight (co',co)) composed in fp32 into one ConvT in the GEMM layout
 //   wc[(dy*2+dx)*C + co'][ci] = sum_co wo[co'][co] * wd[ci][co][dy][dx]      (C x C channels)
+// wc (O, 9, C) bf16 = conv3x3 (w3 OIHW, b3) o conv1x1 (wo [c][i], bo); cb [10][O]: per-tap share of bo, then the interior bias
+void compose_1x1_conv3x3(const float* wo, const float* bo, const float* w3, const float* b3, bf16* wc, float* cb, int O,
+                         int C, cudaStream_t s);
 void compose_deconv_1x1(const float* wd, const float* wo, bf16* wc, int C, cudaStream_t s);
 void pack_oihw_to_hwio_f32(const float* w, float* out, int O, int I, int KH, int KW, cudaStream_t s);
 

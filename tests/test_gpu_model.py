@@ -270,6 +270,43 @@ def test_bf16_layernorm_fold_with_outlier_channels(monkeypatch):
     assert float(e_f.median()) <= 1.5 * float(e_p.median()) + 5e-4
 
 
+def test_bf16_head0_composed_with_decoder_out_conv(model_bf16, oracle_run, monkeypatch):
+    """Default bf16 engine: `decoder.fusions.0.out_conv` (1x1, decoder.py:178) is composed into `head.0` (conv3x3,
+    depth_pro.py:183-185) at finalize, with a border-aware bias (the 1x1's bias does not exist in head.0's zero padding).
+    DEPTHPRO_HEAD0_FUSE=0 keeps the two launches.  One launch less per frame, the same depth far inside the bf16
+    tolerance -- on the outermost pixel ring as well, which is where a wrong border term would show -- and the
+    `decoder_out` tap (now evaluated on demand) still matches the oracle."""
+    x, ref, taps = oracle_run
+    fused = model_bf16.infer(x.to(DEV))
+    n0 = model_bf16.launch_count()
+    model_bf16.infer(x.to(DEV))
+    per_frame_fused = model_bf16.launch_count() - n0
+    got = model_bf16.tap("decoder_out").cpu().reshape(taps["decoder_out"].shape)
+    r = taps["decoder_out"]
+    assert float((got - r).abs().max() / r.abs().max()) < 3e-2
+    monkeypatch.setenv("DEPTHPRO_HEAD0_FUSE", "0")
+    plain_model = depth_pro.DepthPro(device=DEV, precision=torch.bfloat16).init_weights("stress", 1234).eval()
+    plain = plain_model.infer(x.to(DEV))
+    monkeypatch.delenv("DEPTHPRO_HEAD0_FUSE")
+    n0 = plain_model.launch_count()
+    plain_model.infer(x.to(DEV))
+    assert plain_model.launch_count() - n0 == per_frame_fused + 1
+    d_a, d_b, d_r = fused["depth"].cpu(), plain["depth"].cpu(), ref["depth"]
+    assert not torch.equal(d_a, d_b)
+    ok = (d_r < 1e4 - 1) & (d_a < 1e4 - 1) & (d_b < 1e4 - 1)
+    rel = _pix_rel(d_a, d_b)
+    ring = torch.zeros_like(ok)
+    ring[:2], ring[-2:], ring[:, :2], ring[:, -2:] = True, True, True, True
+    e_in, e_ring = rel[ok & ~ring].float(), rel[ok & ring].float()
+    print(f"head.0 composed vs separate: interior median {float(e_in.median()):.3e}, border ring median "
+          f"{float(e_ring.median()):.3e} max {float(e_ring.max()):.3e}")
+    assert float(e_in.median()) <= 1.5e-3
+    assert float(e_ring.median()) <= 2.0 * float(e_in.median()) + 5e-4 and float(e_ring.max()) <= 5e-2
+    e_a, e_b = _pix_rel(d_a, d_r)[ok].float().median(), _pix_rel(d_b, d_r)[ok].float().median()
+    assert float(e_a) <= 5e-3 and float(e_a) <= 1.2 * float(e_b) + 2e-4
+    del plain_model
+
+
 def test_bf16_pair_residual_stream_matches_fp32_stream(model_bf16, oracle_run, monkeypatch):
     """Default: the ViT residual stream is a (hi, lo) pair of 16-bit arrays whose hi half is the next GEMM's operand
     (csrc/common.cuh GemmOp::ln_xlo).  DEPTHPRO_RES_PAIR=0 (read at engine creation) keeps the fp32 stream + separate
