@@ -37,10 +37,18 @@ constexpr int BK = 64;
 // smem ring: as many k-block stages as fit beside the 32 KB epilogue staging (at most 8).  A CTA pair
 // (CL = 2, tcgen05 cta_group::2) keeps only HALF of the weight tile per CTA: 32 KB stages, 6 deep at
 // BN = 256 instead of 4 x 48 KB -- the ring covers 2560 tensor-core cycles of load latency, not 1536.
+// BN = 128 tiles put TWO 64-wide k-blocks into one stage (KSUB): an MMA of the narrow tile lasts 32 tensor-core cycles, a
+// k-block 128 -- less than one full / empty barrier round trip of the issuing warp costs (ncu on head.0, N = 128: tensor
+// pipe 57 % with the tensor core's shared-memory read pipe at 43 %: not a bandwidth limit).  Two k-blocks per hand-shake
+// give the same 256 cycles per round trip as the BN = 256 tiles.
 template <int BN, int CL, int EPI>
 struct Cfg {
   static constexpr int B_ROWS = BN / CL;                      // weight rows held by one CTA
-  static constexpr int STAGE = 128 * 64 * 2 + B_ROWS * 64 * 2;
+#ifndef DP_KSUB128
+#define DP_KSUB128 2  // (-DDP_KSUB128=1 rebuilds the one-k-block-per-stage form for A/B runs)
+#endif
+  static constexpr int KSUB = BN == 128 ? DP_KSUB128 : 1;     // 64-wide k-blocks per ring stage
+  static constexpr int STAGE = KSUB * (128 * 64 * 2 + B_ROWS * 64 * 2);
   static constexpr int STG_WARP = EPI == 3 ? 8192 : 4096;     // EPI_TMA2 stages x and relu(x) side by side
   static constexpr int FIT = (232448 - 1024 - 256 - 8 * STG_WARP) / STAGE;
   static constexpr int STAGES = FIT > 8 ? 8 : FIT;
@@ -415,8 +423,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int STAGES = Cfg<BN, CL, EPI>::STAGES;
   constexpr int STG_WARP_BYTES = Cfg<BN, CL, EPI>::STG_WARP;
   constexpr bool PAIR = CL == 2;
-  constexpr uint32_t A_BYTES = BM * BK * 2;
-  constexpr uint32_t B_BYTES = (BN / CL) * BK * 2;  // per CTA
+  constexpr int KSUB = Cfg<BN, CL, EPI>::KSUB;
+  constexpr uint32_t A_SUB = BM * BK * 2, B_SUB = (BN / CL) * BK * 2;  // one 64-wide k-block (B: this CTA's share)
+  constexpr uint32_t A_BYTES = KSUB * A_SUB;        // per stage
+  constexpr uint32_t B_BYTES = KSUB * B_SUB;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(BM * CL, BN);
@@ -529,34 +539,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         int tap = 0, c0 = 0;  // conv: running (filter tap, channel offset) of the k-block
-        for (int kb = 0; kb < g.k_blocks; ++kb) {
+        for (int kb = 0; kb < g.k_blocks; kb += KSUB) {
+          // an odd K leaves a half-filled last stage
+          const int nsub = KSUB == 1 ? 1 : (g.k_blocks - kb < KSUB ? g.k_blocks - kb : KSUB);
           ptx::mbar_wait(&empty[s], ph ^ 1);
-          if (ptx::elect_one()) {
+          const bool leader_lane = ptx::elect_one();
+          if (leader_lane) {
             if constexpr (PAIR) {
-              // both CTAs' bytes complete on the leader's barrier; the leader arms it for the pair
-              const uint32_t fbar = ptx::mapa_u32(&full[s], 0);
-              if (crank == 0) ptx::mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
-              if (op.a_mode == A_CONV3X3) {
-                const int ky = tap / 3, kx = tap - ky * 3;
-                ptx::tma_load_4d_pair(sA + s * A_BYTES, &tmA, fbar, c0, x0 + kx - 1, y0 + ky - 1, b);
-              } else {
-                ptx::tma_load_2d_pair(sA + s * A_BYTES, &tmA, fbar, kb * BK, a_row);
-              }
-              ptx::tma_load_2d_pair(sB + s * B_BYTES, tmB, fbar, kb * BK, nt * BN + crank * (BN / 2));
+              if (crank == 0) ptx::mbar_expect_tx(&full[s], 2 * nsub * (A_SUB + B_SUB));
             } else {
-              ptx::mbar_expect_tx(&full[s], STAGE_BYTES);
-              if (op.a_mode == A_CONV3X3) {
-                const int ky = tap / 3, kx = tap - ky * 3;
-                ptx::tma_load_4d(sA + s * A_BYTES, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b);
-              } else {
-                ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, a_row);
+              ptx::mbar_expect_tx(&full[s], nsub * (A_SUB + B_SUB));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < KSUB; ++j) {
+            if (j < nsub) {
+              if (leader_lane) {
+                if constexpr (PAIR) {
+                  // both CTAs' bytes complete on the leader's barrier; the leader armed it for the pair
+                  const uint32_t fbar = ptx::mapa_u32(&full[s], 0);
+                  if (op.a_mode == A_CONV3X3) {
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    ptx::tma_load_4d_pair(sA + s * A_BYTES + j * A_SUB, &tmA, fbar, c0, x0 + kx - 1, y0 + ky - 1, b);
+                  } else {
+                    ptx::tma_load_2d_pair(sA + s * A_BYTES + j * A_SUB, &tmA, fbar, (kb + j) * BK, a_row);
+                  }
+                  ptx::tma_load_2d_pair(sB + s * B_BYTES + j * B_SUB, tmB, fbar, (kb + j) * BK, nt * BN + crank * (BN / 2));
+                } else {
+                  if (op.a_mode == A_CONV3X3) {
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    ptx::tma_load_4d(sA + s * A_BYTES + j * A_SUB, &tmA, &full[s], c0, x0 + kx - 1, y0 + ky - 1, b);
+                  } else {
+                    ptx::tma_load_2d(sA + s * A_BYTES + j * A_SUB, &tmA, &full[s], (kb + j) * BK, a_row);
+                  }
+                  ptx::tma_load_2d(sB + s * B_BYTES + j * B_SUB, tmB, &full[s], (kb + j) * BK, nt * BN);
+                }
               }
-              ptx::tma_load_2d(sB + s * B_BYTES, tmB, &full[s], kb * BK, nt * BN);
+              c0 += BK;
+              if (c0 == op.C) c0 = 0, ++tap;
             }
           }
           __syncwarp();
-          c0 += BK;
-          if (c0 == op.C) c0 = 0, ++tap;
           if (++s == STAGES) s = 0, ph ^= 1;
         }
       }
@@ -581,25 +604,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::mbar_wait(&tempty[acc], acc_ph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < g.k_blocks; ++kb) {
+        for (int kb = 0; kb < g.k_blocks; kb += KSUB) {
+          const int nsub = KSUB == 1 ? 1 : (g.k_blocks - kb < KSUB ? g.k_blocks - kb : KSUB);
           ptx::mbar_wait(&full[s], ph);
           ptx::tc_fence_after();
           const uint32_t a_lo = a_lo0 + s * (A_BYTES >> 4);
           const uint32_t b_lo = b_lo0 + s * (B_BYTES >> 4);
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t da = (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + 2 * k);  // +32 B per K=16 step
-              const uint64_t db = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + 2 * k);
-              if (PAIR) ptx::umma_bf16_pair(d_tmem, da, db, IDESC, (kb | k) != 0);
-              else ptx::umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0);
+            for (int j = 0; j < KSUB; ++j) {
+              if (j < nsub) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  // +32 B per K = 16 step inside a 64-wide k-block, + one sub-tile per k-block
+                  const uint64_t da = (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + j * (A_SUB >> 4) + 2 * k);
+                  const uint64_t db = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + j * (B_SUB >> 4) + 2 * k);
+                  if (PAIR) ptx::umma_bf16_pair(d_tmem, da, db, IDESC, (kb | j | k) != 0);
+                  else ptx::umma_bf16(d_tmem, da, db, IDESC, (kb | j | k) != 0);
+                }
+              }
             }
             if (PAIR) {  // release the stage / publish the accumulator in both CTAs
               ptx::umma_commit_pair(&empty[s]);
-              if (kb == g.k_blocks - 1) ptx::umma_commit_pair(&tfull[acc]);
+              if (kb + KSUB >= g.k_blocks) ptx::umma_commit_pair(&tfull[acc]);
             } else {
               ptx::umma_commit(&empty[s]);
-              if (kb == g.k_blocks - 1) ptx::umma_commit(&tfull[acc]);
+              if (kb + KSUB >= g.k_blocks) ptx::umma_commit(&tfull[acc]);
             }
           }
           __syncwarp();
