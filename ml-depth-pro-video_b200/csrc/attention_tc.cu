@@ -641,7 +641,11 @@ static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int 
 
 // DEPTHPRO_ATTN_EXP selects a variant (list at the top of this file); DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams'
 // exp phases overlap freely (slower).
-static std::atomic<int> g_expv{-1}, g_pingpong{1};
+static std::atomic<int> g_expv{-1}, g_pingpong{1}, g_attn_sm_limit{0};
+void attention_tc_set_sm_limit(int sms) {  // experiment knob: at most this many CTAs (= SMs); 0 = all
+  g_attn_sm_limit = sms;
+  bump_config_epoch();
+}
 
 constexpr int ATTN_EXP_DEFAULT = 13;  // measured on B200 (profiles/r2_attention_variants.json)
 static bool variant_compiled(int v) { return v == 0 || v == 5 || v == 12 || v == 13; }
@@ -676,6 +680,8 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
   const CUtensorMap tmo = get_tmap_bf16(out, 3, od, os, ob);
   int ctas = (nseq * NH + 1) / 2;  // two streams per CTA, one (sequence, head) unit at a time each
   if (ctas > sms) ctas = sms;
+  const int lim = g_attn_sm_limit.load();
+  if (lim > 0 && ctas > lim) ctas = lim;
   switch (expv) {
     case 0: launch_attention<0>(tm, tmo, nseq, ctas, pingpong, s); break;
     case 5: launch_attention<5>(tm, tmo, nseq, ctas, pingpong, s); break;

@@ -1290,6 +1290,10 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   // 0x400: L2 persistence of the fp32 residual stream on, set-aside = `iters >> 16` MB (0 -> 96); 0x800: off
   if (kind & 0x400) gemm_tc_set_l2_persist((iters >> 16) ? (iters >> 16) : 96);
   if (kind & 0x800) gemm_tc_set_l2_persist(0);
+  // 0x4000 / 0x8000 (sticky): GEMM / attention launches use at most `iters >> 16` SMs (0 = all) -- the SM-partition
+  // experiment of DESIGN.md §9.6
+  if (kind & 0x4000) gemm_tc_set_sm_limit(iters >> 16);
+  if (kind & 0x8000) attention_tc_set_sm_limit(iters >> 16);
   if (kind & 0x1000) hbm_v2_set(1);  // 0x1000 / 0x2000: opt-in second-generation HBM kernels on / off
   if (kind & 0x2000) hbm_v2_set(0);
   iters &= 0xFFFF;
@@ -1306,7 +1310,7 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   // B200, a GEMM on zero-filled operands runs at the full 1965 MHz (913 W), the same kernel on real data is
   // power-capped to ~1.5 GHz -- zeros overstate the sustained rate by ~40 %.
   static const bool zeros = [] { const char* e = getenv("DEPTHPRO_BENCH_DATA"); return e && std::string(e) == "zeros"; }();
-  const bool tensor_kind = kind <= 4 || (kind >= 11 && kind <= 14);
+  const bool tensor_kind = kind <= 4 || (kind >= 11 && kind <= 14) || kind == 20 || kind == 21;
   auto B = [&](size_t bytes) {
     void* p = dalloc(bytes);
     if (tensor_kind && !zeros && bytes >= 2) fill_random_bf16(p, bytes, 0x9e3779b9u + static_cast<unsigned>(bufs.size()), s);
@@ -1385,6 +1389,51 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
       float* mm = (float*)B(colorize_scratch_bytes());
       run = [&, depth, lut, out, mm] { dp::colorize(depth, M, N, lut, out, mm, NAN, NAN, s); };
     }
+  } else if (kind == 20 || kind == 21) {
+    // SM-partition experiment: the GEMMs of one ViT layer for M rows (qkv, proj, fc1 + GELU, fc2; plain epilogues) and the
+    // attention of N sequences.  kind 20: one after the other on one stream; kind 21: the GEMM chain on one stream, the
+    // attention on a second one (so they can share the chip under the SM limits set with 0x4000 / 0x8000).
+    static cudaStream_t s2 = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (!s2) {
+      DP_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      DP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      DP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    static cudaStream_t s1 = nullptr;
+    if (!s1) DP_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    s = s1;
+    bf16* x = (bf16*)B((size_t)M * EMB * 2);
+    bf16* q = (bf16*)B((size_t)M * 3 * EMB * 2);
+    bf16* hdn = (bf16*)B((size_t)M * 4 * EMB * 2);
+    bf16* aq = (bf16*)B((size_t)N * SEQ * 3 * EMB * 2);
+    bf16* ao = (bf16*)B((size_t)N * SEQ * EMB * 2);
+    void* w_qkv = B((size_t)3 * EMB * EMB * 2);
+    void* w_proj = B((size_t)EMB * EMB * 2);
+    void* w_fc1 = B((size_t)4 * EMB * EMB * 2);
+    void* w_fc2 = B((size_t)4 * EMB * EMB * 2);
+    float* bias = (float*)B((size_t)4 * EMB * 4);
+    auto g1 = [=](const void* A, int Kk, const void* Wt, int Nn, void* out, int act) {
+      GemmOp o;
+      o.M = M, o.N = Nn, o.K = Kk, o.lda = Kk, o.A = A, o.Wt = Wt, o.bias = bias, o.act = act, o.out = out, o.ldo = Nn;
+      gemm_tc(o, s1);
+    };
+    const bool conc = kind == 21;
+    run = [=] {
+      if (conc) {
+        DP_CUDA(cudaEventRecord(ev_fork, s1));
+        DP_CUDA(cudaStreamWaitEvent(s2, ev_fork, 0));
+        attention_bf16_tc(aq, ao, N, s2);
+        DP_CUDA(cudaEventRecord(ev_join, s2));
+      } else {
+        attention_bf16_tc(aq, ao, N, s1);
+      }
+      g1(x, EMB, w_qkv, 3 * EMB, q, ACT_NONE);
+      g1(x, EMB, w_proj, EMB, x, ACT_NONE);
+      g1(x, EMB, w_fc1, 4 * EMB, hdn, ACT_GELU);
+      g1(hdn, 4 * EMB, w_fc2, EMB, x, ACT_NONE);
+      if (conc) DP_CUDA(cudaStreamWaitEvent(s1, ev_join, 0));
+    };
   } else {
     DP_CHECK(false, "kernel_bench: unknown kind");
   }

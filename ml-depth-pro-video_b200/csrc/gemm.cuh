@@ -10,6 +10,7 @@ void gemm_simt(const GemmOp& op, cudaStream_t stream);
 void gemm_tc(const GemmOp& op, cudaStream_t stream);
 void tmap_cache_clear();
 void gemm_tc_set_res_prefetch(int on);
+void gemm_tc_set_sm_limit(int sms);      // experiment knob: GEMM / conv launches use at most this many SMs (0 = all)
 void gemm_tc_set_l2_persist(int mb);     // A/B switch: L2 set-aside (MB) that keeps the fp32 residual stream resident; 0 = off  // A/B switch of the fp32-residual forms' L2 prefetch (gemm_tc.cu)
 
 inline void gemm(int prec, const GemmOp& op, cudaStream_t stream) {

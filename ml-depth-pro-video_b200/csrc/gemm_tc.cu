@@ -1147,6 +1147,8 @@ static size_t l2_persist_bytes() {
 }
 static size_t l2_window_max() { return g_l2_window; }
 
+static std::atomic<int> g_sm_limit{0};
+
 template <int BN, int CL, int EPI>
 void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const WeightMaps& tmW,
             cudaStream_t stream) {
@@ -1157,7 +1159,8 @@ void launch(const GemmOp& op, const TileGeom& g, const CUtensorMap& tmA, const W
     DP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   }
   const int units = g.m_units * g.n_tiles;
-  const int max_clusters = num_sms() / CL;
+  const int lim = g_sm_limit.load();  // experiment knob (gemm_tc_set_sm_limit): run on at most this many SMs
+  const int max_clusters = (lim > 0 && lim < num_sms() ? lim : num_sms()) / CL;
   const int clusters = units < max_clusters ? units : max_clusters;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CL);
@@ -1226,6 +1229,10 @@ CUtensorMap get_tmap_2d_bf16(const void* ptr, uint64_t cols, uint64_t rows, uint
 static std::atomic<int> g_res_prefetch{-1};
 void gemm_tc_set_res_prefetch(int on) {
   g_res_prefetch = on != 0;
+  bump_config_epoch();
+}
+void gemm_tc_set_sm_limit(int sms) {
+  g_sm_limit = sms;
   bump_config_epoch();
 }
 void gemm_tc_set_l2_persist(int mb) {
