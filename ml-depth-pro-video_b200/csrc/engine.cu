@@ -1291,7 +1291,7 @@ float Engine::kernel_bench(int kind, int M, int N, int K, int iters) {
   if (kind & 0x400) gemm_tc_set_l2_persist((iters >> 16) ? (iters >> 16) : 96);
   if (kind & 0x800) gemm_tc_set_l2_persist(0);
   // 0x4000 / 0x8000 (sticky): GEMM / attention launches use at most `iters >> 16` SMs (0 = all) -- the SM-partition
-  // experiment of DESIGN.md §9.6
+  // experiment of DESIGN.md §9.5
   if (kind & 0x4000) gemm_tc_set_sm_limit(iters >> 16);
   if (kind & 0x8000) attention_tc_set_sm_limit(iters >> 16);
   if (kind & 0x1000) hbm_v2_set(1);  // 0x1000 / 0x2000: opt-in second-generation HBM kernels on / off

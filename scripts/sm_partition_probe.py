@@ -1,4 +1,4 @@
-"""SM-partition experiment (DESIGN.md §9.6): the frame is power-capped, the attention kernel latency-bound.  Could a ViT
+"""SM-partition experiment (DESIGN.md §9.5): the frame is power-capped, the attention kernel latency-bound.  Could a ViT
 layer's GEMMs (on part of the SMs) and the attention of the other half of the batch (on the rest) share the chip?
   1. sustained fc1 / qkv throughput when the GEMM may use only L of the 148 SMs (is it power- or SM-bound?);
   2. one layer's GEMM chain + one attention launch, serial on the whole chip (kind 20) vs concurrent on two streams with
