@@ -185,7 +185,7 @@ __device__ unsigned long long g_attn_rescales;
 template <int EXPV>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, int nseq,
-                    int pingpong) {
+                    int pingpong, int reverse) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -246,7 +246,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     if ((warp & 1) == 0) {
       // ---------------------------------------------------------------- TMA producer
       int T = 0;  // query tiles this stream has started
-      for (int u = slot; u < n_units; u += n_slots) {
+      for (int uu = slot; uu < n_units; uu += n_slots) {
+        const int u = reverse ? n_units - 1 - uu : uu;  // (sequence, head) units from the last to the first
         const int h = u % NH, row0 = (u / NH) * SEQ;
         for (int qt = 0; qt < NQT; ++qt, ++T) {
           ptx::mbar_wait(q_empty, (T & 1) ^ 1);
@@ -382,7 +383,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const int bar_mine = 1 + q + 4 * sidx, bar_peer = 1 + q + 4 * (sidx ^ 1);
     int T = 0;
     PROF_DECL
-    for (int u = slot; u < n_units; u += n_slots) {
+    for (int uu = slot; uu < n_units; uu += n_slots) {
+      const int u = reverse ? n_units - 1 - uu : uu;
       const int h = u % NH, seq = u / NH;
       for (int qt = 0; qt < NQT; ++qt, ++T) {
         float m_ref = -INFINITY;  // reference maximum the exponentials (and O, l) are relative to
@@ -629,14 +631,15 @@ unsigned long long attention_tc_rescale_count(bool reset) {
 }
 
 template <int EXPV>
-static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int nseq, int ctas, int pingpong, cudaStream_t s) {
+static void launch_attention(const CUtensorMap& tm, const CUtensorMap& tmo, int nseq, int ctas, int pingpong, int reverse,
+                             cudaStream_t s) {
   constexpr uint32_t SMEM = SMEM_BYTES;
   static_assert(SMEM <= 232448, "more than 227 KB of shared memory");
   static std::atomic<unsigned long long> configured{0};
   if (first_use_on_device(configured)) {
     DP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<EXPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   }
-  launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM, s, tm, tmo, nseq, pingpong);
+  launch_pdl(attention_tc_kernel<EXPV>, dim3(ctas), dim3(THREADS), SMEM, s, tm, tmo, nseq, pingpong, reverse);
 }
 
 // DEPTHPRO_ATTN_EXP selects a variant (list at the top of this file); DEPTHPRO_ATTN_PINGPONG = 0 lets the two streams'
@@ -660,7 +663,7 @@ void attention_tc_set_variant(int expv, int pingpong) {
   g_expv = expv, g_pingpong = pingpong != 0;
 }
 
-void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
+void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s, int reverse) {
   static const int sms = [] {
     int dev, v;
     DP_CUDA(cudaGetDevice(&dev));
@@ -683,10 +686,10 @@ void attention_bf16_tc(const bf16* qkv, bf16* out, int nseq, cudaStream_t s) {
   const int lim = g_attn_sm_limit.load();
   if (lim > 0 && ctas > lim) ctas = lim;
   switch (expv) {
-    case 0: launch_attention<0>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 5: launch_attention<5>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 12: launch_attention<12>(tm, tmo, nseq, ctas, pingpong, s); break;
-    case 13: launch_attention<13>(tm, tmo, nseq, ctas, pingpong, s); break;
+    case 0: launch_attention<0>(tm, tmo, nseq, ctas, pingpong, reverse, s); break;
+    case 5: launch_attention<5>(tm, tmo, nseq, ctas, pingpong, reverse, s); break;
+    case 12: launch_attention<12>(tm, tmo, nseq, ctas, pingpong, reverse, s); break;
+    case 13: launch_attention<13>(tm, tmo, nseq, ctas, pingpong, reverse, s); break;
     default: throw std::runtime_error("attention variant not compiled in");
   }
   DP_LAUNCH_CHECK();

@@ -238,6 +238,10 @@ struct GemmOp {
   //    x = hi + lo, hi = round16(x) in `ln_xb` (the consumer's operand, as above), lo = round16(x - hi) in `ln_xlo`,
   //    both updated in place -- 8 B of traffic per element instead of 10.
   void* ln_xlo = nullptr;
+  // Tile order.  The L2 (126 MB) still holds the END of what the previous kernel wrote: a consumer that walks its
+  // m-units from the last to the first finds its first operands there instead of in HBM (Engine::run_vits alternates
+  // the direction from kernel to kernel).  Results do not depend on the order.
+  int reverse = 0;
   // groups
   int ngroups = 1;
   GemmGroup grp[3];

@@ -237,6 +237,10 @@ Engine::Engine(int device, int prec, int max_batch, int fov_mode)
   ln_fuse_ = prec_ == BF16 && !(lf != nullptr && lf[0] == '0');
   // the ViT residual stream as a (hi, lo) pair of 16-bit arrays (common.cuh GemmOp::ln_xlo) instead of fp32 + a 16-bit
   // copy; needs the folded LayerNorm.  "0" keeps the fp32 stream (A/B, debugging)
+  // "0": every kernel walks its tiles first to last; "1": alternating direction in the ViT only; default: ViT + decoder
+  const char* sp = getenv("DEPTHPRO_SERPENTINE");
+  serpentine_ = prec_ == BF16 && !(sp != nullptr && sp[0] == '0');
+  serpentine_dec_ = serpentine_ && !(sp != nullptr && sp[0] == '1');
   const char* hf = getenv("DEPTHPRO_HEAD0_FUSE");  // "0": keep fusions.0.out_conv as its own 1x1 launch (A/B, debugging)
   head0_fused_ = prec_ == BF16 && !(hf != nullptr && hf[0] == '0');
   const char* rp = getenv("DEPTHPRO_RES_PAIR");
@@ -624,6 +628,14 @@ void Engine::run_vits(int B, cudaStream_t s) {
   const bool pair = fuse && res_pair_;
   bf16* xlo = pair ? (bf16*)xlo_ : nullptr;
   if (fuse) ln_stats_cast(resid, (bf16*)xn, ln_stats_, M, s, xlo);
+  // Serpentine tile order (GemmOp::reverse): every kernel of the chain walks its rows in the direction opposite to its
+  // producer's, so that it starts on what the L2 still holds.  The first consumer follows an ascending elementwise pass.
+  int rev = serpentine_ ? 1 : 0;
+  auto next_dir = [&]() {
+    const int r = rev;
+    if (serpentine_) rev ^= 1;
+    return r;
+  };
   for (int i = 0; i < 24; ++i) {
     NvtxRange r_blk("vit.block");
     if (!fuse) {
@@ -634,6 +646,7 @@ void Engine::run_vits(int B, cudaStream_t s) {
     {
       GemmOp op;
       op.N = 3 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.out = qkv, op.ldo = 3 * EMB;
+      op.reverse = next_dir();
       grouped(op, SEQ, false);
       for (int g = 0; g < NG; ++g) op.grp[g].Wt = vw[g]->blk[i].qkv_w, op.grp[g].bias = vw[g]->blk[i].qkv_b;
       if (fuse) {
@@ -646,7 +659,7 @@ void Engine::run_vits(int B, cudaStream_t s) {
       ProfScope ps(s, KC_ATTENTION, 4.0 * SEQ * SEQ * 64 * 16 * nseq);
       if (prec_ == BF16) {
         if (attn_legacy_) attention_bf16((const bf16*)qkv, (bf16*)attn, nseq, s);
-        else attention_bf16_tc((const bf16*)qkv, (bf16*)attn, nseq, s);
+        else attention_bf16_tc((const bf16*)qkv, (bf16*)attn, nseq, s, next_dir());
       } else {
         attention_f32((const float*)qkv, (float*)attn, nseq, s);
       }
@@ -654,6 +667,7 @@ void Engine::run_vits(int B, cudaStream_t s) {
     {
       GemmOp op;
       op.N = EMB, op.K = EMB, op.A = attn, op.lda = EMB, op.ldo = EMB;
+      op.reverse = next_dir();
       if (!pair) op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1;
       grouped(op, SEQ, false);
       for (int g = 0; g < NG; ++g)
@@ -669,6 +683,7 @@ void Engine::run_vits(int B, cudaStream_t s) {
     {
       GemmOp op;
       op.N = 4 * EMB, op.K = EMB, op.A = xn, op.lda = EMB, op.act = ACT_GELU, op.out = hid, op.ldo = 4 * EMB;
+      op.reverse = next_dir();
       grouped(op, SEQ, false);
       for (int g = 0; g < NG; ++g) op.grp[g].Wt = vw[g]->blk[i].fc1_w, op.grp[g].bias = vw[g]->blk[i].fc1_b;
       if (fuse) {
@@ -680,6 +695,7 @@ void Engine::run_vits(int B, cudaStream_t s) {
     {
       GemmOp op;
       op.N = EMB, op.K = 4 * EMB, op.A = hid, op.lda = 4 * EMB, op.ldo = EMB;
+      op.reverse = next_dir();
       if (!pair) op.res = resid, op.res_f32 = 1, op.ldres = EMB, op.out = resid, op.out_f32 = 1;
       grouped(op, SEQ, false);
       for (int g = 0; g < NG; ++g)
@@ -760,9 +776,18 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
       DP_CUDA(cudaStreamWaitEvent(s, ev_side_[i], 0));
     }
   };
+  // Serpentine tile order along the main chain (GemmOp::reverse, see run_vits): each launch on `s` walks its tiles in
+  // the direction opposite to the previous one's.
+  int dec_dir = 0;
+  auto main_dir = [&](cudaStream_t st) {
+    if (st != s || !serpentine_dec_) return 0;
+    dec_dir ^= 1;
+    return dec_dir;
+  };
   auto conv1x1 = [&](cudaStream_t st, const void* in, int S, int Cin, const std::string& wname, int Cout, void* out,
                      const float* bias) {
     GemmOp op;
+    op.reverse = main_dir(st);
     op.M = S * S, op.N = Cout, op.K = Cin, op.A = in, op.lda = Cin, op.Wt = W(wname), op.bias = bias;
     op.out = out, op.ldo = Cout;
     gemm(prec_, op, st);
@@ -771,6 +796,7 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
   auto convT = [&](cudaStream_t st, const void* in, int S, int Cin, const std::string& wname, int Cout, void* out, int ldo,
                    int col_off, const float* bias, void* out_relu) {
     GemmOp op;
+    op.reverse = main_dir(st);
     op.M = S * S, op.N = 4 * Cout, op.K = Cin, op.A = in, op.lda = Cin, op.Wt = W(wname);
     op.bias = bias, op.bias_mod = bias ? Cout : 0;
     op.B = 1, op.H = S, op.W = S, op.cout = Cout, op.out_mode = O_CONVT2X2;
@@ -780,6 +806,7 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
   auto conv3x3 = [&](cudaStream_t st, const void* in, int S, int Cin, const std::string& wname, int Cout, const float* bias,
                      int act, const void* res, const void* res2, void* out, void* out_relu) {
     GemmOp op;
+    op.reverse = main_dir(st);
     op.M = S * S, op.N = Cout, op.K = 9 * Cin, op.A = in, op.a_mode = A_CONV3X3, op.B = 1, op.H = S, op.W = S, op.C = Cin;
     op.Wt = W(wname), op.bias = bias, op.act = act, op.res = res, op.res2 = res2, op.ldres = Cout;
     op.out = out, op.out_relu = out_relu, op.ldo = Cout;
@@ -891,6 +918,7 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
     GemmOp op;
     op.M = 768 * 768, op.N = 128, op.K = 9 * 256, op.A = x2_, op.a_mode = A_CONV3X3, op.B = 1, op.H = 768, op.W = 768, op.C = 256;
     op.Wt = head0_wc_, op.bias = head0_cb_ + 9 * 128, op.border_cb = head0_cb_, op.out = h0_, op.ldo = 128;
+    op.reverse = main_dir(s);
     gemm(prec_, op, s);
   } else {
     conv3x3(s, feat_[0], 768, 256, "head.0.weight", 128, F("head.0.bias"), ACT_NONE, nullptr, nullptr, h0_, nullptr);
@@ -902,6 +930,7 @@ void Engine::decode_frame(int f, float* canon, float* fov_deg, cudaStream_t s) {
     op.M = 768 * 768, op.N = 128, op.K = 9 * 128, op.A = h0_, op.a_mode = A_CONV3X3, op.B = 1, op.H = 768, op.W = 768, op.C = 128;
     op.Wt = head_wc_, op.head_cb = head_cb_, op.out = canon, op.out_f32 = 1, op.out_mode = O_HEAD_FUSED;
     op.dot_w = F("head.4.weight"), op.dot_b = F("head.4.bias");
+    op.reverse = main_dir(s);
     gemm(prec_, op, s);
   } else {
     convT(s, h0_, 768, 128, "head.1.weight", 128, h1_, 128, 0, F("head.1.bias"), nullptr);

@@ -122,6 +122,8 @@ class Engine {
   void* head0_wc_ = nullptr;   // composed fusions.0.out_conv o head.0 weights (bf16 mode), [128][9][256]
   float* head0_cb_ = nullptr;  // [9][128] per-tap share of out_conv's bias, then [128] the interior bias
   bool head0_fused_ = false;   // DEPTHPRO_HEAD0_FUSE=0 disables
+  bool serpentine_dec_ = false;  // ... and the decoder's main chain (DEPTHPRO_SERPENTINE=1: ViT only)
+  bool serpentine_ = false;    // ViT kernels alternate their tile direction (GemmOp::reverse); DEPTHPRO_SERPENTINE=0 disables
   void *fovlin_, *fov_a_, *fov_b_, *fov_c_, *fovcol_;
   int last_B_ = 0;
   // host-call staging

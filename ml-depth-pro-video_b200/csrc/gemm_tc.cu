@@ -68,6 +68,7 @@ struct TileGeom {
   int tiles_in_group[3]; // real m-tiles per group (tiles beyond are padding: loaded, not stored)
   int tma_out;           // 1: bf16 row-major output goes smem -> TMA store (full-line writes)
   int res_prefetch;      // 1: fp32-residual forms: the producer warp pulls each tile's residual rows into L2
+  int reverse;           // 1: walk the tiles from the last m-unit to the first (GemmOp::reverse)
 };
 struct WeightMaps {
   CUtensorMap b[3];      // one weight tensor map per group
@@ -498,7 +499,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int s = 0;
       uint32_t ph = 0;
       for (int t = cid; t < total_units; t += ncl) {
-        const int nt = t % g.n_tiles, mu = t / g.n_tiles;
+        const int tt = g.reverse ? total_units - 1 - t : t;
+        const int nt = tt % g.n_tiles, mu = tt / g.n_tiles;
         int b = 0, y0 = 0, x0 = 0, a_row = 0;
         const CUtensorMap* tmB = &tmW.b[0];
         if (op.a_mode == A_CONV3X3) {
@@ -649,7 +651,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = cid; t < total_units; t += ncl, ++it) {
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
-      const int nt = t % g.n_tiles, mu = t / g.n_tiles;
+      const int tt = g.reverse ? total_units - 1 - t : t;
+      const int nt = tt % g.n_tiles, mu = tt / g.n_tiles;
       long long m, m_a = 0;  // output row / A row of this thread
       bool valid;
       int gi = 0;
@@ -1263,6 +1266,7 @@ void gemm_tc(const GemmOp& op_in, cudaStream_t stream) {
   DP_CHECK(op.ngroups >= 1 && op.ngroups <= 3, "gemm_tc: 1..3 groups");
 
   TileGeom g{};
+  g.reverse = op.reverse ? 1 : 0;
   g.n_tiles = op.N / bn;
   g.k_blocks = op.K / BK;
   // CTA pairs (cluster of 2 along M) share every weight tile through TMA multicast: the GEMMs are

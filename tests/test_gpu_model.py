@@ -307,6 +307,21 @@ def test_bf16_head0_composed_with_decoder_out_conv(model_bf16, oracle_run, monke
     del plain_model
 
 
+def test_bf16_serpentine_tile_order_is_bit_identical(model_bf16, oracle_run, monkeypatch):
+    """Default: the ViT kernels alternate their tile direction (`GemmOp::reverse`, attention units likewise) so that a
+    consumer starts on what the L2 still holds of its producer's output.  Tiles are independent and the LayerNorm
+    partial sums are added in a fixed slot order, so DEPTHPRO_SERPENTINE=0 (read at engine creation) must give the same
+    bits."""
+    x, _, _ = oracle_run
+    a = model_bf16.infer(x.to(DEV))
+    monkeypatch.setenv("DEPTHPRO_SERPENTINE", "0")
+    plain_model = depth_pro.DepthPro(device=DEV, precision=torch.bfloat16).init_weights("stress", 1234).eval()
+    b = plain_model.infer(x.to(DEV))
+    monkeypatch.delenv("DEPTHPRO_SERPENTINE")
+    assert torch.equal(a["depth"], b["depth"]) and float(a["focallength_px"]) == float(b["focallength_px"])
+    del plain_model
+
+
 def test_bf16_pair_residual_stream_matches_fp32_stream(model_bf16, oracle_run, monkeypatch):
     """Default: the ViT residual stream is a (hi, lo) pair of 16-bit arrays whose hi half is the next GEMM's operand
     (csrc/common.cuh GemmOp::ln_xlo).  DEPTHPRO_RES_PAIR=0 (read at engine creation) keeps the fp32 stream + separate
