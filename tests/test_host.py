@@ -146,3 +146,57 @@ def test_environment_switches_are_documented():
     assert used, "no switches found: the patterns above no longer match the sources"
     assert used - documented == set(), f"undocumented switches: {sorted(used - documented)}"
     assert documented - used == set(), f"documented but unused switches: {sorted(documented - used)}"
+
+
+def test_weight_composition_algebra_out_conv_into_head0():
+    """The algebra behind `compose_1x1_conv3x3` + `GemmOp::border_cb` (csrc/kernels.cu, gemm_tc.cu), restated in torch on
+    the CPU: a 1x1 conv with bias (decoder.fusions.0.out_conv, decoder.py:178) followed by a zero-padded 3x3 conv with
+    bias (head.0, depth_pro.py:183-185) equals ONE 3x3 conv with weights w3 . wo, the interior bias b3 + sum over all
+    nine taps of w3[:, :, tap] . bo, minus -- on the outermost pixel ring only -- the share of every tap that falls
+    into the padding (the 1x1's bias does not exist there)."""
+    g = torch.Generator().manual_seed(3)
+    C, O, H, W = 8, 6, 7, 9
+    x = torch.randn(1, C, H, W, generator=g, dtype=torch.float64)
+    wo, bo = torch.randn(C, C, 1, 1, generator=g, dtype=torch.float64), torch.randn(C, generator=g, dtype=torch.float64)
+    w3, b3 = torch.randn(O, C, 3, 3, generator=g, dtype=torch.float64), torch.randn(O, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.conv2d(x, wo, bo), w3, b3, padding=1)
+    wc = torch.einsum("ockl,ci->oikl", w3, wo[:, :, 0, 0])            # [O][i][ky][kx]
+    cb = torch.einsum("ockl,c->klo", w3, bo).reshape(9, O)              # per-tap share of bo
+    out = torch.nn.functional.conv2d(x, wc, b3 + cb.sum(0), padding=1)
+    for y in range(H):
+        for xx in range(W):
+            for ky in range(3):
+                for kx in range(3):
+                    if not (0 <= y + ky - 1 < H and 0 <= xx + kx - 1 < W):
+                        out[0, :, y, xx] -= cb[ky * 3 + kx]
+    assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
+    interior = torch.nn.functional.conv2d(x, wc, b3 + cb.sum(0), padding=1)
+    assert torch.allclose(interior[..., 1:-1, 1:-1], ref[..., 1:-1, 1:-1], rtol=1e-12, atol=1e-12)
+    assert not torch.allclose(interior, ref)                           # ... and the ring really needs the correction
+
+
+def test_pair_residual_stream_arithmetic():
+    """The (hi, lo) form of the ViT residual stream (csrc/common.cuh GemmOp::ln_xlo), restated in torch on the CPU:
+    hi = bf16(x), lo = bf16(x - hi) carries x to 2^-16 of its value (x - hi is exact in fp32: at most 16 significant bits
+    are left, bf16 keeps 8 of them), hi alone is exactly the operand the next GEMM would have read from a separate copy,
+    and 48 consecutive updates (a ViT-L's 24 proj + 24 fc2) stay within 48 * 2^-17 of the fp32 stream."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(4096, generator=g) * torch.logspace(-3, 3, 4096)
+
+    def split(v):
+        hi = v.bfloat16()
+        return hi, (v - hi.float()).bfloat16()
+
+    hi, lo = split(x)
+    assert torch.equal(hi, x.bfloat16())
+    back = hi.float() + lo.float()
+    assert float(((back - x).abs() / x.abs()).max()) <= 2.0 ** -16
+    x32 = x.clone()
+    scale = x.abs()                                    # largest magnitude the element has had so far
+    for i in range(48):
+        d = torch.randn(4096, generator=g) * 0.1 * x.abs()
+        x32 = x32 + d
+        hi, lo = split(hi.float() + lo.float() + d)
+        scale = torch.maximum(scale, x32.abs())
+    # every split rounds by at most 2^-17 of the value AT THAT TIME (half an ulp of lo's 8-bit mantissa)
+    assert float((((hi.float() + lo.float()) - x32).abs() / scale).max()) <= 48 * 2.0 ** -17
